@@ -1,0 +1,180 @@
+"""Generates the golden vectors tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_harness.py) on seeded inputs.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The reference's own tests hold no known-answer vectors for this path, so these
+files are what pins the oracle (tests/test_oracle_vs_golden.py) and, through it, the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle.ref_harness import import_reference  # noqa: E402
+
+import_reference()
+from torchdrivesim.simulator import Simulator, TorchDriveConfig, CollisionMetric  # noqa: E402
+from torchdrivesim.rendering import CV2RendererConfig  # noqa: E402
+from torchdrivesim.kinematic import KinematicBicycle, BicycleNoReversing  # noqa: E402
+from torchdrivesim.map import find_map_config, traffic_controls_from_map_config  # noqa: E402
+from torchdrivesim.infractions import (collision_detection_with_discs, iou_differentiable,  # noqa: E402
+                                       offroad_infraction_loss)
+from torchdrivesim.utils import Resolution  # noqa: E402
+from torchdrivesim.mesh import BirdviewMesh  # noqa: E402
+
+VEH = (4.97, 2.04, 1.96)   # behavior/heuristic.py:11-13
+PED = (1.5, 1.5)           # examples/imitation_learning.py:80-81
+
+
+def road_points(mesh: BirdviewMesh, n: int, gen: torch.Generator) -> torch.Tensor:
+    road = mesh.separate_by_category()["road"].verts[0]
+    return road[torch.randint(0, road.shape[0], (n,), generator=gen)]
+
+
+def make_sim(map_name, B, A, gen, types=None, type_names=None, with_lights=True, present=None,
+             metric=CollisionMetric.discs, jitter=0.0, npc=0):
+    cfgm = find_map_config(map_name)
+    mesh = cfgm.road_mesh
+    xy = road_points(mesh, B * A, gen).reshape(B, A, 2) + jitter * torch.randn(B, A, 2, generator=gen)
+    psi = torch.rand(B, A, 1, generator=gen) * 2 * np.pi
+    v = torch.rand(B, A, 1, generator=gen) * 5
+    state = torch.cat([xy, psi, v], -1)
+    size = torch.tensor(VEH[:2]).expand(B, A, 2).clone()
+    lr = torch.full((B, A), VEH[2])
+    if types is not None:
+        size = torch.where(types.unsqueeze(-1) == 1, torch.tensor(PED), size)
+    if present is None:
+        present = torch.ones(B, A, dtype=torch.bool)
+    km = KinematicBicycle(left_handed=True)
+    km.set_params(lr=lr)
+    km.set_state(state)
+    tc = None
+    if with_lights:
+        tc = {k: v_.extend(B) for k, v_ in traffic_controls_from_map_config(cfgm).items()}
+        tl = tc["traffic_light"]
+        tl.set_state(torch.randint(0, 3, tl.state.shape, generator=gen))
+    cfg = TorchDriveConfig(left_handed_coordinates=True, collision_metric=metric,
+                           renderer=CV2RendererConfig(left_handed_coordinates=True))
+    sim = Simulator(cfg=cfg, road_mesh=mesh.expand(B), kinematic_model=km, agent_size=size,
+                    initial_present_mask=present, traffic_controls=tc, agent_types=types,
+                    agent_type_names=type_names)
+    return sim, cfgm
+
+
+def golden_render():
+    out = {}
+    gen = torch.Generator().manual_seed(101)
+    cases = []
+    # (name, map, B, A, res, fov, absent pattern, mixed types)
+    cases.append(("town01_64", "carla_Town01", 2, 6, 64, 35.0, None, False))
+    cases.append(("town01_absent0", "carla_Town01", 1, 5, 64, 35.0, [0, 3], False))
+    cases.append(("town02_mixed_128", "carla_Town02", 1, 6, 128, 50.0, [2], True))
+    cases.append(("town01_256", "carla_Town01", 1, 2, 256, 35.0, None, False))
+    for name, mp, B, A, res, fov, absent, mixed in cases:
+        types = names = None
+        if mixed:
+            types = (torch.arange(A) % 3 == 2).long().expand(B, A).clone()
+            names = ["vehicle", "pedestrian"]
+        present = torch.ones(B, A, dtype=torch.bool)
+        if absent:
+            present[:, absent] = False
+        # a tight cluster so that agents see each other
+        sim, cfgm = make_sim(mp, B, A, gen, types=types, type_names=names, present=present)
+        st = sim.get_state().clone()
+        st[:, 1:, :2] = st[:, :1, :2] + 8.0 * torch.randn(B, A - 1, 2, generator=gen)
+        sim.set_state(st)
+        img = sim.render_egocentric(res=Resolution(res, res), fov=fov)       # [B,A,3,H,W]
+        assert float((img - img.round()).abs().max()) == 0.0
+        tl = sim.traffic_controls["traffic_light"]
+        out[name] = dict(map=mp, state=sim.get_state().numpy(), size=sim.get_agent_size().numpy(),
+                         present=present.numpy(), types=(types.numpy() if types is not None else np.zeros((B, A), np.int64)),
+                         type_names=np.array(names or ["vehicle"]), tl_state=tl.state.numpy(),
+                         tl_corners=tl.corners.numpy(), res=res, fov=fov, image=img.numpy().astype(np.uint8))
+        print("render", name, img.shape, "nonzero px", int((img.sum(2) > 0).sum()))
+    flat = {f"{k}/{kk}": vv for k, v in out.items() for kk, vv in v.items()}
+    np.savez_compressed(os.path.join(HERE, "render.npz"), cases=np.array(list(out)), **flat)
+
+
+def golden_kinematic():
+    gen = torch.Generator().manual_seed(202)
+    B, A, T = 3, 7, 12
+    res = {}
+    for name, cls, lh in (("bicycle_rh", KinematicBicycle, False), ("bicycle_lh", KinematicBicycle, True),
+                          ("noreverse_lh", BicycleNoReversing, True)):
+        km = cls(left_handed=lh) if cls is KinematicBicycle else cls(left_handed=lh)
+        state0 = torch.cat([torch.rand(B, A, 2, generator=gen) * 400, torch.rand(B, A, 1, generator=gen) * 6.28 - 3.14,
+                            torch.rand(B, A, 1, generator=gen) * 6 - 1], -1)
+        lr = 1.0 + 2 * torch.rand(B, A, generator=gen)
+        km.set_params(lr=lr)
+        km.set_state(state0)
+        actions = torch.rand(T, B, A, 2, generator=gen) * 2 - 1
+        traj = [state0]
+        for t in range(T):
+            km.step(actions[t])
+            traj.append(km.get_state())
+        res[name] = dict(state0=state0.numpy(), lr=lr.numpy(), actions=actions.numpy(),
+                         traj=torch.stack(traj).numpy(), left_handed=lh)
+    flat = {f"{k}/{kk}": vv for k, v in res.items() for kk, vv in v.items()}
+    np.savez_compressed(os.path.join(HERE, "kinematic.npz"), cases=np.array(list(res)), **flat)
+    print("kinematic", list(res))
+
+
+def golden_collision():
+    gen = torch.Generator().manual_seed(303)
+    B, A = 3, 12
+    present = torch.rand(B, A, generator=gen) > 0.2
+    types = (torch.arange(A) % 4 == 3).long().expand(B, A).clone()
+    sim, _ = make_sim("carla_Town01", B, A, gen, types=types, type_names=["vehicle", "pedestrian"],
+                      with_lights=False, present=present)
+    st = sim.get_state().clone()
+    st[..., :2] = st[:, :1, :2] + 3.5 * torch.randn(B, A, 2, generator=gen)      # dense: many overlaps
+    st[0, 1] = st[0, 0]; st[0, 1, 0] += 0.5                                       # near-coincident pair
+    st[1, 2, :3] = st[1, 3, :3]; st[1, 2, 1] += 2.04                              # parallel side-by-side (argmin tie)
+    sim.set_state(st)
+    coll = sim.compute_collision()
+    size = sim.get_agent_size()
+    box = torch.cat([st[..., :2], size, st[..., 2:3]], -1)
+    n = A
+    pair = collision_detection_with_discs(box.unsqueeze(2).expand(-1, -1, n, -1).reshape(B, A * n, 5),
+                                          box.unsqueeze(1).expand(-1, A, -1, -1).reshape(B, A * n, 5)).reshape(B, A, n)
+    # backward through the aggregate, w.r.t. the state
+    st_g = st.clone().requires_grad_(True)
+    sim.set_state(st_g)
+    sim.compute_collision().sum().backward()
+    # IoU, evaluated by the reference in float64
+    box64 = box.double()
+    iou64 = iou_differentiable(box64.unsqueeze(2).expand(-1, -1, n, -1).reshape(B, A * n, 5),
+                               box64.unsqueeze(1).expand(-1, A, -1, -1).reshape(B, A * n, 5)).reshape(B, A, n)
+    iou32 = iou_differentiable(box.unsqueeze(2).expand(-1, -1, n, -1).reshape(B, A * n, 5).contiguous(),
+                               box.unsqueeze(1).expand(-1, A, -1, -1).reshape(B, A * n, 5).contiguous()).reshape(B, A, n)
+    np.savez_compressed(os.path.join(HERE, "collision.npz"), box=box.numpy(), present=present.numpy(),
+                        discs_pair=pair.numpy(), discs_collision=coll.detach().numpy(),
+                        discs_grad_state=st_g.grad.numpy(), iou64=iou64.numpy(), iou32=iou32.numpy())
+    print("collision: discs nonzero pairs", int((pair > 0).sum()), "iou64 nonzero", int((iou64 > 0).sum()),
+          "fp32 self-iou==1:", float((torch.diagonal(iou32, dim1=1, dim2=2) > 0.999).float().mean()))
+
+
+def golden_offroad():
+    gen = torch.Generator().manual_seed(404)
+    B, A = 1, 24
+    sim, cfgm = make_sim("carla_Town01", B, A, gen, with_lights=False, jitter=6.0)
+    st = sim.get_state().clone()
+    st[0, 0, :2] = torch.tensor([-40.0, -30.0])      # far off the map
+    st[0, 1, :2] = torch.tensor([200.0, 160.0])      # block interior
+    sim.set_state(st)
+    off05 = offroad_infraction_loss(sim.get_state(), sim.get_agent_size(), sim.road_mesh, threshold=0.5,
+                                    use_pytorch3d=False)
+    off0 = offroad_infraction_loss(sim.get_state(), sim.get_agent_size(), sim.road_mesh, threshold=0.0,
+                                   use_pytorch3d=False)
+    np.savez_compressed(os.path.join(HERE, "offroad.npz"), map="carla_Town01", state=st.numpy(),
+                        size=sim.get_agent_size().numpy(), offroad_thr05=off05.numpy(), offroad_thr0=off0.numpy())
+    print("offroad: nonzero", int((off05 > 0).sum()), "of", A, "max", float(off05.max()))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render"]
+    for w in which:
+        globals()["golden_" + w]()
