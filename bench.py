@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the TorchDriveSim per-step hot path on B200 (BASELINE.json metric).
+
+One "step" = kinematic step -> egocentric 64x64 birdview for every agent -> pairwise collisions (discs)
+-> offroad, over one batch of synthetic input: config 2 of BASELINE.json (carla_Town01 standing in for
+the missing Town03 mesh, 1024 environments x 64 agents, bicycle model) PER GPU (weak scaling).
+
+  python bench.py [--gpus N --steps K --warmup W]            our CUDA path  (torchrun for N > 1)
+  python bench.py --impl reference [...]                      the CPU port of the reference (oracle), all host cores
+
+Prints ONE JSON line on rank 0 (see the keys in main()).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAP = "carla_Town01"
+ENVS_PER_GPU = 1024
+AGENTS = 64
+RES = 64
+FOV = 35.0
+VEH = (4.97, 2.04, 1.96)
+BYTES_PER_AGENT_STEP = 12 * RES * RES + 61        # fp32 RGB image + state/action/size/mask/outputs
+METRIC = "agent-env-steps/sec incl. 64x64 BEV render+collisions"
+
+
+def map_npz():
+    return os.path.join(ROOT, "tests", "golden", "maps", f"{MAP}.npz")
+
+
+def synth_inputs(B, A, seed, steps):
+    """Seeded synthetic inputs of SURVEY.md §8(d): on-road positions, psi ~ U[0,2pi), v ~ U[0,5], vehicles."""
+    rng = np.random.default_rng(seed)
+    d = np.load(map_npz())
+    cats = [str(c) for c in d["categories"]]
+    road = d["verts"][d["vert_category"] == cats.index("road")]
+    xy = road[rng.integers(0, road.shape[0], (B, A))]
+    state = np.concatenate([xy, rng.uniform(0, 2 * np.pi, (B, A, 1)), rng.uniform(0, 5, (B, A, 1))], -1).astype(np.float32)
+    size = np.tile(np.array(VEH[:2], np.float32), (B, A, 1))
+    lr = np.full((B, A), VEH[2], np.float32)
+    actions = rng.uniform(-1, 1, (steps, B, A, 2)).astype(np.float32)
+    return state, size, lr, actions
+
+
+# ------------------------------------------------------------------------------------------------ CPU port
+def _cpu_env_step(args):
+    """One environment, one step of the hot path with the oracle (the CPU port of the reference)."""
+    import torch
+    torch.set_num_threads(1)
+    from oracle import collision as OC, kinematic as OK, offroad as OO, raster as OR
+    state, size, lr, action, m = args
+    st = OK.bicycle_step(torch.tensor(state), torch.tensor(action), torch.tensor(lr), 0.1, True).numpy()
+    sc = OR.build_scene(m["verts"], m["faces"], m["face_cat"], st, size, ["vehicle"], None, None)
+    cam_sc = torch.stack([torch.sin(torch.tensor(st[:, 2])), torch.cos(torch.tensor(st[:, 2]))], -1).numpy()
+    chk = 0.0
+    for a in range(st.shape[0]):
+        img, _ = OR.render_camera(sc, st[a, :2], cam_sc[a], RES, FOV)
+        chk += float(img[0, 0, 0])
+    box = torch.cat([torch.tensor(st[:, :2]), torch.tensor(size), torch.tensor(st[:, 2:3])], -1)[None]
+    coll = OC.collision_allpairs(box, box, torch.ones(1, st.shape[0], dtype=torch.bool))
+    off = OO.offroad_loss(st, size, m["verts"], m["faces"], 0.5)
+    return float(coll.sum()) + float(off.sum()) + chk
+
+
+_CPU_MAP = None
+
+
+def _cpu_map():
+    global _CPU_MAP
+    if _CPU_MAP is None:
+        d = np.load(map_npz())
+        cats = [str(c) for c in d["categories"]]
+        _CPU_MAP = dict(verts=d["verts"], faces=d["faces"], face_cat=[cats[i] for i in d["vert_category"][d["faces"][:, 0]]])
+    return _CPU_MAP
+
+
+def _cpu_worker(task):
+    state, size, lr, action = task
+    return _cpu_env_step((state, size, lr, action, _cpu_map()))
+
+
+def cpu_port_throughput(sample_envs, repeats=1, seed=1):
+    """agent-env-steps/s of the oracle on `sample_envs` environments spread over all host cores."""
+    import oracle
+    oracle.build_clib()
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, sample_envs))
+    state, size, lr, actions = synth_inputs(sample_envs, AGENTS, seed, 1)
+    tasks = [(state[b], size[b], lr[b], actions[0, b]) for b in range(sample_envs)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, tasks[:procs])                       # warm-up: page in libs, build caches
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, tasks, chunksize=1)
+            times.append(time.perf_counter() - t0)
+    return sample_envs * AGENTS / min(times), procs, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_envs = max(8, min(2 * cores, 256))
+    import oracle
+    oracle.build_clib()
+    procs = max(1, min(cores, sample_envs))
+    state, size, lr, actions = synth_inputs(sample_envs, AGENTS, 1, 1)
+    tasks = [(state[b], size[b], lr[b], actions[0, b]) for b in range(sample_envs)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_worker, tasks[:procs])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_worker, tasks, chunksize=1)
+        dt = time.perf_counter() - t0
+    value = sample_envs * AGENTS * args.steps / dt
+    sample = f"{sample_envs} of {ENVS_PER_GPU} environments x {AGENTS} agents per step, one process per core"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "agent-env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "agent-env-steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": f"config 2: {MAP} (Town03 mesh is a missing blob), {ENVS_PER_GPU} envs x {AGENTS} agents per GPU, "
+                        f"bicycle, {RES}x{RES} BEV fov {FOV} m, discs collisions + offroad(0.5)",
+            "envs_per_gpu": ENVS_PER_GPU, "agents": AGENTS, "res": RES, "n_gpus": n_gpus,
+            "l2_policy": "each step writes 3.2 GB of images per GPU (>> 126 MB L2), which evicts every input; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torchdrivesim_b200 as tds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback of the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    B, A = ENVS_PER_GPU, AGENTS
+
+    # ---- this rank's shard of independent environments (weak scaling: ENVS_PER_GPU each)
+    state, size, lr, actions = synth_inputs(B, A, 1000 + rank, W + K)
+    town = tds.StaticMap.from_npz(map_npz())
+    km = tds.KinematicBicycle(left_handed=True)
+    km.set_params(lr=torch.tensor(lr, device=dev))
+    km.set_state(torch.tensor(state, device=dev))
+    cfg = tds.TorchDriveConfig(left_handed_coordinates=True)
+    sim = tds.Simulator(town, km, torch.tensor(size, device=dev), torch.ones(B, A, dtype=torch.bool, device=dev), cfg)
+    state0 = torch.tensor(state, device=dev)
+    act_dev = torch.tensor(actions, device=dev)
+    images = torch.empty(B, A, 3, RES, RES, dtype=torch.float32, device=dev)
+    metrics = torch.zeros(4, dtype=torch.float64, device=dev)
+    lib = tds._lib.load()
+
+    def step(action, out_images, ev=None):
+        sim.step(action)
+        if ev is not None:
+            lib.tds_raster_set_timing_events(ev[0].cuda_event, ev[1].cuda_event)
+        img = sim.render_egocentric(out=out_images)
+        if ev is not None:
+            lib.tds_raster_set_timing_events(None, None)
+        coll = sim.compute_collision()
+        off = sim.compute_offroad()
+        return img, coll, off
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for i in range(W):
+        step(act_dev[i], images)
+    sim.set_state(state0.clone())
+    raster_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for e0, e1 in raster_ev:   # create the CUDA events before the timed region
+        e0.record(); e1.record()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        img, coll, off = step(act_dev[W + i], images, raster_ev[i])
+        metrics += torch.stack([coll.sum(), off.sum(), (coll > 0).sum(), (off > 0).sum()]).double()
+    if world > 1:
+        dist.all_reduce(metrics)          # the only collective of the path: aggregate infraction metrics
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    raster_ms = sum(a.elapsed_time(b) for a, b in raster_ev) / K
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * A * K / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: pinned actions in, state/collision/offroad AND the
+    # images out to pinned host memory every step
+    h_act = torch.tensor(actions).pin_memory()
+    h_img = torch.empty(B, A, 3, RES, RES, dtype=torch.float32).pin_memory()
+    h_state = torch.empty(B, A, 4).pin_memory()
+    h_coll = torch.empty(B, A).pin_memory()
+    h_off = torch.empty(B, A).pin_memory()
+
+    def e2e_step(i, to_host_images):
+        a = h_act[i].to(dev, non_blocking=True)
+        sim.step(a)
+        if to_host_images:
+            sim.render_egocentric_to_host(h_img, chunk_envs=128)
+        else:
+            sim.render_egocentric(out=images)
+        h_coll.copy_(sim.compute_collision(), non_blocking=True)
+        h_off.copy_(sim.compute_offroad(), non_blocking=True)
+        h_state.copy_(sim.get_state(), non_blocking=True)
+
+    e2e = {"host_images": float("nan"), "device_images": float("nan")}
+    for name, to_host in (() if args.kernels_only else (("host_images", True), ("device_images", False))):
+        sim.set_state(state0.clone())
+        for i in range(W):
+            e2e_step(i, to_host)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            e2e_step(W + i, to_host)
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e[name] = world * B * A * K / (float(tt.item()) * 1e-3)
+    small_out = (h_state.numel() + h_coll.numel() + h_off.numel()) * 4
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        achieved = B * A * 12 * RES * RES / (raster_ms * 1e-3) / 1e9
+        cpu_val, cpu_procs = float("nan"), 0
+        if not args.kernels_only:
+            cpu_val, cpu_procs, _ = cpu_port_throughput(max(8, min(os.cpu_count() or 1, 128)))
+        line = {
+            "metric": METRIC, "value": value, "unit": "agent-env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e["host_images"], "unit": "agent-env-steps/s", "h2d_bytes_per_step": int(h_act[0].numel() * 4),
+                    "d2h_bytes_per_step": int(h_img.numel() * 4 + small_out),
+                    "note": "public API, pinned host buffers; images delivered to host every step (PCIe-bound)"},
+            "e2e_device_images": {"value": e2e["device_images"], "unit": "agent-env-steps/s",
+                                  "h2d_bytes_per_step": int(h_act[0].numel() * 4), "d2h_bytes_per_step": int(small_out),
+                                  "note": "same, images stay in HBM for a GPU consumer (the reference API returns device tensors)"},
+            "gpu_launches": 5 * K,
+            "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "raster_ms_per_launch": raster_ms, "algorithmic_bytes_per_launch": B * A * 12 * RES * RES,
+                         "step_frac_of_hbm_roofline": value / world * BYTES_PER_AGENT_STEP / 1e9 / peak},
+            "cpu_baseline": {"value": cpu_val, "unit": "agent-env-steps/s", "cores": cpu_procs, "kind": "port",
+                             "sample": f"{max(8, min(os.cpu_count() or 1, 128))} environments x {AGENTS} agents, one step, "
+                                       f"oracle (C + numpy port of the reference path), one process per core"},
+            "infraction_metrics": {"collision_sum": float(metrics[0]), "offroad_sum": float(metrics[1]),
+                                   "colliding_agent_steps": float(metrics[2]), "offroad_agent_steps": float(metrics[3])},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="profiling aid: only the device-resident loop (no e2e legs, no CPU baseline)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+/*
+ * tds_b200.h — C ABI of the B200-native TorchDriveSim hot path (libtds_b200.so).
+ *
+ * The reference (inverted-ai/torchdrivesim 0.2.3) is pure Python: it has no FFI.  Its
+ * "plugin API" for this path is constructor injection into `Simulator`
+ * (torchdrivesim/simulator.py:299-309) plus module-level functions.  Each entry point below
+ * replaces one of those Python call sites; the Python host layer (torchdrivesim_b200/*.py)
+ * binds them with ctypes and mirrors the reference's classes.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory on the current CUDA device, contiguous, in the
+ *     reference's layout and dtype (fp32 state/boxes/images, uint8 masks, int32 indices);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only
+ *     enqueue work: no host synchronisation, CUDA-graph capturable (except tds_map_create);
+ *   - return value 0 = OK, otherwise an error code; tds_last_error() describes the last failure
+ *     on the calling thread.  Data values never raise: NaNs are scrubbed where the reference
+ *     scrubs them (simulator.py:1095-1103, infractions.py:171).
+ *   - ownership: the caller owns all buffers; the library retains only tds_map_t handles.
+ */
+#ifndef TDS_B200_H
+#define TDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDS_OK 0
+#define TDS_ERR_INVALID_ARGUMENT 1
+#define TDS_ERR_CUDA 2
+#define TDS_ERR_UNSUPPORTED 3
+
+#define TDS_MAX_CLASSES 32
+#define TDS_MAX_AGENT_TYPES 8
+#define TDS_MAX_TL_STATES 8
+#define TDS_MAX_MAPS 8
+
+int tds_version(void);
+const char* tds_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Kinematic state transition.  Replaces KinematicBicycle.step (kinematic.py:462-477),
+ * BicycleNoReversing.step (kinematic.py:509-523) and the boolean-mask dispatch of
+ * CompoundKinematicModel.step (kinematic.py:197-201); adds the unicycle the README names.
+ * ---------------------------------------------------------------------------------------- */
+#define TDS_MODEL_BICYCLE 0
+#define TDS_MODEL_BICYCLE_NO_REVERSING 1
+#define TDS_MODEL_UNICYCLE 2
+
+typedef struct {
+    float dt;               /* seconds */
+    float max_acceleration; /* action[0] scale (kinematic.py:415) */
+    float max_steering;     /* action[1] scale for the bicycle, float32(pi/2) by default */
+    float max_yaw_rate;     /* action[1] scale for the unicycle */
+    int32_t left_handed;    /* negate steering / yaw rate (kinematic.py:466-467) */
+} tds_kinematic_params_t;
+
+/* d_state [n,4] (x,y,psi,v), d_action [n,2], d_lr [n], d_model [n] int32 or NULL (then
+ * uniform_model applies to every agent), d_out_state [n,4] (may alias d_state). */
+int tds_kinematic_step_fwd(const float* d_state, const float* d_action, const float* d_lr,
+                           const int32_t* d_model, int32_t uniform_model, int64_t n,
+                           const tds_kinematic_params_t* params, float* d_out_state, void* stream);
+
+/* Backward of the above.  d_grad_out [n,4]; outputs d_grad_state [n,4], d_grad_action [n,2],
+ * d_grad_lr [n] (any may be NULL). */
+int tds_kinematic_step_bwd(const float* d_state, const float* d_action, const float* d_lr,
+                           const int32_t* d_model, int32_t uniform_model, int64_t n,
+                           const tds_kinematic_params_t* params, const float* d_grad_out,
+                           float* d_grad_state, float* d_grad_action, float* d_grad_lr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Collisions.  Boxes are (x, y, length, width, psi).
+ * ---------------------------------------------------------------------------------------- */
+#define TDS_METRIC_DISCS 0 /* infractions.py:503-545 collision_detection_with_discs, 5 discs */
+#define TDS_METRIC_IOU 1   /* infractions.py:307-324 iou_differentiable (fast)              */
+
+/* Element-wise API of the reference functions: d_box1, d_box2 [p,5] -> d_out [p]. */
+int tds_collision_pairwise_fwd(const float* d_box1, const float* d_box2, int64_t p, int32_t metric,
+                               float* d_out, void* stream);
+/* discs only: d_grad_out [p] -> d_grad_box1, d_grad_box2 [p,5] */
+int tds_collision_discs_pairwise_bwd(const float* d_box1, const float* d_box2, int64_t p,
+                                     const float* d_grad_out, float* d_grad_box1, float* d_grad_box2,
+                                     void* stream);
+
+/* Fused Simulator.compute_collision (simulator.py:1161-1194, 1064-1109):
+ *   out[b,i] = sum_j o(ego_i, all_j) m[b,j] - max_j o(ego_i, all_j) m[b,j]
+ * d_ego_box [B,A,5], d_all_box [B,N,5], d_mask [B,N] uint8 (column presence),
+ * d_out [B,A], d_argmax [B,A] int32 or NULL (index of the subtracted maximum, kept for bwd).
+ * ego_is_prefix != 0 declares that ego agent i IS column i (the Simulator's layout); the IoU
+ * metric then defines o(i,i) = 1 exactly (the reference's fp32 self-IoU is numerically chaotic). */
+int tds_collision_allpairs_fwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
+                               int32_t B, int32_t A, int32_t N, int32_t metric, int32_t ego_is_prefix,
+                               float* d_out, int32_t* d_argmax, void* stream);
+/* discs only.  d_grad_ego [B,A,5] is overwritten, d_grad_all [B,N,5] is ACCUMULATED into
+ * (the caller zero-fills it). */
+int tds_collision_discs_allpairs_bwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
+                                     int32_t B, int32_t A, int32_t N, const float* d_grad_out,
+                                     const int32_t* d_argmax, float* d_grad_ego, float* d_grad_all,
+                                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Static map: triangle mesh + uniform grids, built once per map per GPU.  Replaces the
+ * per-camera / per-corner expansion of the mesh (mesh.py:1147-1157, infractions.py:219-226).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tds_map tds_map_t;
+
+/* Host inputs: verts [nv,2] f32, faces [nf,3] i32, face_class [nf] u8 (palette class of the face,
+ * i.e. the category of its first vertex, cv2.py:58).  Cell sizes in metres (<= 0: defaults).
+ * Synchronous (allocates and uploads).  Returns NULL on failure. */
+tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int32_t* h_faces, int32_t nf,
+                          const uint8_t* h_face_class, float raster_cell, float offroad_cell);
+void tds_map_destroy(tds_map_t* map);
+
+typedef struct {
+    int32_t n_verts, n_faces;
+    int32_t raster_gx, raster_gy, raster_records;
+    int32_t offroad_gx, offroad_gy, offroad_entries;
+    float raster_cell, offroad_cell;
+    float min_x, min_y, max_x, max_y;
+    int64_t device_bytes;
+} tds_map_info_t;
+int tds_map_info(const tds_map_t* map, tds_map_info_t* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Offroad.  Replaces offroad_infraction_loss (infractions.py:176-229) + point_to_mesh_distance_pt
+ * (infractions.py:86-173): out[b,a] = sum over the 4 box corners of (d2 if d2 > threshold else 0),
+ * d2 = min over ALL map faces of the reference's squared point-triangle distance; times present.
+ * maps[d_env_map[b]] is the map of environment b (d_env_map NULL: map 0 for all).
+ * d_face [B,A,4] int32 or NULL receives the argmin face per corner (for the backward).
+ * ---------------------------------------------------------------------------------------- */
+int tds_offroad_fwd(const tds_map_t* const* maps, int32_t n_maps, const int32_t* d_env_map,
+                    const float* d_state, const float* d_lenwid, const uint8_t* d_present,
+                    int32_t B, int32_t A, float threshold, float* d_out, int32_t* d_face, void* stream);
+/* d_grad_out [B,A] -> d_grad_state [B,A,4] (x,y,psi; v gets 0), d_grad_lenwid [B,A,2] or NULL */
+int tds_offroad_bwd(const tds_map_t* const* maps, int32_t n_maps, const int32_t* d_env_map,
+                    const float* d_state, const float* d_lenwid, const uint8_t* d_present,
+                    int32_t B, int32_t A, float threshold, const int32_t* d_face, const float* d_grad_out,
+                    float* d_grad_state, float* d_grad_lenwid, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Birdview raster.  Replaces BirdviewRGBMeshGenerator.generate (mesh.py:1053-1157) +
+ * BirdviewRenderer.render_frame (rendering/base.py:167-204) + CV2Renderer.render_rgb_mesh
+ * (rendering/cv2.py:27-70) with pixel-identical output (cv2.fillConvexPoly integer rule).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_classes;                              /* size of the tables below, <= TDS_MAX_CLASSES */
+    uint8_t active[TDS_MAX_CLASSES];                /* 1: the class may occur and gets a draw pass */
+    uint8_t rank[TDS_MAX_CLASSES];                  /* draw order, 0 first (= highest z level) */
+    uint8_t rgb[TDS_MAX_CLASSES][3];                /* colour of the class, 0..255 */
+    int32_t agent_type_class[TDS_MAX_AGENT_TYPES];  /* class of agent type index t */
+    int32_t direction_class;                        /* class of the direction triangle, -1: none */
+    int32_t tl_state_class[TDS_MAX_TL_STATES];      /* class of traffic-light state index s */
+} tds_palette_t;
+
+/* bytes of the per-step scratch buffer (world-space dynamic triangles of every environment) */
+int64_t tds_raster_workspace_bytes(int32_t B, int32_t N, int32_t L, int32_t R);
+
+/* Renders Nc cameras per environment.
+ *   d_cam_xy, d_cam_sc [B,Nc,2]  camera positions and (sin, cos) of the camera orientation
+ *   d_agent_state [B,N,4], d_agent_size [B,N,2], d_agent_type [B,N] int32 (NULL: type 0)
+ *   d_present [B,N] uint8, or [B,Nc,N] when present_per_camera != 0 (rendering_mask)
+ *   d_tl_corners [B,L,4,2], d_tl_state [B,L] int32 (L may be 0)
+ *   d_rect_corners [B,R,4,2], d_rect_class [B,R] int32: extra rectangles (stop / yield signs)
+ *   scale = 2 / fov, res = H = W (square only, as the reference)
+ *   d_out [B,Nc,3,res,res] float32 in [0,255]
+ *   d_workspace: tds_raster_workspace_bytes(B,N,L,R) bytes */
+int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps, const int32_t* d_env_map,
+                        int32_t B, int32_t Nc, int32_t N,
+                        const float* d_cam_xy, const float* d_cam_sc,
+                        const float* d_agent_state, const float* d_agent_size, const int32_t* d_agent_type,
+                        const uint8_t* d_present, int32_t present_per_camera,
+                        const float* d_tl_corners, const int32_t* d_tl_state, int32_t L,
+                        const float* d_rect_corners, const int32_t* d_rect_class, int32_t R,
+                        const tds_palette_t* palette, float scale, int32_t res,
+                        float* d_out, void* d_workspace, void* stream);
+
+/* Measurement hook: when both are non-NULL cudaEvent_t handles, the next tds_raster_birdview calls on
+ * this thread record `start` / `stop` on their stream immediately around the raster kernel launch
+ * (the dominant kernel), so a benchmark can time it in situ.  Pass NULLs to disable. */
+void tds_raster_set_timing_events(void* start_event, void* stop_event);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDS_B200_H */

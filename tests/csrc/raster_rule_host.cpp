@@ -1,0 +1,10 @@
+// Host build of the product's triangle coverage rule (torchdrivesim_b200/csrc/tds_raster_tri.h)
+// so that the exact code the CUDA kernel runs can be checked against cv2 on the CPU.
+#include <stdint.h>
+#include "tds_raster_tri.h"
+
+extern "C" void tds_host_draw_triangle(uint8_t* img, int W, int H, const int32_t* p) {
+    tds::draw_triangle(W, H, p[0], p[1], p[2], p[3], p[4], p[5],
+        [&](int x, int y) { img[y * W + x] = 1; },
+        [&](int y, int xa, int xb) { for (int x = xa; x <= xb; x++) img[y * W + x] = 1; });
+}

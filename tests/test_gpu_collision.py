@@ -1,0 +1,128 @@
+"""Collision kernels (discs fwd+bwd, IoU fwd, fused all-pairs) vs the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+IOU_RTOL, IOU_ATOL = 1e-5, 2e-6       # IoU is compared against the reference in float64
+
+
+def _boxes(B, N, rng, spread=6.0, ped_every=3, zero_size_every=0):
+    xy = rng.uniform(0, 300, (B, 1, 2)) + spread * rng.standard_normal((B, N, 2))
+    lw = np.tile(np.array(util.VEH[:2], np.float32), (B, N, 1))
+    if ped_every:
+        lw[:, ped_every - 1::ped_every] = util.PED
+    if zero_size_every:
+        lw[:, zero_size_every - 1::zero_size_every] = 0.0
+    psi = rng.uniform(-7, 7, (B, N, 1))
+    return np.concatenate([xy, lw, psi], -1).astype(np.float32)
+
+
+def test_golden_discs_and_iou():
+    import torchdrivesim_b200 as tds
+    g = util.golden("collision")
+    box = torch.tensor(g["box"]).cuda()
+    present = torch.tensor(g["present"]).cuda()
+    B, A = box.shape[:2]
+    e = box.unsqueeze(2).expand(-1, -1, A, -1).reshape(B, A * A, 5).contiguous()
+    o = box.unsqueeze(1).expand(-1, A, -1, -1).reshape(B, A * A, 5).contiguous()
+    pair = tds.collision_detection_with_discs(e, o).reshape(B, A, A).cpu().numpy()
+    np.testing.assert_allclose(pair, g["discs_pair"], rtol=RTOL, atol=ATOL)
+    st = torch.cat([box[..., :2], box[..., 4:5], torch.zeros(B, A, 1).cuda()], -1).requires_grad_(True)
+    bx = torch.cat([st[..., :2], box[..., 2:4], st[..., 2:3]], -1)
+    coll = tds.collision_allpairs(bx, bx, present, "discs")
+    np.testing.assert_allclose(coll.detach().cpu().numpy(), g["discs_collision"], rtol=RTOL, atol=ATOL)
+    coll.sum().backward()
+    np.testing.assert_allclose(st.grad.cpu().numpy()[..., :3], g["discs_grad_state"][..., :3], rtol=1e-4, atol=1e-5)
+    iou = tds.iou_differentiable(e, o).reshape(B, A, A).cpu().numpy()
+    np.testing.assert_allclose(iou, g["iou64"], rtol=IOU_RTOL, atol=IOU_ATOL)
+
+
+@pytest.mark.parametrize("B,A,N", [(4, 9, 9), (2, 64, 64), (1, 70, 300), (3, 1, 1)])
+def test_discs_allpairs_vs_oracle(B, A, N):
+    from oracle import collision as C
+    import torchdrivesim_b200 as tds
+    rng = np.random.default_rng(B * 100 + N)
+    allb = _boxes(B, N, rng, zero_size_every=7 if N > 8 else 0)
+    mask = rng.uniform(size=(B, N)) > 0.25
+    w = rng.standard_normal((B, A)).astype(np.float32)
+    a_o = torch.tensor(allb, requires_grad=True)
+    out_o = C.collision_allpairs(a_o[:, :A], a_o, torch.tensor(mask))
+    (out_o * torch.tensor(w)).sum().backward()
+    a_g = torch.tensor(allb).cuda().requires_grad_(True)
+    out_g = tds.collision_allpairs(a_g[:, :A], a_g, torch.tensor(mask).cuda(), "discs")
+    (out_g * torch.tensor(w).cuda()).sum().backward()
+    np.testing.assert_allclose(out_g.detach().cpu().numpy(), out_o.detach().numpy(), rtol=RTOL, atol=2e-6)
+    go, gg = a_o.grad.numpy(), a_g.grad.cpu().numpy()
+    # zero-size (padding) boxes: their 0/0 self pair makes the reference's autograd NaN for the whole box;
+    # the kernel returns the finite gradient of the remaining pairs.  Compare where the oracle is finite.
+    ok = np.isfinite(go).all(-1)
+    assert ok.mean() > 0.8 and np.isfinite(gg).all()
+    np.testing.assert_allclose(gg[ok], go[ok], rtol=2e-4, atol=2e-5)
+
+
+def test_discs_pairwise_gradients_incl_size():
+    from oracle import collision as C
+    import torchdrivesim_b200 as tds
+    rng = np.random.default_rng(3)
+    b1 = _boxes(1, 400, rng, spread=2.5)[0]
+    b2 = _boxes(1, 400, rng, spread=2.5)[0]
+    b2[:, :2] = b1[:, :2] + rng.normal(0, 2.0, (400, 2)).astype(np.float32)
+    t1o, t2o = torch.tensor(b1, requires_grad=True), torch.tensor(b2, requires_grad=True)
+    C.discs_pairwise(t1o, t2o).sum().backward()
+    t1g, t2g = torch.tensor(b1).cuda().requires_grad_(True), torch.tensor(b2).cuda().requires_grad_(True)
+    out = tds.collision_detection_with_discs(t1g[None], t2g[None])
+    out.sum().backward()
+    assert int((out > 0).sum()) > 50
+    np.testing.assert_allclose(t1g.grad.cpu().numpy(), t1o.grad.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(t2g.grad.cpu().numpy(), t2o.grad.numpy(), rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,N", [(3, 24), (1, 200)])
+def test_iou_allpairs_vs_oracle_f64(B, N):
+    from oracle import iou as I
+    import torchdrivesim_b200 as tds
+    rng = np.random.default_rng(N)
+    allb = _boxes(B, N, rng, spread=5.0)
+    allb[0, 1] = allb[0, 0]                                  # identical boxes
+    allb[0, 2, :4] = allb[0, 3, :4]; allb[0, 2, 4] = allb[0, 3, 4]; allb[0, 2, 0] += 1.0   # parallel, shifted
+    mask = rng.uniform(size=(B, N)) > 0.2
+    g = torch.tensor(allb).cuda()
+    e = g.unsqueeze(2).expand(-1, -1, N, -1).reshape(B, N * N, 5).contiguous()
+    o = g.unsqueeze(1).expand(-1, N, -1, -1).reshape(B, N * N, 5).contiguous()
+    pair = tds.iou_differentiable(e, o).reshape(B, N, N).cpu().numpy()
+    ref = np.stack([I.iou_matrix(allb[b], allb[b]) for b in range(B)])
+    np.testing.assert_allclose(pair, ref, rtol=IOU_RTOL, atol=IOU_ATOL)
+    # fused aggregate with diag := 1
+    refd = ref.copy()
+    for b in range(B):
+        np.fill_diagonal(refd[b], 1.0)
+    om = refd * mask[:, None, :]
+    agg = om.sum(-1) - om.max(-1)
+    out = tds.collision_allpairs(g, g, torch.tensor(mask).cuda(), "iou").cpu().numpy()
+    np.testing.assert_allclose(out, agg, rtol=1e-5, atol=N * IOU_ATOL)
+
+
+def test_simulator_collision_properties_full_size():
+    """Size-independent checks at the config-2 size (1024 x 64): permutation invariance of the row sums,
+    zero for isolated agents, symmetry of the pair matrix."""
+    import torchdrivesim_b200 as tds
+    rng = np.random.default_rng(0)
+    B, N = 1024, 64
+    allb = torch.tensor(_boxes(B, N, rng, spread=15.0)).cuda()
+    mask = torch.ones(B, N, dtype=torch.bool).cuda()
+    out = tds.collision_allpairs(allb, allb, mask, "discs")
+    perm = torch.randperm(N).cuda()
+    out_p = tds.collision_allpairs(allb[:, perm], allb[:, perm], mask, "discs")
+    np.testing.assert_allclose(out_p.cpu().numpy(), out[:, perm].cpu().numpy(), rtol=1e-5, atol=1e-5)
+    far = allb.clone()
+    far[..., 0] += torch.arange(N).cuda() * 100.0
+    assert float(tds.collision_allpairs(far, far, mask, "discs").abs().max()) == 0.0
+    e = allb[:8].unsqueeze(2).expand(-1, -1, N, -1).reshape(8, N * N, 5).contiguous()
+    o = allb[:8].unsqueeze(1).expand(-1, N, -1, -1).reshape(8, N * N, 5).contiguous()
+    pm = tds.collision_detection_with_discs(e, o).reshape(8, N, N)
+    np.testing.assert_allclose(pm.cpu().numpy(), pm.transpose(1, 2).cpu().numpy(), rtol=0, atol=1e-6)
+    assert float((torch.diagonal(pm, dim1=1, dim2=2) - 1).abs().max()) == 0.0

@@ -1,0 +1,420 @@
+// Pairwise oriented-box collision metrics.
+//
+// discs : TrafficSim disc approximation, collision_detection_with_discs + bbox2discs
+//         (torchdrivesim/infractions.py:503-545, 378-409), forward and backward.
+// iou   : rotated-box IoU, iou_differentiable_fast (torchdrivesim/_iou_utils.py:344-367), forward.
+//         The reference finds the intersection polygon by sorting 24 candidate vertices by angle
+//         in world coordinates; in fp32 that is chaotic on the diagonal.
+//         Here box 2 is moved into the frame of box 1 and clipped against an axis-aligned
+//         rectangle (Sutherland-Hodgman), which computes the same area and agrees with the
+//         reference evaluated in float64 to ~1e-7.
+// all-pairs: Simulator.compute_collision (torchdrivesim/simulator.py:1161-1194, 1064-1109):
+//         out[b,i] = sum_j o_ij m_j - max_j o_ij m_j, one warp per row i, lanes over columns j,
+//         warp-shuffle reductions; per-environment box data staged in shared memory.
+// This work is FP32-pipe bound (no HBM traffic to speak of: 20 B per box in, 4 B per row out).
+#include <math_constants.h>
+
+#include "tds_common.cuh"
+
+namespace {
+
+constexpr int kDiscs = 5;
+
+struct Discs {
+    float cx[kDiscs], cy[kDiscs];
+    float r;        // disc radius = min(l, w) / 2
+    float half;     // max(l, w) / 2   (bounding radius along the major axis)
+    float x, y;     // box centre
+};
+
+// bbox2discs, infractions.py:378-409 (nan_to_num of the box as in simulator.py:1095-1096)
+__device__ __forceinline__ Discs make_discs(float x, float y, float l, float w, float psi) {
+    Discs d;
+    if (x != x) x = 0.f;
+    if (y != y) y = 0.f;
+    if (l != l) l = 0.f;
+    if (w != w) w = 0.f;
+    if (psi != psi) psi = 0.f;
+    d.x = x; d.y = y;
+    d.r = fminf(l, w) / 2.0f;
+    d.half = fmaxf(l, w) / 2.0f;
+    const float span = d.half - d.r;
+    const float yaw = psi + 1.5707963705062866f * (w > l ? 1.0f : 0.0f);   // float32(pi/2)
+    float s, c;
+    tds::sincos_cr(yaw, s, c);
+#pragma unroll
+    for (int i = 0; i < kDiscs; i++) {
+        const float off = ((float)(i - 2) * span) / 2.0f;
+        d.cx[i] = off * c + x;
+        d.cy[i] = off * s + y;
+    }
+    return d;
+}
+
+// overlap in [0,1]; amin/bmin receive the argmin disc pair (first in row-major order), dmin the distance
+__device__ __forceinline__ float discs_overlap(const Discs& p, const Discs& q, int* amin, int* bmin, float* dmin) {
+    float best = CUDART_INF_F;
+    int ba = 0, bb = 0;
+#pragma unroll
+    for (int a = 0; a < kDiscs; a++) {
+#pragma unroll
+        for (int b = 0; b < kDiscs; b++) {
+            const float dx = p.cx[a] - q.cx[b], dy = p.cy[a] - q.cy[b];
+            const float d2 = dx * dx + dy * dy;
+            if (d2 < best) { best = d2; ba = a; bb = b; }
+        }
+    }
+    const float d = sqrtf(best);
+    if (amin) { *amin = ba; *bmin = bb; *dmin = d; }
+    float o = 1.0f - d / (p.r + q.r);
+    o = o > 0.0f ? o : 0.0f;         // relu; NaN (0/0 for zero-size boxes) compares false -> 0, as nan_to_num
+    return o;
+}
+
+// ---------------------------------------------------------------- IoU
+struct Box {
+    float x, y, l, w, s, c;   // s, c = sin/cos(psi)
+};
+
+__device__ __forceinline__ Box make_box(float x, float y, float l, float w, float psi) {
+    Box b;
+    if (x != x) x = 0.f;
+    if (y != y) y = 0.f;
+    if (l != l) l = 0.f;
+    if (w != w) w = 0.f;
+    if (psi != psi) psi = 0.f;
+    b.x = x; b.y = y; b.l = l; b.w = w;
+    tds::sincos_cr(psi, b.s, b.c);
+    return b;
+}
+
+// clip polygon (px,py,n) against  sign*coord <= bound  (coord = x if axis==0 else y)
+__device__ __forceinline__ int clip_axis(const float* px, const float* py, int n, float* qx, float* qy, int axis,
+                                         float sign, float bound) {
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        const float ax = px[i], ay = py[i], bx = px[j], by = py[j];
+        const float da = sign * (axis ? ay : ax) - bound;
+        const float db = sign * (axis ? by : bx) - bound;
+        const bool ina = da <= 0.0f, inb = db <= 0.0f;
+        if (ina) { qx[m] = ax; qy[m] = ay; m++; }
+        if (ina != inb) {
+            const float t = da / (da - db);
+            qx[m] = ax + t * (bx - ax);
+            qy[m] = ay + t * (by - ay);
+            m++;
+        }
+    }
+    return m;
+}
+
+__device__ float iou_pair(const Box& p, const Box& q) {
+    const float a1 = p.l * p.w, a2 = q.l * q.w;
+    // bounding-circle early out: exact 0 in the reference for disjoint boxes
+    const float dx = q.x - p.x, dy = q.y - p.y;
+    const float rp = 0.5f * sqrtf(p.l * p.l + p.w * p.w), rq = 0.5f * sqrtf(q.l * q.l + q.w * q.w);
+    const float reach = rp + rq;
+    if (dx * dx + dy * dy > reach * reach * 1.0001f + 1e-6f) return 0.0f;
+    // box q in the frame of box p: rotate by -psi_p
+    const float cr = p.c * q.c + p.s * q.s;       // cos(psi_q - psi_p)
+    const float sr = p.c * q.s - p.s * q.c;       // sin(psi_q - psi_p)
+    const float tx = p.c * dx + p.s * dy;
+    const float ty = p.c * dy - p.s * dx;
+    const float hx = 0.5f * q.l, hy = 0.5f * q.w;
+    float px[10], py[10], qx[10], qy[10];
+    const float sx[4] = {1.f, -1.f, -1.f, 1.f}, sy[4] = {1.f, 1.f, -1.f, -1.f};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float ux = sx[k] * hx, uy = sy[k] * hy;
+        px[k] = tx + (ux * cr - uy * sr);
+        py[k] = ty + (ux * sr + uy * cr);
+    }
+    const float bx = 0.5f * p.l, by = 0.5f * p.w;
+    int n = 4;
+    n = clip_axis(px, py, n, qx, qy, 0, 1.f, bx);
+    n = clip_axis(qx, qy, n, px, py, 0, -1.f, bx);
+    n = clip_axis(px, py, n, qx, qy, 1, 1.f, by);
+    n = clip_axis(qx, qy, n, px, py, 1, -1.f, by);
+    if (n < 3) return 0.0f;
+    float tot = 0.0f;
+    for (int i = 0; i < n; i++) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        tot += px[i] * py[j] - py[i] * px[j];
+    }
+    const float inter = 0.5f * fabsf(tot);
+    const float iou = inter / (a1 + a2 - inter);
+    return iou == iou ? iou : 0.0f;               // nan_to_num, simulator.py:1103
+}
+
+// ---------------------------------------------------------------- element-wise API
+__global__ void __launch_bounds__(256) pairwise_fwd_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
+                                                           int64_t n, int metric, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = b1 + 5 * i;
+    const float* q = b2 + 5 * i;
+    if (metric == TDS_METRIC_DISCS) {
+        const Discs dp = make_discs(p[0], p[1], p[2], p[3], p[4]);
+        const Discs dq = make_discs(q[0], q[1], q[2], q[3], q[4]);
+        out[i] = discs_overlap(dp, dq, nullptr, nullptr, nullptr);
+    } else {
+        out[i] = iou_pair(make_box(p[0], p[1], p[2], p[3], p[4]), make_box(q[0], q[1], q[2], q[3], q[4]));
+    }
+}
+
+// gradient of one disc pair w.r.t. both boxes, scaled by wgt; returns false if the pair has zero gradient
+struct BoxGrad {
+    float g[5];
+};
+__device__ __forceinline__ void disc_center_grad(float l, float w, float psi, int k, float gcx, float gcy, float gr,
+                                                 BoxGrad& out) {
+    // centre_k = (x,y) + off_k (cos yaw, sin yaw), off_k = (k-2) (half - r) / 2, yaw = psi + pi/2 [w > l]
+    const float yaw = psi + 1.5707963705062866f * (w > l ? 1.0f : 0.0f);
+    float s, c;
+    tds::sincos_cr(yaw, s, c);
+    const float half = fmaxf(l, w) / 2.0f, r = fminf(l, w) / 2.0f;
+    const float kk = (float)(k - 2) * 0.5f;
+    const float off = kk * (half - r);
+    const float goff = gcx * c + gcy * s;
+    out.g[0] += gcx;
+    out.g[1] += gcy;
+    out.g[4] += off * (gcy * c - gcx * s);
+    // d half / d(l,w), d r / d(l,w): torch.maximum / minimum split the gradient evenly on ties
+    float hl, hw, rl, rw;
+    if (l > w) { hl = 0.5f; hw = 0.f; rl = 0.f; rw = 0.5f; }
+    else if (l < w) { hl = 0.f; hw = 0.5f; rl = 0.5f; rw = 0.f; }
+    else { hl = hw = rl = rw = 0.25f; }
+    out.g[2] += goff * kk * (hl - rl) + gr * rl;
+    out.g[3] += goff * kk * (hw - rw) + gr * rw;
+}
+
+__device__ __forceinline__ bool discs_pair_grad(const float* p, const float* q, float wgt, BoxGrad& gp, BoxGrad& gq) {
+    const Discs dp = make_discs(p[0], p[1], p[2], p[3], p[4]);
+    const Discs dq = make_discs(q[0], q[1], q[2], q[3], q[4]);
+    int a, b;
+    float d;
+    const float o = discs_overlap(dp, dq, &a, &b, &d);
+    if (!(o > 0.0f) || wgt == 0.0f) return false;
+    const float R = dp.r + dq.r;
+    const float go_d = -wgt / R;                 // d o / d dist
+    const float go_R = wgt * d / (R * R);        // d o / d (r1 + r2)
+    float ux = 0.f, uy = 0.f;                    // cdist backward: 0 at zero distance
+    if (d > 0.0f) { ux = (dp.cx[a] - dq.cx[b]) / d; uy = (dp.cy[a] - dq.cy[b]) / d; }
+    disc_center_grad(p[2], p[3], p[4], a, go_d * ux, go_d * uy, go_R, gp);
+    disc_center_grad(q[2], q[3], q[4], b, -go_d * ux, -go_d * uy, go_R, gq);
+    return true;
+}
+
+__global__ void __launch_bounds__(256) discs_pairwise_bwd_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
+                                                                 int64_t n, const float* __restrict__ gout,
+                                                                 float* __restrict__ g1, float* __restrict__ g2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    BoxGrad gp = {}, gq = {};
+    discs_pair_grad(b1 + 5 * i, b2 + 5 * i, gout[i], gp, gq);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (g1) g1[5 * i + k] = gp.g[k];
+        if (g2) g2[5 * i + k] = gq.g[k];
+    }
+}
+
+// ---------------------------------------------------------------- all-pairs
+constexpr int kRowsPerCta = 64;
+constexpr int kWarps = 8;
+
+// shared memory: all N column boxes of the environment, as discs (12 floats) or Box (6 floats)
+template <int METRIC>
+__global__ void __launch_bounds__(kWarps * 32) allpairs_fwd_kernel(const float* __restrict__ ego, const float* __restrict__ all,
+                                                                  const uint8_t* __restrict__ mask, int A, int N,
+                                                                  int ego_is_prefix, float* __restrict__ out,
+                                                                  int32_t* __restrict__ argmax) {
+    extern __shared__ float smem[];
+    constexpr int STRIDE = METRIC == TDS_METRIC_DISCS ? 13 : 7;   // odd strides: conflict-free column reads
+    const int b = blockIdx.y;
+    const int row0 = blockIdx.x * kRowsPerCta;
+    const float* allb = all + (size_t)b * N * 5;
+    const uint8_t* mb = mask + (size_t)b * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float* q = allb + 5 * j;
+        float* s = smem + j * STRIDE;
+        if (METRIC == TDS_METRIC_DISCS) {
+            const Discs d = make_discs(q[0], q[1], q[2], q[3], q[4]);
+#pragma unroll
+            for (int k = 0; k < kDiscs; k++) { s[2 * k] = d.cx[k]; s[2 * k + 1] = d.cy[k]; }
+            s[10] = d.r; s[11] = d.half; s[12] = mb[j] ? 1.0f : 0.0f;
+        } else {
+            const Box d = make_box(q[0], q[1], q[2], q[3], q[4]);
+            s[0] = d.x; s[1] = d.y; s[2] = d.l; s[3] = d.w; s[4] = d.s; s[5] = d.c; s[6] = mb[j] ? 1.0f : 0.0f;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < kRowsPerCta; r += kWarps) {
+        const int i = row0 + r;
+        if (i >= A) break;
+        const float* p = ego + ((size_t)b * A + i) * 5;
+        float sum = 0.0f, best = -CUDART_INF_F;
+        int besti = 0;
+        if (METRIC == TDS_METRIC_DISCS) {
+            const Discs dp = make_discs(p[0], p[1], p[2], p[3], p[4]);
+            for (int j = lane; j < N; j += 32) {
+                const float* s = smem + j * STRIDE;
+                Discs dq;
+#pragma unroll
+                for (int k = 0; k < kDiscs; k++) { dq.cx[k] = s[2 * k]; dq.cy[k] = s[2 * k + 1]; }
+                dq.r = s[10]; dq.half = s[11];
+                float o = 0.0f;
+                // centres further apart than the two half-lengths cannot have touching discs
+                const float ddx = dp.cx[2] - dq.cx[2], ddy = dp.cy[2] - dq.cy[2];
+                const float reach = dp.half + dq.half;
+                if (ddx * ddx + ddy * ddy <= reach * reach * 1.0001f + 1e-6f)
+                    o = discs_overlap(dp, dq, nullptr, nullptr, nullptr);
+                o *= s[12];
+                sum += o;
+                if (o > best) { best = o; besti = j; }
+            }
+        } else {
+            const Box bp = make_box(p[0], p[1], p[2], p[3], p[4]);
+            for (int j = lane; j < N; j += 32) {
+                const float* s = smem + j * STRIDE;
+                Box bq;
+                bq.x = s[0]; bq.y = s[1]; bq.l = s[2]; bq.w = s[3]; bq.s = s[4]; bq.c = s[5];
+                float o = (ego_is_prefix && j == i) ? 1.0f : iou_pair(bp, bq);
+                o *= s[6];
+                sum += o;
+                if (o > best) { best = o; besti = j; }
+            }
+        }
+        sum = tds::warp_sum(sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) {
+            const bool any = N > 0;
+            out[(size_t)b * A + i] = any ? sum - best : 0.0f;
+            if (argmax) argmax[(size_t)b * A + i] = besti;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32) discs_allpairs_bwd_kernel(const float* __restrict__ ego, const float* __restrict__ all,
+                                                                        const uint8_t* __restrict__ mask, int A, int N,
+                                                                        const float* __restrict__ gout,
+                                                                        const int32_t* __restrict__ argmax,
+                                                                        float* __restrict__ g_ego, float* __restrict__ g_all) {
+    extern __shared__ float gcol[];              // [N][5] column gradients of this CTA
+    const int b = blockIdx.y;
+    const int row0 = blockIdx.x * kRowsPerCta;
+    const float* allb = all + (size_t)b * N * 5;
+    const uint8_t* mb = mask + (size_t)b * N;
+    for (int k = threadIdx.x; k < N * 5; k += blockDim.x) gcol[k] = 0.0f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < kRowsPerCta; r += kWarps) {
+        const int i = row0 + r;
+        if (i >= A) break;
+        const float* p = ego + ((size_t)b * A + i) * 5;
+        const float g = gout[(size_t)b * A + i];
+        const int am = argmax[(size_t)b * A + i];
+        BoxGrad gp = {};
+        for (int j = lane; j < N; j += 32) {
+            // d out_i / d o_ij = m_j (1 - [j == argmax_i])
+            const float wgt = (mb[j] && j != am) ? g : 0.0f;
+            if (wgt == 0.0f) continue;
+            BoxGrad gq = {};
+            if (discs_pair_grad(p, allb + 5 * j, wgt, gp, gq)) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) atomicAdd(&gcol[5 * j + k], gq.g[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float v = tds::warp_sum(gp.g[k]);
+            if (lane == 0) g_ego[((size_t)b * A + i) * 5 + k] = v;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < N * 5; k += blockDim.x) {
+        const float v = gcol[k];
+        if (v != 0.0f) atomicAdd(&g_all[(size_t)b * N * 5 + k], v);
+    }
+}
+
+}  // namespace
+
+extern "C" int tds_collision_pairwise_fwd(const float* d_box1, const float* d_box2, int64_t p, int32_t metric,
+                                          float* d_out, void* stream) {
+    TDS_REQUIRE(d_box1 && d_box2 && d_out, "collision_pairwise: null pointer");
+    TDS_REQUIRE(metric == TDS_METRIC_DISCS || metric == TDS_METRIC_IOU, "collision_pairwise: unknown metric %d", metric);
+    TDS_REQUIRE(p >= 0, "collision_pairwise: negative size");
+    if (p == 0) return TDS_OK;
+    pairwise_fwd_kernel<<<(unsigned)((p + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_box1, d_box2, p, metric, d_out);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_collision_discs_pairwise_bwd(const float* d_box1, const float* d_box2, int64_t p,
+                                                const float* d_grad_out, float* d_grad_box1, float* d_grad_box2,
+                                                void* stream) {
+    TDS_REQUIRE(d_box1 && d_box2 && d_grad_out, "collision_pairwise_bwd: null pointer");
+    TDS_REQUIRE(p >= 0, "collision_pairwise_bwd: negative size");
+    if (p == 0) return TDS_OK;
+    discs_pairwise_bwd_kernel<<<(unsigned)((p + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_box1, d_box2, p, d_grad_out,
+                                                                                             d_grad_box1, d_grad_box2);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_collision_allpairs_fwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
+                                          int32_t B, int32_t A, int32_t N, int32_t metric, int32_t ego_is_prefix,
+                                          float* d_out, int32_t* d_argmax, void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0 && N >= 0, "collision_allpairs: negative size");
+    if (B == 0 || A == 0) return TDS_OK;
+    TDS_REQUIRE(d_ego_box && d_out, "collision_allpairs: null pointer");
+    TDS_REQUIRE(N == 0 || (d_all_box && d_mask), "collision_allpairs: null pointer");
+    TDS_REQUIRE(metric == TDS_METRIC_DISCS || metric == TDS_METRIC_IOU, "collision_allpairs: unknown metric %d", metric);
+    TDS_REQUIRE(B <= 65535, "collision_allpairs: B=%d exceeds 65535 (shard the batch)", B);
+    const dim3 grid((A + kRowsPerCta - 1) / kRowsPerCta, B);
+    const size_t smem = (size_t)N * (metric == TDS_METRIC_DISCS ? 13 : 7) * sizeof(float);
+    TDS_REQUIRE(smem <= 200 * 1024, "collision_allpairs: N=%d does not fit shared memory", N);
+    if (metric == TDS_METRIC_DISCS) {
+        if (smem > 48 * 1024)
+            TDS_CUDA_OK(cudaFuncSetAttribute(allpairs_fwd_kernel<TDS_METRIC_DISCS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allpairs_fwd_kernel<TDS_METRIC_DISCS><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
+            d_ego_box, d_all_box, d_mask, A, N, ego_is_prefix, d_out, d_argmax);
+    } else {
+        if (smem > 48 * 1024)
+            TDS_CUDA_OK(cudaFuncSetAttribute(allpairs_fwd_kernel<TDS_METRIC_IOU>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allpairs_fwd_kernel<TDS_METRIC_IOU><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
+            d_ego_box, d_all_box, d_mask, A, N, ego_is_prefix, d_out, d_argmax);
+    }
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_collision_discs_allpairs_bwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
+                                                int32_t B, int32_t A, int32_t N, const float* d_grad_out,
+                                                const int32_t* d_argmax, float* d_grad_ego, float* d_grad_all,
+                                                void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0 && N >= 0, "collision_allpairs_bwd: negative size");
+    if (B == 0 || A == 0 || N == 0) return TDS_OK;
+    TDS_REQUIRE(d_ego_box && d_all_box && d_mask && d_grad_out && d_argmax && d_grad_ego && d_grad_all,
+                "collision_allpairs_bwd: null pointer");
+    TDS_REQUIRE(B <= 65535, "collision_allpairs_bwd: B=%d exceeds 65535 (shard the batch)", B);
+    const dim3 grid((A + kRowsPerCta - 1) / kRowsPerCta, B);
+    const size_t smem = (size_t)N * 5 * sizeof(float);
+    TDS_REQUIRE(smem <= 200 * 1024, "collision_allpairs_bwd: N=%d does not fit shared memory", N);
+    if (smem > 48 * 1024)
+        TDS_CUDA_OK(cudaFuncSetAttribute(discs_allpairs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    discs_allpairs_bwd_kernel<<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(d_ego_box, d_all_box, d_mask, A, N,
+                                                                                d_grad_out, d_argmax, d_grad_ego, d_grad_all);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}

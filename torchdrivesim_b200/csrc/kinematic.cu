@@ -1,0 +1,161 @@
+// Kinematic state transition, forward and backward (one thread per agent, float4 state I/O).
+//
+// Reference semantics: KinematicBicycle.step (torchdrivesim/kinematic.py:462-477),
+// BicycleNoReversing.step (:509-523); the per-agent `model` id replaces the boolean-mask
+// split/merge of CompoundKinematicModel.step (:197-201), which costs a host sync per step.
+// The unicycle is defined by this build (the reference only names it, README.md:16).
+// HBM traffic per agent: 16 B state in + 8 B action + 4 B lr (+4 B model) + 16 B state out.
+#include "tds_common.cuh"
+
+namespace {
+
+struct KinIn {
+    float x, y, psi, v, a0, a1, lr;
+    int model;
+};
+
+__device__ __forceinline__ KinIn load_agent(const float* state, const float* action, const float* lr,
+                                            const int32_t* model, int uniform_model, int64_t i) {
+    const float4 s = reinterpret_cast<const float4*>(state)[i];
+    const float2 a = reinterpret_cast<const float2*>(action)[i];
+    KinIn k;
+    k.x = s.x; k.y = s.y; k.psi = s.z; k.v = s.w;
+    k.a0 = a.x; k.a1 = a.y;
+    k.model = model ? model[i] : uniform_model;
+    k.lr = (k.model == TDS_MODEL_UNICYCLE || lr == nullptr) ? 1.0f : lr[i];
+    return k;
+}
+
+// de-normalised controls shared by forward and backward
+struct Controls {
+    float acc, ang;      // acceleration, steering (bicycle) or yaw rate (unicycle) after all flips
+    bool reversing;      // BicycleNoReversing clamp active
+};
+
+__device__ __forceinline__ Controls controls(const KinIn& k, const tds_kinematic_params_t& p) {
+    Controls c;
+    const float ang_scale = k.model == TDS_MODEL_UNICYCLE ? p.max_yaw_rate : p.max_steering;
+    c.acc = k.a0 * p.max_acceleration;
+    c.ang = k.a1 * ang_scale;
+    c.reversing = false;
+    if (k.model == TDS_MODEL_BICYCLE_NO_REVERSING) {
+        c.reversing = (k.v + c.acc * p.dt) < 0.0f;
+        if (c.reversing) c.acc = (-k.v) / p.dt;
+        // the reference re-normalises and de-normalises the modified action (kinematic.py:521-523)
+        c.acc = (c.acc / p.max_acceleration) * p.max_acceleration;
+        c.ang = (c.ang / ang_scale) * ang_scale;
+    }
+    if (p.left_handed) c.ang = -c.ang;
+    return c;
+}
+
+__global__ void __launch_bounds__(256) kin_fwd_kernel(const float* __restrict__ state, const float* __restrict__ action,
+                                                      const float* __restrict__ lr, const int32_t* __restrict__ model,
+                                                      int uniform_model, int64_t n, tds_kinematic_params_t p,
+                                                      float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KinIn k = load_agent(state, action, lr, model, uniform_model, i);
+    const Controls c = controls(k, p);
+    const float v = k.v + c.acc * p.dt;
+    float4 o;
+    if (k.model == TDS_MODEL_UNICYCLE) {
+        float s, co;
+        tds::sincos_cr(k.psi, s, co);
+        o.x = k.x + (v * co) * p.dt;
+        o.y = k.y + (v * s) * p.dt;
+        o.z = k.psi + c.ang * p.dt;
+    } else {
+        float s, co, sb, cb;
+        tds::sincos_cr(k.psi + c.ang, s, co);
+        tds::sincos_cr(c.ang, sb, cb);
+        o.x = k.x + (v * co) * p.dt;
+        o.y = k.y + (v * s) * p.dt;
+        o.z = k.psi + ((v / k.lr) * sb) * p.dt;
+    }
+    o.w = v;
+    reinterpret_cast<float4*>(out)[i] = o;
+}
+
+__global__ void __launch_bounds__(256) kin_bwd_kernel(const float* __restrict__ state, const float* __restrict__ action,
+                                                      const float* __restrict__ lr, const int32_t* __restrict__ model,
+                                                      int uniform_model, int64_t n, tds_kinematic_params_t p,
+                                                      const float* __restrict__ grad_out, float* __restrict__ g_state,
+                                                      float* __restrict__ g_action, float* __restrict__ g_lr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KinIn k = load_agent(state, action, lr, model, uniform_model, i);
+    const Controls c = controls(k, p);
+    const float4 g = reinterpret_cast<const float4*>(grad_out)[i];   // d/d(x', y', psi', v')
+    const float v = k.v + c.acc * p.dt;
+    const float dt = p.dt;
+    float gv, gpsi, gang, glr = 0.0f;
+    if (k.model == TDS_MODEL_UNICYCLE) {
+        float s, co;
+        tds::sincos_cr(k.psi, s, co);
+        gv = g.w + g.x * co * dt + g.y * s * dt;
+        gpsi = g.z + (g.y * v * co - g.x * v * s) * dt;
+        gang = g.z * dt;
+    } else {
+        float s, co, sb, cb;
+        tds::sincos_cr(k.psi + c.ang, s, co);
+        tds::sincos_cr(c.ang, sb, cb);
+        const float inv_lr = 1.0f / k.lr;
+        gv = g.w + g.x * co * dt + g.y * s * dt + g.z * sb * dt * inv_lr;
+        const float gth = (g.y * v * co - g.x * v * s) * dt;
+        gpsi = g.z + gth;
+        gang = gth + g.z * v * cb * dt * inv_lr;
+        glr = -g.z * v * sb * dt * inv_lr * inv_lr;
+    }
+    // v' = v + acc dt; with the no-reversing clamp acc = -v/dt, so d v'/d v = 0 and d v'/d a0 = 0
+    float gacc = gv * dt;
+    float gv_in = gv;
+    if (c.reversing) { gv_in = gv - gacc / dt; gacc = 0.0f; }
+    if (p.left_handed) gang = -gang;
+    const float ang_scale = k.model == TDS_MODEL_UNICYCLE ? p.max_yaw_rate : p.max_steering;
+    if (g_state) reinterpret_cast<float4*>(g_state)[i] = make_float4(g.x, g.y, gpsi, gv_in);
+    if (g_action) reinterpret_cast<float2*>(g_action)[i] = make_float2(gacc * p.max_acceleration, gang * ang_scale);
+    if (g_lr) g_lr[i] = glr;
+}
+
+int check(const float* state, const float* action, int64_t n, const tds_kinematic_params_t* p, int32_t uniform_model) {
+    TDS_REQUIRE(state && action && p, "kinematic: null pointer");
+    TDS_REQUIRE(n >= 0, "kinematic: negative n");
+    TDS_REQUIRE(uniform_model >= 0 && uniform_model <= TDS_MODEL_UNICYCLE, "kinematic: unknown model %d", uniform_model);
+    TDS_REQUIRE(p->dt > 0.0f, "kinematic: dt must be positive");
+    return TDS_OK;
+}
+
+}  // namespace
+
+extern "C" int tds_kinematic_step_fwd(const float* d_state, const float* d_action, const float* d_lr,
+                                      const int32_t* d_model, int32_t uniform_model, int64_t n,
+                                      const tds_kinematic_params_t* params, float* d_out_state, void* stream) {
+    if (n == 0) return TDS_OK;
+    if (int e = check(d_state, d_action, n, params, uniform_model)) return e;
+    TDS_REQUIRE(d_out_state, "kinematic: null output");
+    if (n == 0) return TDS_OK;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    kin_fwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_state, d_action, d_lr, d_model, uniform_model, n,
+                                                                *params, d_out_state);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_kinematic_step_bwd(const float* d_state, const float* d_action, const float* d_lr,
+                                      const int32_t* d_model, int32_t uniform_model, int64_t n,
+                                      const tds_kinematic_params_t* params, const float* d_grad_out,
+                                      float* d_grad_state, float* d_grad_action, float* d_grad_lr, void* stream) {
+    if (n == 0) return TDS_OK;
+    if (int e = check(d_state, d_action, n, params, uniform_model)) return e;
+    TDS_REQUIRE(d_grad_out, "kinematic: null grad_out");
+    if (n == 0) return TDS_OK;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    kin_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_state, d_action, d_lr, d_model, uniform_model, n,
+                                                                *params, d_grad_out, d_grad_state, d_grad_action,
+                                                                d_grad_lr);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}

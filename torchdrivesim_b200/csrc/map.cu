@@ -1,0 +1,204 @@
+// Host-side construction of the per-map grids (tds_map_create).  Runs once per map; nothing here
+// is on the per-step path.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "tds_map.cuh"
+
+namespace tds {
+
+int gather_maps(const tds_map_t* const* maps, int32_t n_maps, MapSetDev& out) {
+    TDS_REQUIRE(maps && n_maps >= 1 && n_maps <= TDS_MAX_MAPS, "n_maps must be in [1,%d]", TDS_MAX_MAPS);
+    int dev = -1;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < n_maps; i++) {
+        TDS_REQUIRE(maps[i], "null map handle at index %d", i);
+        TDS_REQUIRE(maps[i]->device == dev, "map %d lives on device %d, current device is %d", i, maps[i]->device, dev);
+        out.m[i] = maps[i]->dev;
+    }
+    for (int i = n_maps; i < TDS_MAX_MAPS; i++) out.m[i] = maps[0]->dev;
+    return TDS_OK;
+}
+
+}  // namespace tds
+
+namespace {
+
+template <class T>
+bool upload(const std::vector<T>& h, void** d, int64_t& bytes) {
+    const size_t n = std::max<size_t>(h.size(), 1) * sizeof(T);
+    if (cudaMalloc(d, n) != cudaSuccess) return false;
+    if (!h.empty() && cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    bytes += (int64_t)n;
+    return true;
+}
+
+}  // namespace
+
+extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int32_t* h_faces, int32_t nf,
+                                     const uint8_t* h_face_class, float raster_cell, float offroad_cell) {
+    using namespace tds;
+    if (!h_verts || !h_faces || !h_face_class || nv < 0 || nf < 0) {
+        fail(TDS_ERR_INVALID_ARGUMENT, "map_create: null pointer or negative size");
+        return nullptr;
+    }
+    if (raster_cell <= 0.f) raster_cell = 8.0f;
+    if (offroad_cell <= 0.f) offroad_cell = 4.0f;
+    for (int f = 0; f < nf; f++) {
+        for (int k = 0; k < 3; k++) {
+            const int v = h_faces[3 * f + k];
+            if (v < 0 || v >= nv) {
+                fail(TDS_ERR_INVALID_ARGUMENT, "map_create: face %d references vertex %d (nv=%d)", f, v, nv);
+                return nullptr;
+            }
+        }
+        if (h_face_class[f] >= TDS_MAX_CLASSES) {
+            fail(TDS_ERR_INVALID_ARGUMENT, "map_create: face class %d >= %d", (int)h_face_class[f], TDS_MAX_CLASSES);
+            return nullptr;
+        }
+    }
+    float minx = 0.f, miny = 0.f, maxx = 1.f, maxy = 1.f;
+    if (nv > 0) {
+        minx = maxx = h_verts[0];
+        miny = maxy = h_verts[1];
+        for (int v = 0; v < nv; v++) {
+            minx = std::min(minx, h_verts[2 * v]); maxx = std::max(maxx, h_verts[2 * v]);
+            miny = std::min(miny, h_verts[2 * v + 1]); maxy = std::max(maxy, h_verts[2 * v + 1]);
+        }
+    }
+    tds_map* m = new tds_map();
+    MapDev& d = m->dev;
+    for (auto& a : m->allocations) a = nullptr;
+    cudaGetDevice(&m->device);
+    int64_t bytes = 0;
+
+    // ---------------- slots
+    int slot_of[TDS_MAX_CLASSES];
+    std::fill(slot_of, slot_of + TDS_MAX_CLASSES, -1);
+    int n_slots = 0;
+    for (int f = 0; f < nf; f++) {
+        if (slot_of[h_face_class[f]] < 0) {
+            if (n_slots == kMaxSlots) {
+                fail(TDS_ERR_UNSUPPORTED, "map_create: more than %d distinct static classes", kMaxSlots);
+                delete m;
+                return nullptr;
+            }
+            slot_of[h_face_class[f]] = n_slots++;
+        }
+    }
+    // ---------------- raster grid (vertex binning)
+    d.rcs = raster_cell;
+    d.rinv = 1.0f / raster_cell;
+    d.rx0 = minx - 0.5f * raster_cell;
+    d.ry0 = miny - 0.5f * raster_cell;
+    d.rgx = std::max(1, (int)std::floor((maxx - d.rx0) / raster_cell) + 1);
+    d.rgy = std::max(1, (int)std::floor((maxy - d.ry0) / raster_cell) + 1);
+    d.n_slots = n_slots;
+    for (int c = 0; c < TDS_MAX_CLASSES; c++) d.slot_of_class[c] = slot_of[c];
+    const int nc = d.rgx * d.rgy;
+    auto rcell_of = [&](float x, float y) {
+        int cx = (int)std::floor(((double)x - d.rx0) / raster_cell), cy = (int)std::floor(((double)y - d.ry0) / raster_cell);
+        cx = std::min(std::max(cx, 0), d.rgx - 1);
+        cy = std::min(std::max(cy, 0), d.rgy - 1);
+        return cy * d.rgx + cx;
+    };
+    struct Rec { int key; int face; int own; };
+    std::vector<Rec> recs;
+    recs.reserve((size_t)nf * 2);
+    for (int f = 0; f < nf; f++) {
+        int cell[3];
+        for (int k = 0; k < 3; k++) cell[k] = rcell_of(h_verts[2 * h_faces[3 * f + k]], h_verts[2 * h_faces[3 * f + k] + 1]);
+        const int slot = slot_of[h_face_class[f]];
+        for (int k = 0; k < 3; k++) {
+            bool seen = false;
+            for (int j = 0; j < k; j++) seen |= cell[j] == cell[k];
+            if (seen) continue;
+            int own = 0;
+            for (int j = 0; j < 3; j++) own |= (cell[j] == cell[k]) << j;
+            recs.push_back({slot * nc + cell[k], f, own});
+        }
+    }
+    std::stable_sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.key < b.key; });
+    std::vector<int32_t> rcell((size_t)n_slots * nc + 1, 0);
+    for (const Rec& r : recs) rcell[r.key + 1]++;
+    for (size_t i = 0; i + 1 < rcell.size(); i++) rcell[i + 1] += rcell[i];
+    std::vector<float> recdata(recs.size() * 8, 0.f);
+    for (size_t i = 0; i < recs.size(); i++) {
+        const int f = recs[i].face;
+        for (int k = 0; k < 3; k++) {
+            recdata[8 * i + 2 * k] = h_verts[2 * h_faces[3 * f + k]];
+            recdata[8 * i + 2 * k + 1] = h_verts[2 * h_faces[3 * f + k] + 1];
+        }
+        memcpy(&recdata[8 * i + 6], &recs[i].own, sizeof(int));
+    }
+    // ---------------- offroad grid (bounding-box binning)
+    d.ocs = offroad_cell;
+    d.oinv = 1.0f / offroad_cell;
+    d.ox0 = minx - 0.5f * offroad_cell;
+    d.oy0 = miny - 0.5f * offroad_cell;
+    d.ogx = std::max(1, (int)std::floor((maxx - d.ox0) / offroad_cell) + 1);
+    d.ogy = std::max(1, (int)std::floor((maxy - d.oy0) / offroad_cell) + 1);
+    d.nf = nf;
+    const int onc = d.ogx * d.ogy;
+    auto oc = [&](float v, float o, int g) {
+        int c = (int)std::floor(((double)v - o) / offroad_cell);
+        return std::min(std::max(c, 0), g - 1);
+    };
+    std::vector<int32_t> ocell((size_t)onc + 1, 0);
+    std::vector<float> tri((size_t)nf * 6);
+    const float eps = 1e-3f;
+    std::vector<int32_t> oidx, cursor;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            for (int i = 0; i < onc; i++) ocell[i + 1] += ocell[i];
+            cursor.assign(ocell.begin(), ocell.end() - 1);
+            oidx.assign((size_t)ocell[onc], 0);
+        }
+        for (int f = 0; f < nf; f++) {
+            float x[3], y[3];
+            for (int k = 0; k < 3; k++) { x[k] = h_verts[2 * h_faces[3 * f + k]]; y[k] = h_verts[2 * h_faces[3 * f + k] + 1]; }
+            if (pass == 0) for (int k = 0; k < 3; k++) { tri[6 * f + 2 * k] = x[k]; tri[6 * f + 2 * k + 1] = y[k]; }
+            const int cx0 = oc(std::min({x[0], x[1], x[2]}) - eps, d.ox0, d.ogx), cx1 = oc(std::max({x[0], x[1], x[2]}) + eps, d.ox0, d.ogx);
+            const int cy0 = oc(std::min({y[0], y[1], y[2]}) - eps, d.oy0, d.ogy), cy1 = oc(std::max({y[0], y[1], y[2]}) + eps, d.oy0, d.ogy);
+            for (int cy = cy0; cy <= cy1; cy++)
+                for (int cx = cx0; cx <= cx1; cx++) {
+                    if (pass == 0) ocell[cy * d.ogx + cx + 1]++;
+                    else oidx[cursor[cy * d.ogx + cx]++] = f;
+                }
+        }
+    }
+    m->info.offroad_entries = (int32_t)oidx.size();
+    if (!(upload(recdata, &m->allocations[0], bytes) && upload(rcell, &m->allocations[1], bytes) &&
+          upload(tri, &m->allocations[2], bytes) && upload(ocell, &m->allocations[3], bytes) &&
+          upload(oidx, &m->allocations[4], bytes))) {
+        fail(TDS_ERR_CUDA, "map_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        tds_map_destroy(m);
+        return nullptr;
+    }
+    d.rec = (const float4*)m->allocations[0];
+    d.rcell = (const int32_t*)m->allocations[1];
+    d.tri = (const float*)m->allocations[2];
+    d.ocell = (const int32_t*)m->allocations[3];
+    d.oidx = (const int32_t*)m->allocations[4];
+    m->info.n_verts = nv; m->info.n_faces = nf;
+    m->info.raster_gx = d.rgx; m->info.raster_gy = d.rgy; m->info.raster_records = (int32_t)recs.size();
+    m->info.offroad_gx = d.ogx; m->info.offroad_gy = d.ogy;
+    m->info.raster_cell = raster_cell; m->info.offroad_cell = offroad_cell;
+    m->info.min_x = minx; m->info.min_y = miny; m->info.max_x = maxx; m->info.max_y = maxy;
+    m->info.device_bytes = bytes;
+    return m;
+}
+
+extern "C" void tds_map_destroy(tds_map_t* map) {
+    if (!map) return;
+    for (auto& a : map->allocations) if (a) cudaFree(a);
+    delete map;
+}
+
+extern "C" int tds_map_info(const tds_map_t* map, tds_map_info_t* out) {
+    TDS_REQUIRE(map && out, "map_info: null pointer");
+    *out = map->info;
+    return TDS_OK;
+}

@@ -1,0 +1,236 @@
+// Offroad infraction: squared distance from the four box corners to the nearest map face.
+//
+// Reference: offroad_infraction_loss (torchdrivesim/infractions.py:176-229, pure-torch branch) and
+// point_to_mesh_distance_pt (infractions.py:86-173), which expand the mesh to a
+// [B*A*4, F, 3, 3] tensor (290 TB at 1024 x 64 agents on Town01).  Here one thread owns one
+// corner and walks the per-map uniform grid in expanding rings; the per-face arithmetic is the
+// reference's, operation for operation (fp32, no FMA), so the minimum over the visited faces is
+// the reference's minimum over all faces.  The grid (~1 MB per map) is L2 resident; HBM traffic is
+// the 28 B per agent of state/size in and 4 B out.
+#include <math_constants.h>
+
+#include "tds_map.cuh"
+
+namespace {
+
+using tds::MapDev;
+using tds::MapSetDev;
+
+struct EdgeHit {
+    float d2, qx, qy;   // squared distance and closest point
+};
+
+__device__ __forceinline__ EdgeHit edge_dist2(float px, float py, float ax, float ay, float bx, float by) {
+    const float abx = bx - ax, aby = by - ay;
+    const float l2 = abx * abx + aby * aby;
+    const float t = (abx * (px - ax) + aby * (py - ay)) / (l2 + 1e-8f);
+    const float tt = fminf(fmaxf(t, 0.f), 1.f);
+    EdgeHit h;
+    h.qx = ax + tt * abx;
+    h.qy = ay + tt * aby;
+    if (l2 <= 1e-8f) { h.qx = bx; h.qy = by; }     // degenerate edge: distance to v1 (infractions.py:156-158)
+    const float dx = px - h.qx, dy = py - h.qy;
+    h.d2 = dx * dx + dy * dy;
+    return h;
+}
+
+// infractions.py:100-169 for z = 0: 0 inside a non-degenerate triangle, else min edge distance
+__device__ __forceinline__ float point_tri_dist2(float px, float py, float x0, float y0, float x1, float y1, float x2,
+                                                 float y2) {
+    const float ax = x2 - x0, ay = y2 - y0, bx = x1 - x0, by = y1 - y0;
+    const float cz = ax * by - ay * bx;
+    const float p2x = px - x0, p2y = py - y0;
+    const float d00 = bx * bx + by * by;
+    const float d01 = bx * ax + by * ay;
+    const float d11 = ax * ax + ay * ay;
+    const float d20 = p2x * bx + p2y * by;
+    const float d21 = p2x * ax + p2y * ay;
+    const float denom = d00 * d11 - d01 * d01 + 1e-8f;
+    const float w1 = (d11 * d20 - d01 * d21) / denom;
+    const float w2 = (d00 * d21 - d01 * d20) / denom;
+    const float w0 = 1.0f - w1 - w2;
+    const bool inside = (0.f <= w0) & (w0 <= 1.f) & (0.f <= w1) & (w1 <= 1.f) & (0.f <= w2) & (w2 <= 1.f);
+    const float area = fabsf(bx * ay - by * ax) / 2.0f;
+    const bool cond = inside & !(area < 5e-3f) & (fabsf(cz) > 1e-8f);
+    if (cond) return 0.0f;
+    const float e01 = edge_dist2(px, py, x0, y0, x1, y1).d2;
+    const float e02 = edge_dist2(px, py, x0, y0, x2, y2).d2;
+    const float e12 = edge_dist2(px, py, x1, y1, x2, y2).d2;
+    return fminf(fminf(e01, e02), e12);
+}
+
+__device__ __forceinline__ void visit_cell(const MapDev& m, int cx, int cy, float px, float py, float& best, int& bf) {
+    const int c = cy * m.ogx + cx;
+    const int e0 = m.ocell[c], e1 = m.ocell[c + 1];
+    for (int e = e0; e < e1; e++) {
+        const int f = m.oidx[e];
+        const float2* t = reinterpret_cast<const float2*>(m.tri + 6 * (size_t)f);
+        const float2 v0 = __ldg(t), v1 = __ldg(t + 1), v2 = __ldg(t + 2);
+        const float d = point_tri_dist2(px, py, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
+        if (d < best || (d == best && f < bf)) { best = d; bf = f; }
+    }
+}
+
+// min over all faces of the map; returns the squared distance, *face = argmin (lowest index on ties)
+__device__ float nearest_face(const MapDev& m, float px, float py, int* face) {
+    float best = CUDART_INF_F;
+    int bf = -1;
+    if (m.nf == 0) { *face = -1; return 0.0f; }
+    const float fx = floorf((px - m.ox0) * m.oinv), fy = floorf((py - m.oy0) * m.oinv);
+    const int cx = (int)fminf(fmaxf(fx, -1.0e6f), 1.0e6f), cy = (int)fminf(fmaxf(fy, -1.0e6f), 1.0e6f);
+    const int kmax = max(max(cx, m.ogx - 1 - cx), max(cy, m.ogy - 1 - cy));
+    // first ring that touches the grid at all
+    int k0 = max(max(-cx, cx - (m.ogx - 1)), max(-cy, cy - (m.ogy - 1)));
+    k0 = max(k0, 0);
+    for (int k = k0; k <= kmax; k++) {
+        const int xa = max(cx - k, 0), xb = min(cx + k, m.ogx - 1);
+        const int ya = max(cy - k, 0), yb = min(cy + k, m.ogy - 1);
+        if (k == 0) {
+            visit_cell(m, cx, cy, px, py, best, bf);
+        } else {
+            if (cy - k >= 0) for (int x = xa; x <= xb; x++) visit_cell(m, x, cy - k, px, py, best, bf);
+            if (cy + k < m.ogy) for (int x = xa; x <= xb; x++) visit_cell(m, x, cy + k, px, py, best, bf);
+            const int y0 = max(cy - k + 1, 0), y1 = min(cy + k - 1, m.ogy - 1);
+            if (cx - k >= 0) for (int y = y0; y <= y1; y++) visit_cell(m, cx - k, y, px, py, best, bf);
+            if (cx + k < m.ogx) for (int y = y0; y <= y1; y++) visit_cell(m, cx + k, y, px, py, best, bf);
+        }
+        // every face with a point closer than k cells has been visited (1 mm slack for the cell
+        // assignment of p itself)
+        const float reach = fmaxf((float)k * m.ocs - 1e-3f, 0.0f);
+        if (best <= reach * reach) break;
+    }
+    if (best != best) best = 0.0f;      // nan_to_num, infractions.py:171
+    *face = bf;
+    return best;
+}
+
+__device__ __forceinline__ void corner_of(const float* st, const float* lw, int k, float& px, float& py, float& s, float& c) {
+    // box2corners_th, _iou_utils.py:270-299: (+,+), (-,+), (-,-), (+,-) rotated by psi
+    const float sx = (k == 0 || k == 3) ? 0.5f : -0.5f;
+    const float sy = (k < 2) ? 0.5f : -0.5f;
+    tds::sincos_cr(st[2], s, c);
+    const float ux = sx * lw[0], uy = sy * lw[1];
+    px = (ux * c + uy * (-s)) + st[0];
+    py = (ux * s + uy * c) + st[1];
+}
+
+__global__ void __launch_bounds__(128) offroad_fwd_kernel(MapSetDev maps, const int32_t* __restrict__ env_map,
+                                                          const float* __restrict__ state, const float* __restrict__ lenwid,
+                                                          const uint8_t* __restrict__ present, int B, int A, float thr,
+                                                          float* __restrict__ out, int32_t* __restrict__ face) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t agent = t >> 2;
+    const int k = (int)(t & 3);
+    const bool valid = agent < (int64_t)B * A;
+    float v = 0.0f;
+    int bf = -1;
+    if (valid) {
+        const int b = (int)(agent / A);
+        const bool here = present ? present[agent] != 0 : true;
+        if (here) {
+            const MapDev& m = maps.m[env_map ? env_map[b] : 0];
+            float px, py, s, c;
+            corner_of(state + 4 * agent, lenwid + 2 * agent, k, px, py, s, c);
+            const float d2 = nearest_face(m, px, py, &bf);
+            v = d2 > thr ? d2 : 0.0f;           // F.threshold(d2, thr, 0), infractions.py:172
+        }
+        if (face) face[t] = bf;
+    }
+    // sum of the 4 corners (lanes 4a..4a+3), in corner order
+    const unsigned full = 0xffffffffu;
+    const int base = (threadIdx.x & 31) & ~3;
+    const float v0 = __shfl_sync(full, v, base), v1 = __shfl_sync(full, v, base + 1);
+    const float v2 = __shfl_sync(full, v, base + 2), v3 = __shfl_sync(full, v, base + 3);
+    if (valid && k == 0) out[agent] = ((v0 + v1) + v2) + v3;
+}
+
+__global__ void __launch_bounds__(128) offroad_bwd_kernel(MapSetDev maps, const int32_t* __restrict__ env_map,
+                                                          const float* __restrict__ state, const float* __restrict__ lenwid,
+                                                          const uint8_t* __restrict__ present, int B, int A, float thr,
+                                                          const int32_t* __restrict__ face, const float* __restrict__ gout,
+                                                          float* __restrict__ g_state, float* __restrict__ g_lenwid) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t agent = t >> 2;
+    const int k = (int)(t & 3);
+    const bool valid = agent < (int64_t)B * A;
+    float gx = 0.f, gy = 0.f, gpsi = 0.f, gl = 0.f, gw = 0.f;
+    if (valid) {
+        const int b = (int)(agent / A);
+        const bool here = present ? present[agent] != 0 : true;
+        const int f = face[t];
+        if (here && f >= 0) {
+            const MapDev& m = maps.m[env_map ? env_map[b] : 0];
+            const float* st = state + 4 * agent;
+            const float* lw = lenwid + 2 * agent;
+            float px, py, s, c;
+            corner_of(st, lw, k, px, py, s, c);
+            const float2* tr = reinterpret_cast<const float2*>(m.tri + 6 * (size_t)f);
+            const float2 v0 = tr[0], v1 = tr[1], v2 = tr[2];
+            const float d2 = point_tri_dist2(px, py, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
+            if (d2 > thr) {
+                // d2 is the smallest of the three edge distances; d d2 / d p = 2 (p - q)
+                EdgeHit h = edge_dist2(px, py, v0.x, v0.y, v1.x, v1.y);
+                const EdgeHit h2 = edge_dist2(px, py, v0.x, v0.y, v2.x, v2.y);
+                const EdgeHit h3 = edge_dist2(px, py, v1.x, v1.y, v2.x, v2.y);
+                if (h2.d2 < h.d2) h = h2;
+                if (h3.d2 < h.d2) h = h3;
+                const float g = gout[agent];
+                const float dpx = 2.0f * (px - h.qx) * g, dpy = 2.0f * (py - h.qy) * g;
+                const float sx = (k == 0 || k == 3) ? 0.5f : -0.5f;
+                const float sy = (k < 2) ? 0.5f : -0.5f;
+                const float ux = sx * lw[0], uy = sy * lw[1];
+                gx = dpx;
+                gy = dpy;
+                gpsi = dpx * (-ux * s - uy * c) + dpy * (ux * c - uy * s);
+                gl = sx * (dpx * c + dpy * s);
+                gw = sy * (dpy * c - dpx * s);
+            }
+        }
+    }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        gx += __shfl_xor_sync(full, gx, o);
+        gy += __shfl_xor_sync(full, gy, o);
+        gpsi += __shfl_xor_sync(full, gpsi, o);
+        gl += __shfl_xor_sync(full, gl, o);
+        gw += __shfl_xor_sync(full, gw, o);
+    }
+    if (valid && k == 0) {
+        if (g_state) reinterpret_cast<float4*>(g_state)[agent] = make_float4(gx, gy, gpsi, 0.0f);
+        if (g_lenwid) reinterpret_cast<float2*>(g_lenwid)[agent] = make_float2(gl, gw);
+    }
+}
+
+}  // namespace
+
+extern "C" int tds_offroad_fwd(const tds_map_t* const* maps, int32_t n_maps, const int32_t* d_env_map,
+                               const float* d_state, const float* d_lenwid, const uint8_t* d_present,
+                               int32_t B, int32_t A, float threshold, float* d_out, int32_t* d_face, void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0, "offroad: negative size");
+    if (B == 0 || A == 0) return TDS_OK;
+    TDS_REQUIRE(d_state && d_lenwid && d_out, "offroad: null pointer");
+    MapSetDev set;
+    if (int e = tds::gather_maps(maps, n_maps, set)) return e;
+    const int64_t threads = (int64_t)B * A * 4;
+    offroad_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        set, d_env_map, d_state, d_lenwid, d_present, B, A, threshold, d_out, d_face);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_offroad_bwd(const tds_map_t* const* maps, int32_t n_maps, const int32_t* d_env_map,
+                               const float* d_state, const float* d_lenwid, const uint8_t* d_present,
+                               int32_t B, int32_t A, float threshold, const int32_t* d_face, const float* d_grad_out,
+                               float* d_grad_state, float* d_grad_lenwid, void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0, "offroad_bwd: negative size");
+    if (B == 0 || A == 0) return TDS_OK;
+    TDS_REQUIRE(d_state && d_lenwid && d_face && d_grad_out, "offroad_bwd: null pointer");
+    MapSetDev set;
+    if (int e = tds::gather_maps(maps, n_maps, set)) return e;
+    const int64_t threads = (int64_t)B * A * 4;
+    offroad_bwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        set, d_env_map, d_state, d_lenwid, d_present, B, A, threshold, d_face, d_grad_out, d_grad_state, d_grad_lenwid);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}

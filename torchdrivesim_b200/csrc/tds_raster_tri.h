@@ -1,0 +1,144 @@
+// Integer triangle coverage rule of the reference's cv2 backend, in closed form.
+//
+// The reference draws every triangle with cv2.fillConvexPoly(img_f32, pts_int32, shift=0,
+// lineType=LINE_AA) (torchdrivesim/rendering/cv2.py:59).  On a float32 image that is:
+//   outline : three 8-connected LineIterator segments (clipLine + Bresenham, left-to-right)
+//   fill    : 16.16 fixed-point scan conversion, rows [y_top, y_bottom-1] only
+// This header enumerates exactly that pixel set for ONE triangle without walking rows from
+// the top vertex: each row's span is evaluated directly from the two active edges, so a GPU
+// thread (or any subset of rows) can be processed independently.
+//
+// It is host/device code so the very same functions are unit-tested on the CPU against the
+// live cv2 module (tests/test_raster_rule.py) and used by the sm_100a kernel (raster.cu).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TDS_HD __host__ __device__ __forceinline__
+#else
+#define TDS_HD static inline
+#endif
+
+namespace tds {
+
+// OpenCV clipLine on the rectangle [0,W-1]x[0,H-1]; returns false when nothing is left.
+// Integer division truncating toward zero reproduces OpenCV's (int64)(double * int / int)
+// exactly for |operands| < 2^26 (the quotient of two such integers is never within one
+// double ulp of an integer it does not equal).
+TDS_HD bool clip_line(int W, int H, long long& x1, long long& y1, long long& x2, long long& y2) {
+    const long long right = W - 1, bottom = H - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += ((a - y1) * (x2 - x1)) / (y2 - y1);
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += ((a - y2) * (x2 - x1)) / (y2 - y1);
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += ((a - x1) * (y2 - y1)) / (x2 - x1);
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += ((a - x2) * (y2 - y1)) / (x2 - x1);
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// 8-connected line from (xa,ya) to (xb,yb), both endpoints inclusive.  plot(x, y).
+template <class Plot>
+TDS_HD void draw_line8(int W, int H, int xa, int ya, int xb, int yb, Plot&& plot) {
+    if ((unsigned)xa >= (unsigned)W || (unsigned)xb >= (unsigned)W ||
+        (unsigned)ya >= (unsigned)H || (unsigned)yb >= (unsigned)H) {
+        long long x1 = xa, y1 = ya, x2 = xb, y2 = yb;
+        if (!clip_line(W, H, x1, y1, x2, y2)) return;
+        xa = (int)x1; ya = (int)y1; xb = (int)x2; yb = (int)y2;
+    }
+    int dx = xb - xa, dy = yb - ya;
+    int x = xa, y = ya;
+    if (dx < 0) { dx = -dx; dy = -dy; x = xb; y = yb; }
+    int sy = 1;
+    if (dy < 0) { dy = -dy; sy = -1; }
+    const bool vert = dy > dx;
+    if (vert) { int t = dx; dx = dy; dy = t; }
+    int err = dx - (dy + dy);
+    const int plus = dx + dx, minus = -(dy + dy);
+    for (int i = 0; i <= dx; i++) {
+        plot(x, y);
+        const bool m = err < 0;
+        err += minus + (m ? plus : 0);
+        if (vert) { y += sy; x += m ? 1 : 0; }
+        else      { x += 1;  y += m ? sy : 0; }
+    }
+}
+
+// slope of edge a->b (a.y < b.y) in 16.16, C-style truncating division as in FillConvexPoly.
+// I = int is exact while |coordinates| < 8192 (|num| < 2^31); I = long long otherwise.
+template <class I>
+TDS_HD I edge_dx(int ax, int ay, int bx, int by) {
+    const I dy = (I)by - ay;
+    const I num = ((((I)bx - ax) << 16) * 2) + dy;
+    return num / (2 * dy);
+}
+
+template <class I, class Span>
+TDS_HD void fill_rows(int W, int H, int tx, int ty, int mx, int my, int bx, int by, Span&& span) {
+    const int ylo = ty > 0 ? ty : 0;
+    const int yhi = (by - 1) < (H - 1) ? (by - 1) : (H - 1);
+    if (ylo > yhi) return;
+    const I dTB = edge_dx<I>(tx, ty, bx, by);
+    const I dTM = my > ty ? edge_dx<I>(tx, ty, mx, my) : 0;
+    const I dMB = by > my ? edge_dx<I>(mx, my, bx, by) : 0;
+    for (int y = ylo; y <= yhi; y++) {
+        const I xa = ((I)tx << 16) + (I)(y - ty) * dTB;
+        const I xb = y < my ? ((I)tx << 16) + (I)(y - ty) * dTM : ((I)mx << 16) + (I)(y - my) * dMB;
+        const I xl = xa < xb ? xa : xb, xr = xa < xb ? xb : xa;
+        int c1 = (int)((xl + 32768) >> 16), c2 = (int)((xr + 32768) >> 16);
+        if (c2 >= 0 && c1 < W) {
+            if (c1 < 0) c1 = 0;
+            if (c2 >= W) c2 = W - 1;
+            span(y, c1, c2);
+        }
+    }
+}
+
+// span(y, x_first, x_last) is called once per filled row with clamped inclusive columns.
+// plot(x, y) is called for every outline pixel.
+template <class Plot, class Span>
+TDS_HD void draw_triangle(int W, int H, int x0, int y0, int x1, int y1, int x2, int y2,
+                          Plot&& plot, Span&& span) {
+    // outline: v2->v0, v0->v1, v1->v2
+    draw_line8(W, H, x2, y2, x0, y0, plot);
+    draw_line8(W, H, x0, y0, x1, y1, plot);
+    draw_line8(W, H, x1, y1, x2, y2, plot);
+    // sort by y: (tx,ty) top, (mx,my) middle, (bx,by) bottom
+    int tx = x0, ty = y0, mx = x1, my = y1, bx = x2, by = y2, t;
+    if (my < ty) { t = tx; tx = mx; mx = t; t = ty; ty = my; my = t; }
+    if (by < my) { t = mx; mx = bx; bx = t; t = my; my = by; by = t; }
+    if (my < ty) { t = tx; tx = mx; mx = t; t = ty; ty = my; my = t; }
+    int xmin = x0 < x1 ? x0 : x1; xmin = xmin < x2 ? xmin : x2;
+    int xmax = x0 > x1 ? x0 : x1; xmax = xmax > x2 ? xmax : x2;
+    if (xmax < 0 || by < 0 || xmin >= W || ty >= H) return;   // bbox misses the image: outline only
+    if (by == ty) return;                                     // no fill rows
+    const bool small = xmin > -8192 && xmax < 8192 && ty > -8192 && by < 8192;
+    if (small) fill_rows<int>(W, H, tx, ty, mx, my, bx, by, span);
+    else fill_rows<long long>(W, H, tx, ty, mx, my, bx, by, span);
+}
+
+}  // namespace tds

@@ -1,0 +1,169 @@
+"""Static maps: the triangle mesh of a location plus its device-side acceleration grids.
+
+Loading mirrors the reference's data formats: `*_mesh.json` in the BirdviewMesh schema
+(torchdrivesim/mesh.py:700-719), stoplines json (torchdrivesim/map.py:203-229), or the compact npz
+fixtures under tests/golden/maps.  A `StaticMap` replaces the batch-expanded `road_mesh`
+(`mesh.expand(B)`, simulator.py) by ONE copy per GPU shared by all environments through `env_map`.
+"""
+import ctypes
+import json
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .palette import class_id
+
+
+class StaticMap:
+    """verts [V,2] f32, faces [F,3] i32, per-face category name index; device handles are created lazily
+    (one per CUDA device) by `handle(device)`."""
+
+    def __init__(self, verts: np.ndarray, faces: np.ndarray, categories: Sequence[str], vert_category: np.ndarray,
+                 name: str = "map", left_handed: bool = False, stoplines: Optional[np.ndarray] = None,
+                 stopline_types: Optional[Sequence[str]] = None, raster_cell: float = 8.0, offroad_cell: float = 4.0):
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 2)
+        self.faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+        self.categories = [str(c) for c in categories]
+        self.vert_category = np.ascontiguousarray(vert_category).reshape(-1).astype(np.int64)
+        self.name = name
+        self.left_handed = bool(left_handed)
+        self.stoplines = np.zeros((0, 5), np.float32) if stoplines is None else np.asarray(stoplines, np.float32)
+        self.stopline_types = [] if stopline_types is None else [str(s) for s in stopline_types]
+        self.raster_cell = raster_cell
+        self.offroad_cell = offroad_cell
+        # a face takes the colour / level of its FIRST vertex (rendering/cv2.py:44-47, 58)
+        if self.faces.shape[0]:
+            self.face_category = self.vert_category[self.faces[:, 0]]
+        else:
+            self.face_category = np.zeros((0,), np.int64)
+        self._handles: Dict[int, int] = {}
+
+    # ---- constructors -------------------------------------------------------------------------
+    @classmethod
+    def from_npz(cls, path: str, **kw) -> "StaticMap":
+        d = np.load(path)
+        return cls(d["verts"], d["faces"], [str(c) for c in d["categories"]], d["vert_category"],
+                   name=os.path.splitext(os.path.basename(path))[0], left_handed=bool(d["left_handed"]),
+                   stoplines=d["stoplines"], stopline_types=[str(s) for s in d["stopline_types"]], **kw)
+
+    @classmethod
+    def from_mesh_json(cls, path: str, stoplines_path: Optional[str] = None, left_handed: bool = False, **kw) -> "StaticMap":
+        """Reads the reference's `{name}_mesh.json` (BirdviewMesh.serialize, mesh.py:700-719)."""
+        with open(path) as f:
+            d = json.load(f)
+        verts = np.asarray(d["verts"], np.float32)[0][:, :2]
+        faces = np.asarray(d["faces"], np.int32)[0]
+        vcat = np.asarray(d["vert_category"])[0]
+        lines, types = None, None
+        if stoplines_path is not None:
+            with open(stoplines_path) as f:
+                sl = json.load(f)
+            norm = {"traffic-light": "traffic_light", "stop-sign": "stop_sign", "yield-sign": "yield_sign",
+                    "yield": "yield_sign"}
+            types = [norm.get(s["agent_type"], s["agent_type"]) for s in sl]
+            lines = np.array([[s["x"], s["y"], s["length"], s["width"], s["orientation"]] for s in sl], np.float32)
+        return cls(verts, faces, d["categories"], vcat, name=os.path.basename(path), left_handed=left_handed,
+                   stoplines=lines, stopline_types=types, **kw)
+
+    @classmethod
+    def from_birdview_mesh(cls, mesh, batch_index: int = 0, **kw) -> "StaticMap":
+        """Accepts a reference `BirdviewMesh` (duck-typed: verts [B,V,2+], faces [B,F,3], categories,
+        vert_category [B,V]); takes one batch element."""
+        verts = mesh.verts[batch_index][:, :2].detach().cpu().numpy()
+        faces = mesh.faces[batch_index].detach().cpu().numpy()
+        vcat = mesh.vert_category[batch_index].detach().cpu().numpy()
+        return cls(verts, faces, list(mesh.categories), vcat, **kw)
+
+    # ---- queries ------------------------------------------------------------------------------
+    @property
+    def face_category_names(self) -> List[str]:
+        return [self.categories[i] for i in self.face_category]
+
+    def category_verts(self, name: str) -> np.ndarray:
+        return self.verts[self.vert_category == self.categories.index(name)]
+
+    @property
+    def world_center(self) -> np.ndarray:
+        """Centre of the bounding box of the 'road' category (mesh.py:860-868), else of everything."""
+        v = self.category_verts("road") if "road" in self.categories else self.verts
+        if v.shape[0] == 0:
+            return np.zeros(2, np.float32)
+        return ((v.min(0) + v.max(0)) / 2).astype(np.float32)
+
+    def traffic_light_poses(self) -> np.ndarray:
+        idx = [i for i, t in enumerate(self.stopline_types) if t == "traffic_light"]
+        return self.stoplines[idx] if idx else np.zeros((0, 5), np.float32)
+
+    # ---- device ---------------------------------------------------------------------------------
+    def handle(self, device) -> int:
+        """tds_map_t* for `device` (built on first use)."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.TdsError("StaticMap needs a CUDA device: there is no CPU implementation")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._handles:
+            lib = _lib.load()
+            face_class = np.ascontiguousarray([class_id(self.categories[c]) for c in self.face_category], np.uint8)
+            with torch.cuda.device(idx):
+                h = lib.tds_map_create(self.verts.ctypes.data_as(ctypes.c_void_p), self.verts.shape[0],
+                                       self.faces.ctypes.data_as(ctypes.c_void_p), self.faces.shape[0],
+                                       face_class.ctypes.data_as(ctypes.c_void_p), self.raster_cell, self.offroad_cell)
+            if not h:
+                raise _lib.TdsError(f"tds_map_create failed: {lib.tds_last_error().decode()}")
+            self._handles[idx] = h
+        return self._handles[idx]
+
+    def info(self, device) -> "_lib.MapInfo":
+        out = _lib.MapInfo()
+        _lib.check(_lib.load().tds_map_info(self.handle(device), ctypes.byref(out)))
+        return out
+
+    def release(self) -> None:
+        lib = _lib.load()
+        for h in self._handles.values():
+            lib.tds_map_destroy(h)
+        self._handles.clear()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class MapSet:
+    """The maps used by a batch: `maps[env_map[b]]` is the map of environment b."""
+
+    def __init__(self, maps: Sequence[StaticMap], env_map: Optional[torch.Tensor] = None):
+        if not 1 <= len(maps) <= _lib.MAX_MAPS:
+            raise _lib.TdsError(f"a batch may use 1..{_lib.MAX_MAPS} distinct maps")
+        self.maps = list(maps)
+        self.env_map = None if env_map is None else env_map.to(torch.int32).contiguous()
+
+    def handles(self, device):
+        arr = (ctypes.c_void_p * len(self.maps))(*[m.handle(device) for m in self.maps])
+        return arr, len(self.maps)
+
+    def env_map_on(self, device) -> Optional[torch.Tensor]:
+        if self.env_map is None:
+            return None
+        if self.env_map.device != torch.device(device):
+            self.env_map = self.env_map.to(device)
+        return self.env_map
+
+    def static_categories(self) -> List[str]:
+        out: List[str] = []
+        for m in self.maps:
+            for c in sorted(set(m.face_category_names)):
+                if c not in out:
+                    out.append(c)
+        return out
+
+    def select(self, idx: torch.Tensor) -> "MapSet":
+        return MapSet(self.maps, None if self.env_map is None else self.env_map[idx.to(self.env_map.device)])
+
+    def extend(self, n: int) -> "MapSet":
+        return MapSet(self.maps, None if self.env_map is None else self.env_map.repeat_interleave(n))

@@ -1,0 +1,247 @@
+"""Functional ops over libtds_b200.so with autograd wiring (kinematics, discs collision, offroad).
+
+Every function takes CUDA tensors in the reference's layouts and launches on the current torch
+stream.  Nothing here has a CPU implementation; `_lib.ptr` raises on CPU tensors.
+"""
+import ctypes
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .maps import MapSet
+
+_F32_HALF_PI = 1.5707963705062866  # float32(pi / 2), the reference's _normalization_factor (kinematic.py:420)
+
+
+def kinematic_params(dt: float = 0.1, max_acceleration: float = 5.0, max_steering: float = math.pi / 2,
+                     max_yaw_rate: float = math.pi / 2, left_handed: bool = False) -> "_lib.KinematicParams":
+    return _lib.KinematicParams(dt, max_acceleration, max_steering, max_yaw_rate, 1 if left_handed else 0)
+
+
+# ------------------------------------------------------------------------------------ kinematics
+class _KinematicStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, action, lr, model, uniform_model, params):
+        lib = _lib.load()
+        shape = state.shape
+        s = _lib.as_f32(state).reshape(-1, 4)
+        a = _lib.as_f32(action).reshape(-1, 2)
+        l = None if lr is None else _lib.as_f32(lr).reshape(-1)
+        m = None if model is None else _lib.as_i32(model).reshape(-1)
+        n = s.shape[0]
+        if a.shape[0] != n or (l is not None and l.shape[0] != n) or (m is not None and m.shape[0] != n):
+            raise _lib.TdsError("kinematic_step: state, action, lr and model must agree on the batch shape")
+        out = torch.empty_like(s)
+        _lib.check(lib.tds_kinematic_step_fwd(_lib.ptr(s), _lib.ptr(a), _lib.ptr(l), _lib.ptr(m), uniform_model, n,
+                                              ctypes.byref(params), _lib.ptr(out), _lib.stream_ptr(s.device)))
+        ctx.save_for_backward(s, a, l, m)
+        ctx.meta = (uniform_model, params, shape, action.shape, None if lr is None else lr.shape)
+        return out.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        s, a, l, m = ctx.saved_tensors
+        uniform_model, params, sshape, ashape, lshape = ctx.meta
+        g = _lib.as_f32(grad_out).reshape(-1, 4)
+        n = s.shape[0]
+        gs = torch.empty_like(s)
+        ga = torch.empty_like(a)
+        gl = None if l is None else torch.empty_like(l)
+        _lib.check(lib.tds_kinematic_step_bwd(_lib.ptr(s), _lib.ptr(a), _lib.ptr(l), _lib.ptr(m), uniform_model, n,
+                                              ctypes.byref(params), _lib.ptr(g), _lib.ptr(gs), _lib.ptr(ga), _lib.ptr(gl),
+                                              _lib.stream_ptr(s.device)))
+        return gs.reshape(sshape), ga.reshape(ashape), (None if gl is None else gl.reshape(lshape)), None, None, None
+
+
+def kinematic_step(state: torch.Tensor, action: torch.Tensor, lr: Optional[torch.Tensor],
+                   model: Optional[torch.Tensor] = None, uniform_model: int = _lib.MODEL_BICYCLE,
+                   params: Optional["_lib.KinematicParams"] = None) -> torch.Tensor:
+    """state [...,4], action [...,2], lr [...], model [...] int (or None: `uniform_model`) -> new state."""
+    return _KinematicStep.apply(state, action, lr, model, uniform_model, params or kinematic_params())
+
+
+# ------------------------------------------------------------------------------------ collisions
+class _DiscsPairwise(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, box1, box2):
+        lib = _lib.load()
+        b1 = _lib.as_f32(box1).reshape(-1, 5)
+        b2 = _lib.as_f32(box2).reshape(-1, 5)
+        out = torch.empty(b1.shape[0], dtype=torch.float32, device=b1.device)
+        _lib.check(lib.tds_collision_pairwise_fwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], _lib.METRIC_DISCS,
+                                                  _lib.ptr(out), _lib.stream_ptr(b1.device)))
+        ctx.save_for_backward(b1, b2)
+        ctx.shapes = (box1.shape, box2.shape)
+        return out.reshape(box1.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        b1, b2 = ctx.saved_tensors
+        g = _lib.as_f32(grad_out).reshape(-1)
+        g1, g2 = torch.empty_like(b1), torch.empty_like(b2)
+        _lib.check(lib.tds_collision_discs_pairwise_bwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], _lib.ptr(g),
+                                                        _lib.ptr(g1), _lib.ptr(g2), _lib.stream_ptr(b1.device)))
+        return g1.reshape(ctx.shapes[0]), g2.reshape(ctx.shapes[1])
+
+
+def collision_pairwise(box1: torch.Tensor, box2: torch.Tensor, metric: int = _lib.METRIC_DISCS) -> torch.Tensor:
+    """Element-wise overlap of box1[...,5] and box2[...,5] (same shape) -> [...]."""
+    if box1.shape != box2.shape or box1.shape[-1] != 5:
+        raise _lib.TdsError("collision_pairwise: boxes must have identical shape [...,5]")
+    if metric == _lib.METRIC_DISCS:
+        return _DiscsPairwise.apply(box1, box2)
+    lib = _lib.load()
+    b1 = _lib.as_f32(box1).reshape(-1, 5)
+    b2 = _lib.as_f32(box2).reshape(-1, 5)
+    out = torch.empty(b1.shape[0], dtype=torch.float32, device=b1.device)
+    _lib.check(lib.tds_collision_pairwise_fwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], metric, _lib.ptr(out),
+                                              _lib.stream_ptr(b1.device)))
+    return out.reshape(box1.shape[:-1])
+
+
+class _DiscsAllPairs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ego_box, all_box, mask, ego_is_prefix):
+        lib = _lib.load()
+        e = _lib.as_f32(ego_box)
+        a = _lib.as_f32(all_box)
+        m = _lib.as_u8(mask)
+        B, A, N = e.shape[0], e.shape[1], a.shape[1]
+        out = torch.zeros(B, A, dtype=torch.float32, device=e.device)
+        arg = torch.zeros(B, A, dtype=torch.int32, device=e.device)
+        _lib.check(lib.tds_collision_allpairs_fwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, _lib.METRIC_DISCS,
+                                                  1 if ego_is_prefix else 0, _lib.ptr(out), _lib.ptr(arg),
+                                                  _lib.stream_ptr(e.device)))
+        ctx.save_for_backward(e, a, m, arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        e, a, m, arg = ctx.saved_tensors
+        B, A, N = e.shape[0], e.shape[1], a.shape[1]
+        g = _lib.as_f32(grad_out)
+        ge = torch.zeros_like(e)
+        ga = torch.zeros_like(a)
+        _lib.check(lib.tds_collision_discs_allpairs_bwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, _lib.ptr(g),
+                                                        _lib.ptr(arg), _lib.ptr(ge), _lib.ptr(ga),
+                                                        _lib.stream_ptr(e.device)))
+        return ge, ga, None, None
+
+
+def collision_allpairs(ego_box: torch.Tensor, all_box: torch.Tensor, mask: torch.Tensor,
+                       metric: int = _lib.METRIC_DISCS, ego_is_prefix: bool = True) -> torch.Tensor:
+    """Fused Simulator.compute_collision: ego_box [B,A,5], all_box [B,N,5], mask [B,N] -> [B,A]."""
+    if ego_box.dim() != 3 or all_box.dim() != 3 or ego_box.shape[-1] != 5 or all_box.shape[-1] != 5:
+        raise _lib.TdsError("collision_allpairs: expected ego_box [B,A,5] and all_box [B,N,5]")
+    if ego_box.shape[0] != all_box.shape[0] or tuple(mask.shape) != tuple(all_box.shape[:2]):
+        raise _lib.TdsError("collision_allpairs: batch / mask shape mismatch")
+    if metric == _lib.METRIC_DISCS:
+        return _DiscsAllPairs.apply(ego_box, all_box, mask, ego_is_prefix)
+    lib = _lib.load()
+    e, a, m = _lib.as_f32(ego_box), _lib.as_f32(all_box), _lib.as_u8(mask)
+    B, A, N = e.shape[0], e.shape[1], a.shape[1]
+    out = torch.zeros(B, A, dtype=torch.float32, device=e.device)
+    _lib.check(lib.tds_collision_allpairs_fwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, metric,
+                                              1 if ego_is_prefix else 0, _lib.ptr(out), None, _lib.stream_ptr(e.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------ offroad
+class _Offroad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, lenwid, present, mapset, threshold):
+        lib = _lib.load()
+        s = _lib.as_f32(state)
+        lw = _lib.as_f32(lenwid)
+        p = None if present is None else _lib.as_u8(present)
+        B, A = s.shape[0], s.shape[1]
+        handles, n_maps = mapset.handles(s.device)
+        env_map = mapset.env_map_on(s.device)
+        out = torch.zeros(B, A, dtype=torch.float32, device=s.device)
+        face = torch.empty(B, A, 4, dtype=torch.int32, device=s.device)
+        _lib.check(lib.tds_offroad_fwd(handles, n_maps, _lib.ptr(env_map), _lib.ptr(s), _lib.ptr(lw), _lib.ptr(p), B, A,
+                                       float(threshold), _lib.ptr(out), _lib.ptr(face), _lib.stream_ptr(s.device)))
+        ctx.save_for_backward(s, lw, p, face)
+        ctx.meta = (mapset, float(threshold), state.shape, lenwid.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        s, lw, p, face = ctx.saved_tensors
+        mapset, threshold, sshape, lshape = ctx.meta
+        B, A = s.shape[0], s.shape[1]
+        handles, n_maps = mapset.handles(s.device)
+        env_map = mapset.env_map_on(s.device)
+        g = _lib.as_f32(grad_out)
+        gs = torch.zeros_like(s)
+        gl = torch.zeros_like(lw)
+        _lib.check(lib.tds_offroad_bwd(handles, n_maps, _lib.ptr(env_map), _lib.ptr(s), _lib.ptr(lw), _lib.ptr(p), B, A,
+                                       threshold, _lib.ptr(face), _lib.ptr(g), _lib.ptr(gs), _lib.ptr(gl),
+                                       _lib.stream_ptr(s.device)))
+        return gs.reshape(sshape), gl.reshape(lshape), None, None, None
+
+
+def offroad(state: torch.Tensor, lenwid: torch.Tensor, mapset: MapSet, threshold: float = 0.0,
+            present: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """state [B,A,4], lenwid [B,A,2] -> [B,A] sum over corners of thresholded squared distance to the map."""
+    if state.dim() != 3 or state.shape[-1] != 4:
+        raise _lib.TdsError("offroad: expected state [B,A,4]")
+    if lenwid.dim() == 2:
+        lenwid = lenwid.unsqueeze(-2).expand(lenwid.shape[0], state.shape[1], lenwid.shape[1])
+    if tuple(lenwid.shape) != (state.shape[0], state.shape[1], 2):
+        raise _lib.TdsError("offroad: expected lenwid [B,A,2] or [B,2]")
+    return _Offroad.apply(state, lenwid, present, mapset, threshold)
+
+
+# ------------------------------------------------------------------------------------ raster
+def raster_birdview(mapset: MapSet, palette: "_lib.Palette", cam_xy: torch.Tensor, cam_sc: torch.Tensor,
+                    agent_state: Optional[torch.Tensor], agent_size: Optional[torch.Tensor],
+                    agent_type: Optional[torch.Tensor], present: Optional[torch.Tensor],
+                    tl_corners: Optional[torch.Tensor], tl_state: Optional[torch.Tensor],
+                    rect_corners: Optional[torch.Tensor], rect_class: Optional[torch.Tensor],
+                    res: int, fov: float, out: Optional[torch.Tensor] = None,
+                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cam_xy, cam_sc [B,Nc,2] -> images [B,Nc,3,res,res] float32 in [0,255] (not differentiable, like
+    the cv2 backend).  present is [B,N] or [B,Nc,N]."""
+    lib = _lib.load()
+    dev = cam_xy.device
+    cxy, csc = _lib.as_f32(cam_xy), _lib.as_f32(cam_sc)
+    B, Nc = cxy.shape[0], cxy.shape[1]
+    N = 0 if agent_state is None else agent_state.shape[-2]
+    L = 0 if tl_corners is None else tl_corners.shape[1]
+    R = 0 if rect_corners is None else rect_corners.shape[1]
+    ast = None if N == 0 else _lib.as_f32(agent_state[..., :4])
+    asz = None if N == 0 else _lib.as_f32(agent_size)
+    aty = None if (N == 0 or agent_type is None) else _lib.as_i32(agent_type)
+    per_cam = 0
+    pr = None
+    if N > 0 and present is not None:
+        pr = _lib.as_u8(present)
+        per_cam = 1 if pr.dim() == 3 else 0
+        if per_cam and tuple(pr.shape) != (B, Nc, N) or (not per_cam and tuple(pr.shape) != (B, N)):
+            raise _lib.TdsError("raster: present mask must be [B,N] or [B,Nc,N]")
+    tlc = None if L == 0 else _lib.as_f32(tl_corners)
+    tls = None if L == 0 else _lib.as_i32(tl_state)
+    rc = None if R == 0 else _lib.as_f32(rect_corners)
+    rcl = None if R == 0 else _lib.as_i32(rect_class)
+    if out is None:
+        out = torch.empty(B, Nc, 3, res, res, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (B, Nc, 3, res, res) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise _lib.TdsError("raster: `out` must be a contiguous float32 [B,Nc,3,res,res] tensor")
+    need = lib.tds_raster_workspace_bytes(B, N, L, R)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    handles, n_maps = mapset.handles(dev)
+    env_map = mapset.env_map_on(dev)
+    _lib.check(lib.tds_raster_birdview(handles, n_maps, _lib.ptr(env_map), B, Nc, N, _lib.ptr(cxy), _lib.ptr(csc),
+                                       _lib.ptr(ast), _lib.ptr(asz), _lib.ptr(aty), _lib.ptr(pr), per_cam,
+                                       _lib.ptr(tlc), _lib.ptr(tls), L, _lib.ptr(rc), _lib.ptr(rcl), R,
+                                       ctypes.byref(palette), float(2.0 / fov), int(res), _lib.ptr(out),
+                                       _lib.ptr(workspace), _lib.stream_ptr(dev)))
+    return out

@@ -1,0 +1,265 @@
+"""Host driver of the per-step hot path: the subset of the reference's `Simulator`
+(torchdrivesim/simulator.py:280-1194) that the B200 kernels accelerate, with the same method names and
+tensor conventions:
+
+    step(action)            simulator.py:841-861   -> fused kinematic kernel
+    render / render_egocentric  :920-1033          -> scene descriptor + raster kernel
+    compute_collision       :1161-1194             -> ONE all-pairs launch instead of a Python loop over agents
+    compute_offroad         :1035-1044             -> grid-accelerated point-to-mesh kernel
+
+NPC / spawn controllers, waypoint goals, observation noise and lanelet-based losses are out of scope
+(SURVEY.md §2); all agents live in the kinematic model.
+"""
+import copy as _copy
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Dict, List, Optional, Union
+
+import math
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+from .kinematic import KinematicModel
+from .maps import MapSet, StaticMap
+from .mesh import B200BirdviewMeshGenerator
+from .rendering import B200RendererConfig, BirdviewRenderer, RendererConfig, Resolution, renderer_from_config
+
+
+class CollisionMetric(Enum):
+    """Subset of simulator.py:27-34 that has a GPU kernel."""
+    discs = 'discs'
+    iou = 'iou'
+
+
+@dataclass
+class TorchDriveConfig:
+    """Same fields as simulator.py:37-51 where they apply to the hot path."""
+    renderer: RendererConfig = field(default_factory=B200RendererConfig)
+    single_agent_rendering: bool = False
+    collision_metric: CollisionMetric = CollisionMetric.discs
+    offroad_threshold: float = 0.5
+    left_handed_coordinates: bool = False
+
+
+class Simulator:
+    def __init__(self, road_mesh: Union[StaticMap, MapSet], kinematic_model: KinematicModel, agent_size: Tensor,
+                 initial_present_mask: Tensor, cfg: TorchDriveConfig, renderer: Optional[BirdviewRenderer] = None,
+                 birdview_mesh_generator: Optional[B200BirdviewMeshGenerator] = None, internal_time: int = 0,
+                 traffic_controls: Optional[Dict[str, object]] = None, agent_types: Optional[Tensor] = None,
+                 agent_type_names: Optional[List[str]] = None):
+        self.road_mesh = road_mesh if isinstance(road_mesh, MapSet) else MapSet([road_mesh])
+        self.kinematic_model = kinematic_model
+        self.agent_size = agent_size
+        self.present_mask = initial_present_mask
+        self._agent_types = agent_type_names or ['vehicle']
+        self.agent_type = torch.zeros_like(initial_present_mask).long() if agent_types is None else agent_types
+        self._batch_size = initial_present_mask.shape[0]
+        self.cfg = cfg
+        self.traffic_controls = traffic_controls
+        self.internal_time = internal_time
+        state = self.get_state()
+        if state.dim() != 3 or agent_size.shape[:2] != state.shape[:2] or initial_present_mask.shape != state.shape[:2]:
+            raise _lib.TdsError("expected state [B,A,4], agent_size [B,A,2] and present mask [B,A]")
+        if renderer is None:
+            cfg.renderer.left_handed_coordinates = cfg.left_handed_coordinates
+            renderer = renderer_from_config(cfg.renderer)
+        self.renderer = renderer
+        if cfg.left_handed_coordinates:
+            self.kinematic_model.left_handed = True
+        if birdview_mesh_generator is None:
+            # note: like simulator.py:371, render_agent_direction from the config is NOT forwarded
+            birdview_mesh_generator = B200BirdviewMeshGenerator(self.road_mesh, self.renderer.color_map,
+                                                                self.renderer.rendering_levels,
+                                                                batch_size=self._batch_size)
+            birdview_mesh_generator.initialize_actors_mesh(self.get_all_agent_size(), self.get_all_agent_type(),
+                                                           self.agent_types)
+            if traffic_controls is not None:
+                birdview_mesh_generator.initialize_traffic_controls_mesh(traffic_controls)
+        self.birdview_mesh_generator = birdview_mesh_generator
+
+    # ---- properties / getters (simulator.py:383-400, 561-640) ----------------------------------
+    @property
+    def agent_types(self) -> List[str]:
+        return self._agent_types
+
+    @property
+    def action_size(self) -> int:
+        return self.kinematic_model.action_size
+
+    @property
+    def batch_size(self) -> int:
+        return self._batch_size
+
+    @property
+    def agent_count(self) -> int:
+        return self.present_mask.shape[-1]
+
+    def get_world_center(self) -> Tensor:
+        return self.birdview_mesh_generator.world_center
+
+    def get_state(self) -> Tensor:
+        return self.kinematic_model.get_state()
+
+    def get_agent_size(self) -> Tensor:
+        return self.agent_size
+
+    def get_agent_type(self) -> Tensor:
+        return self.agent_type
+
+    def get_present_mask(self) -> Tensor:
+        return self.present_mask
+
+    # no NPCs: "all agents" are the controlled agents
+    get_all_agent_state = get_state
+    get_all_agent_size = get_agent_size
+    get_all_agent_type = get_agent_type
+    get_all_agent_present_mask = get_present_mask
+
+    def get_traffic_controls(self):
+        return self.traffic_controls
+
+    # ---- batch plumbing (simulator.py:401-517) -------------------------------------------------
+    def to(self, device):
+        self.kinematic_model = self.kinematic_model.to(device)
+        self.agent_size = self.agent_size.to(device)
+        self.agent_type = self.agent_type.to(device)
+        self.present_mask = self.present_mask.to(device)
+        if self.road_mesh.env_map is not None:
+            self.road_mesh.env_map = self.road_mesh.env_map.to(device)
+        self.birdview_mesh_generator = self.birdview_mesh_generator.to(device)
+        if self.traffic_controls is not None:
+            self.traffic_controls = {k: v.to(device) for k, v in self.traffic_controls.items()}
+        return self
+
+    def copy(self):
+        other = _copy.copy(self)
+        other.kinematic_model = self.kinematic_model.copy()
+        other.renderer = self.renderer.copy()
+        other.birdview_mesh_generator = self.birdview_mesh_generator.copy()
+        if self.traffic_controls is not None:
+            other.traffic_controls = {k: v.copy() for k, v in self.traffic_controls.items()}
+        return other
+
+    def select_batch_elements(self, idx: Tensor, in_place: bool = True):
+        """Picks environments `idx` (the batch shard of one GPU in a multi-GPU run)."""
+        other = self if in_place else self.copy()
+        other.kinematic_model.select_batch_elements(idx)
+        other.agent_size = other.agent_size[idx]
+        other.agent_type = other.agent_type[idx]
+        other.present_mask = other.present_mask[idx]
+        other.road_mesh = other.road_mesh.select(idx)
+        other.birdview_mesh_generator = other.birdview_mesh_generator.select_batch_elements(idx)
+        if other.traffic_controls is not None:
+            other.traffic_controls = {k: v.select_batch_elements(idx, in_place=in_place) for k, v in other.traffic_controls.items()}
+        other._batch_size = int(idx.numel())
+        return other
+
+    # ---- hot path ---------------------------------------------------------------------------------
+    def step(self, agent_action: Tensor) -> None:
+        self.internal_time += 1
+        if agent_action.dim() != 3 or agent_action.shape[0] != self.batch_size or agent_action.shape[-2] != self.agent_count:
+            raise _lib.TdsError(f"action must be [B={self.batch_size}, A={self.agent_count}, Ac]")
+        self.kinematic_model.step(agent_action)
+        if self.traffic_controls is not None:
+            for control in self.traffic_controls.values():
+                control.step(self.internal_time)
+
+    def set_state(self, agent_state: Tensor, mask: Optional[Tensor] = None) -> None:
+        if mask is None:
+            self.kinematic_model.set_state(agent_state)
+        else:
+            self.kinematic_model.set_state(agent_state.where(mask.unsqueeze(-1), self.kinematic_model.get_state()))
+
+    def update_present_mask(self, present_mask: Tensor) -> None:
+        self.present_mask = present_mask
+
+    def fit_action(self, future_state: Tensor, current_state: Optional[Tensor] = None) -> Tensor:
+        return self.kinematic_model.fit_action(future_state=future_state, current_state=current_state)
+
+    def render(self, camera_xy: Tensor, camera_psi: Tensor, res: Optional[Resolution] = None,
+               rendering_mask: Optional[Tensor] = None, fov: Optional[float] = None, out: Optional[Tensor] = None) -> Tensor:
+        """camera_xy BxNx2, camera_psi BxNx1 -> BxNx3xHxW (simulator.py:920-992)."""
+        camera_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
+        if camera_xy.dim() == 2:
+            camera_xy, camera_sc = camera_xy.unsqueeze(1), camera_sc.unsqueeze(1)
+        n_cameras = camera_xy.shape[-2]
+        present = self.get_all_agent_present_mask()
+        if rendering_mask is not None:
+            present = present.unsqueeze(-2).expand(-1, n_cameras, -1).logical_and(rendering_mask)
+        else:
+            present = present.unsqueeze(-2).expand(-1, n_cameras, -1)
+        tl = self.traffic_controls.get('traffic_light') if self.traffic_controls is not None else None
+        scene = self.birdview_mesh_generator.generate(
+            n_cameras, agent_state=self.get_all_agent_state().detach()[:, None].expand(-1, n_cameras, -1, -1),
+            present_mask=present, traffic_lights=tl)
+        img = self.renderer.render_frame(scene, camera_xy, camera_sc, res=res, fov=fov, out=out)
+        return img.reshape((self.batch_size, n_cameras) + img.shape[1:])
+
+    def render_egocentric(self, ego_rotate: bool = True, res: Optional[Resolution] = None, fov: Optional[float] = None,
+                          visibility_matrix: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+        """One camera per agent -> BxAx3xHxW (simulator.py:994-1033)."""
+        state = self.get_state().detach()
+        camera_xy, camera_psi = state[..., :2], state[..., 2:3]
+        if not ego_rotate:
+            camera_psi = torch.ones_like(camera_psi) * (math.pi / 2)
+        rendering_mask = visibility_matrix
+        if self.cfg.single_agent_rendering:
+            rendering_mask = torch.eye(self.agent_count, dtype=torch.bool, device=state.device).unsqueeze(0).expand(
+                self.batch_size, -1, -1)
+        return self.render(camera_xy, camera_psi, rendering_mask=rendering_mask, res=res, fov=fov, out=out)
+
+    def render_egocentric_to_host(self, host_out: Tensor, chunk_envs: int = 128, res: Optional[Resolution] = None,
+                                  fov: Optional[float] = None) -> Tensor:
+        """Egocentric birdviews delivered into a PINNED host tensor [B,A,3,H,W]: environments are rendered
+        in chunks into two device buffers while the previous chunk is copied out on a side stream, so the
+        PCIe transfer overlaps the raster kernel.  Returns `host_out` (valid after the returned stream
+        work is synchronised by the caller, e.g. torch.cuda.synchronize())."""
+        res = self.renderer.res if res is None else res
+        state = self.get_state().detach()
+        dev = state.device
+        B, A = state.shape[0], state.shape[1]
+        if tuple(host_out.shape) != (B, A, 3, res.height, res.width) or not host_out.is_pinned():
+            raise _lib.TdsError("host_out must be a pinned float32 tensor of shape [B,A,3,H,W]")
+        cam_xy = state[..., :2].contiguous()
+        cam_sc = torch.cat([torch.sin(state[..., 2:3]), torch.cos(state[..., 2:3])], dim=-1)
+        present = self.get_all_agent_present_mask()
+        tl = self.traffic_controls.get('traffic_light') if self.traffic_controls is not None else None
+        scene = self.birdview_mesh_generator.generate(A, agent_state=state[:, None].expand(-1, A, -1, -1),
+                                                      present_mask=present.unsqueeze(-2).expand(-1, A, -1), traffic_lights=tl)
+        chunk = max(1, min(chunk_envs, B))
+        if getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, A, 3, res.height, res.width):
+            self._h2d_bufs = [torch.empty(chunk, A, 3, res.height, res.width, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._buf_free = [None, None]
+        main = torch.cuda.current_stream(dev)
+        for i, b0 in enumerate(range(0, B, chunk)):
+            b1 = min(b0 + chunk, B)
+            buf = self._h2d_bufs[i % 2][: b1 - b0]
+            if self._buf_free[i % 2] is not None:
+                main.wait_event(self._buf_free[i % 2])          # the previous copy out of this buffer is done
+            self.renderer.render_frame(scene.slice(b0, b1), cam_xy[b0:b1], cam_sc[b0:b1], res=res, fov=fov, out=buf)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(done)
+                host_out[b0:b1].copy_(buf, non_blocking=True)
+                free = torch.cuda.Event()
+                free.record(self._copy_stream)
+            self._buf_free[i % 2] = free
+        main.wait_stream(self._copy_stream)
+        return host_out
+
+    def compute_offroad(self) -> Tensor:
+        """simulator.py:1035-1044: offroad_infraction_loss(...) * present mask."""
+        return ops.offroad(self.get_state(), self.get_agent_size(), self.road_mesh, self.cfg.offroad_threshold,
+                           self.get_present_mask())
+
+    def compute_collision(self) -> Tensor:
+        """simulator.py:1161-1194 for the `discs` and `iou` metrics, all agents in one launch."""
+        state, size = self.get_state(), self.get_agent_size()[..., :2]
+        box = torch.cat([state[..., :2], size, state[..., 2:3]], dim=-1)
+        if box.shape[-2] == 0:
+            return torch.zeros_like(box[..., 0])
+        metric = _lib.METRIC_IOU if self.cfg.collision_metric == CollisionMetric.iou else _lib.METRIC_DISCS
+        return ops.collision_allpairs(box, box, self.get_all_agent_present_mask(), metric, ego_is_prefix=True)
