@@ -8,3 +8,11 @@ extern "C" void tds_host_draw_triangle(uint8_t* img, int W, int H, const int32_t
         [&](int x, int y) { img[y * W + x] = 1; },
         [&](int y, int xa, int xb) { for (int x = xa; x <= xb; x++) img[y * W + x] = 1; });
 }
+
+// fast path (|coordinates| < 8192), x-major target like the kernel's shared-memory tile
+extern "C" void tds_host_draw_triangle_fast(uint8_t* img, int W, int H, const int32_t* p) {
+    // img is row-major [H][W]: index = x * 1 + y * W
+    tds::draw_triangle_fast(W, H, 1, W, p[0], p[1], p[2], p[3], p[4], p[5],
+        [&](int idx) { img[idx] = 1; },
+        [&](int idx, int n, int step) { for (int i = 0; i < n; i++) img[idx + i * step] = 1; });
+}

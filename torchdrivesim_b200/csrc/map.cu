@@ -170,9 +170,24 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
         }
     }
     m->info.offroad_entries = (int32_t)oidx.size();
+    // inline the triangle data per cell entry, largest faces first
+    auto area2 = [&](int f) {
+        const float* t = &tri[6 * (size_t)f];
+        return std::fabs((t[2] - t[0]) * (t[5] - t[1]) - (t[3] - t[1]) * (t[4] - t[0]));
+    };
+    std::vector<float> orec(oidx.size() * 8, 0.f);
+    for (int c = 0; c < onc; c++) {
+        std::stable_sort(oidx.begin() + ocell[c], oidx.begin() + ocell[c + 1],
+                         [&](int a, int b) { return area2(a) > area2(b); });
+        for (int e = ocell[c]; e < ocell[c + 1]; e++) {
+            const int f = oidx[e];
+            for (int k = 0; k < 6; k++) orec[8 * (size_t)e + k] = tri[6 * (size_t)f + k];
+            memcpy(&orec[8 * (size_t)e + 6], &f, sizeof(int));
+        }
+    }
     if (!(upload(recdata, &m->allocations[0], bytes) && upload(rcell, &m->allocations[1], bytes) &&
           upload(tri, &m->allocations[2], bytes) && upload(ocell, &m->allocations[3], bytes) &&
-          upload(oidx, &m->allocations[4], bytes))) {
+          upload(orec, &m->allocations[4], bytes))) {
         fail(TDS_ERR_CUDA, "map_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         tds_map_destroy(m);
         return nullptr;
@@ -181,7 +196,7 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     d.rcell = (const int32_t*)m->allocations[1];
     d.tri = (const float*)m->allocations[2];
     d.ocell = (const int32_t*)m->allocations[3];
-    d.oidx = (const int32_t*)m->allocations[4];
+    d.orec = (const float4*)m->allocations[4];
     m->info.n_verts = nv; m->info.n_faces = nf;
     m->info.raster_gx = d.rgx; m->info.raster_gy = d.rgy; m->info.raster_records = (int32_t)recs.size();
     m->info.offroad_gx = d.ogx; m->info.offroad_gy = d.ogy;

@@ -34,6 +34,7 @@ struct PaletteDev {
     int32_t agent_type_class[TDS_MAX_AGENT_TYPES];
     int32_t direction_class;
     int32_t tl_state_class[TDS_MAX_TL_STATES];
+    uint32_t dyn_mask;                            // classes that dynamic primitives may carry
 };
 
 // ------------------------------------------------------------------ dynamic primitives (per env)
@@ -155,36 +156,80 @@ __device__ __forceinline__ bool inside_quad(const Camera& cam, float x, float y)
     return nr == 4 || nr == 0;
 }
 
-__device__ __forceinline__ void project(const Camera& cam, float x, float y, int& u, int& v) {
-    // base.py:102-115 then .to(int32) (cv2.py:48): truncation toward zero
-    float u0 = cam.C * x + cam.S * y;
-    float u1 = (-cam.S) * x + cam.C * y;
+// ---- stage 1: cull (mesh.py:311-313) + project one world-space triangle --------------------------
+// Pixel-space shortcut for the cull: the 1.05x view quad is the image square scaled by 1.05 about its
+// centre, i.e. pixel coordinates in [-0.025 res, 1.025 res].  A projected vertex further than ~0.01 px from
+// that boundary is decided from its pixel coordinates; the thin band around the boundary falls back to
+// the reference's fp32 edge functions, so the decision is always the reference's.
+struct Item {
+    uint32_t a, b, c;       // (x0,y0), (x1,y1), (x2,y2) as int16 pairs
+};
+
+__device__ __noinline__ bool inside_quad_exact(const Camera& cam, float x, float y) { return inside_quad(cam, x, y); }
+
+__device__ __forceinline__ int classify(float u, float v, float lo, float hi, float m) {
+    // 1 inside, 0 outside, -1 undecided
+    const bool in = (u > lo + m) & (u < hi - m) & (v > lo + m) & (v < hi - m);
+    const bool out = (u < lo - m) | (u > hi + m) | (v < lo - m) | (v > hi + m);
+    return in ? 1 : (out ? 0 : -1);
+}
+
+__device__ __forceinline__ void project_f(const Camera& cam, float x, float y, float& u0, float& u1) {
+    u0 = cam.C * x + cam.S * y;
+    u1 = (-cam.S) * x + cam.C * y;
     u0 = (-u0) * cam.scale; u1 = (-u1) * cam.scale;
     u0 = u0 * cam.fmin;     u1 = u1 * cam.fmin;
     u0 = u0 / 2.0f;         u1 = u1 / 2.0f;
     u0 = u0 + cam.half;     u1 = u1 + cam.half;
-    u = __float2int_rz(u0);
-    v = __float2int_rz(u1);
 }
 
-// cull (mesh.py:311-313), project and scan-convert one world-space triangle; `own` = bitmask of the
-// vertices whose grid cell is the one this record was read from (7 for dynamic triangles)
-__device__ __forceinline__ void raster_triangle(const Camera& cam, uint8_t* img, uint8_t val, float x0, float y0,
-                                                float x1, float y1, float x2, float y2, int own) {
+// returns 0: culled, 1: item valid (|coords| < 8192), 2: kept but needs the 64-bit slow path (ints in xy[])
+__device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float y0, float x1, float y1, float x2,
+                                              float y2, int own, Item& it, int xy[6]) {
     const float px0 = x0 + cam.ncx, py0 = y0 + cam.ncy;
     const float px1 = x1 + cam.ncx, py1 = y1 + cam.ncy;
     const float px2 = x2 + cam.ncx, py2 = y2 + cam.ncy;
-    const bool i0 = inside_quad(cam, px0, py0), i1 = inside_quad(cam, px1, py1), i2 = inside_quad(cam, px2, py2);
-    if (!(i0 | i1 | i2)) return;
-    const int first = i0 ? 0 : (i1 ? 1 : 2);
-    if (!((own >> first) & 1)) return;          // another cell's copy of this face draws it
-    int ax, ay, bx, by, cx, cy;
-    project(cam, px0, py0, ax, ay);
-    project(cam, px1, py1, bx, by);
-    project(cam, px2, py2, cx, cy);
-    const int res = cam.res;
-    // tile is x-major: img[x * res + y] == transposed image (cv2.py:61)
-    tds::draw_triangle(res, res, ax, ay, bx, by, cx, cy,
+    float u0, v0, u1, v1, u2, v2;
+    project_f(cam, px0, py0, u0, v0);
+    project_f(cam, px1, py1, u1, v1);
+    project_f(cam, px2, py2, u2, v2);
+    const float lo = -0.025f * cam.fmin, hi = 1.025f * cam.fmin;
+    // fp32 disagreement between the pixel-space and the edge-function test is < 1e-4 m; band = 0.01 px + 2e-3 m
+    const float band = 0.01f + 0.002f * (cam.scale * cam.half);
+    int c0 = classify(u0, v0, lo, hi, band), c1 = classify(u1, v1, lo, hi, band), c2 = classify(u2, v2, lo, hi, band);
+    if ((c0 | c1 | c2) < 0) {       // some vertex is within the band around the quad boundary (or NaN): exact test
+        if (c0 < 0) c0 = inside_quad_exact(cam, px0, py0);
+        if (c1 < 0) c1 = inside_quad_exact(cam, px1, py1);
+        if (c2 < 0) c2 = inside_quad_exact(cam, px2, py2);
+    }
+    if (!(c0 | c1 | c2)) return 0;
+    const int first = c0 ? 0 : (c1 ? 1 : 2);
+    if (!((own >> first) & 1)) return 0;          // another cell's copy of this face draws it
+    xy[0] = __float2int_rz(u0); xy[1] = __float2int_rz(v0);
+    xy[2] = __float2int_rz(u1); xy[3] = __float2int_rz(v1);
+    xy[4] = __float2int_rz(u2); xy[5] = __float2int_rz(v2);
+    int big = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) big |= (xy[k] <= -8192) | (xy[k] >= 8192);
+    if (big) return 2;
+    it.a = (uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16);
+    it.b = (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16);
+    it.c = (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16);
+    return 1;
+}
+
+// ---- stage 2: scan-convert.  The tile is x-major (img[x * res + y]) which IS the transpose of cv2.py:61
+__device__ __forceinline__ void draw_item(uint8_t* img, int res, uint8_t val, const Item& it) {
+    const int x0 = (int16_t)(it.a & 0xffff), y0 = (int32_t)it.a >> 16;
+    const int x1 = (int16_t)(it.b & 0xffff), y1 = (int32_t)it.b >> 16;
+    const int x2 = (int16_t)(it.c & 0xffff), y2 = (int32_t)it.c >> 16;
+    tds::draw_triangle_fast(res, res, res, 1, x0, y0, x1, y1, x2, y2,
+        [&](int idx) { img[idx] = val; },
+        [&](int idx, int n, int step) { for (; n > 0; n--, idx += step) img[idx] = val; });
+}
+
+__device__ __noinline__ void draw_item_slow(uint8_t* img, int res, uint8_t val, const int* xy) {
+    tds::draw_triangle(res, res, xy[0], xy[1], xy[2], xy[3], xy[4], xy[5],
         [&](int x, int y) { img[x * res + y] = val; },
         [&](int y, int xa, int xb) { for (int x = xa; x <= xb; x++) img[x * res + y] = val; });
 }
@@ -197,34 +242,57 @@ struct RasterArgs {
     const uint8_t* ws;
     float* out;
     int32_t B, Nc, N, T, present_per_camera, res;
+    int32_t ncam;
     float scale;
 };
 
-__global__ void raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
+constexpr int kQueue = 256;          // items per group queue (3 KB)
+constexpr int kRows = tds::kMaxRasterRows;
+
+// G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras per CTA, no block barriers)
+// for tiles up to 64x64, or the whole CTA for larger tiles.
+template <int G>
+__device__ __forceinline__ void group_sync() {
+    if (G == 32) __syncwarp();
+    else __syncthreads();
+}
+
+template <int G>
+__global__ void __launch_bounds__(G == 32 ? 128 : G) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr int GROUPS = G == 32 ? 4 : 1;
     const int res = a.res;
-    uint8_t* img = smem_raw;                                   // [res*res], x-major
-    __shared__ int s_row_lo[kMaxRasterRows], s_row_hi[kMaxRasterRows];
-    __shared__ int s_start[kMaxSlots][kMaxRasterRows];
-    __shared__ int s_pref[kMaxSlots][kMaxRasterRows + 1];
+    const int group = G == 32 ? (threadIdx.x >> 5) : 0;
+    const int tid = G == 32 ? (threadIdx.x & 31) : threadIdx.x;
+    const int camid = blockIdx.x * GROUPS + group;
+    const bool active = camid < a.ncam;         // whole group is inactive together
+
+    // per-group shared memory: tile | queue | row tables
+    const int tile_bytes = res * res;
+    const int group_bytes = tile_bytes + kQueue * 12 + kRows * 8 + 16;
+    uint8_t* base = smem_raw + (size_t)group * group_bytes;
+    uint8_t* img = base;
+    uint32_t* queue = reinterpret_cast<uint32_t*>(base + tile_bytes);      // [3][kQueue]
+    int* s_start = reinterpret_cast<int*>(base + tile_bytes + kQueue * 12);
+    int* s_pref = s_start + kRows;                                         // exclusive prefix of the row counts
+    int* s_cnt = s_pref + kRows;                                           // [0],[1] queue counts (ping-pong), [2] total
     __shared__ float s_lut[(TDS_MAX_CLASSES + 1) * 3];
+    for (int i = threadIdx.x; i < (TDS_MAX_CLASSES + 1) * 3; i += blockDim.x) s_lut[i] = pal.rgb[i / 3][i % 3];
+    __syncthreads();
+    if (!active) return;                        // no block barrier is used below when G == 32
 
-    const int camid = blockIdx.x;
     const int b = camid / a.Nc;
-    const int tid = threadIdx.x, nthr = blockDim.x;
     const MapDev& map = maps.m[a.env_map ? a.env_map[b] : 0];
-
     Camera cam;
     float qx[4], qy[4];
     const float2 cxy = reinterpret_cast<const float2*>(a.cam_xy)[camid];
     const float2 csc = reinterpret_cast<const float2*>(a.cam_sc)[camid];
     make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy);
 
-    // ---- clear tile, load LUT
-    {
+    {   // clear the tile
         uint32_t* w = reinterpret_cast<uint32_t*>(img);
-        for (int i = tid; i < res * res / 4; i += nthr) w[i] = 0u;
-        for (int i = tid; i < (TDS_MAX_CLASSES + 1) * 3; i += nthr) s_lut[i] = pal.rgb[i / 3][i % 3];
+        for (int i = tid; i < tile_bytes / 4; i += G) w[i] = 0u;
+        if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
     }
     // ---- grid rows touched by the view quad (world coordinates), with a 5 cm safety margin
     const float margin = 0.05f;
@@ -236,7 +304,9 @@ __global__ void raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     int r0 = (int)floorf((ymin - map.ry0) * map.rinv), r1 = (int)floorf((ymax - map.ry0) * map.rinv);
     r0 = max(r0, 0);
     r1 = min(r1, map.rgy - 1);
-    const int nrows = min(max(r1 - r0 + 1, 0), kMaxRasterRows);
+    const int nrows = min(max(r1 - r0 + 1, 0), kRows);
+    // column interval of row (r0 + tid), kept in registers of lane/thread tid < nrows
+    int my_c0 = 0, my_c1 = -1;
     if (tid < nrows) {
         const int r = r0 + tid;
         const float ylo = map.ry0 + (float)r * map.rcs - margin, yhi = map.ry0 + (float)(r + 1) * map.rcs + margin;
@@ -258,86 +328,123 @@ __global__ void raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
             xmin = fminf(xmin, fminf(xa, xb));
             xmax = fmaxf(xmax, fmaxf(xa, xb));
         }
-        int c0 = (int)floorf((xmin - margin - map.rx0) * map.rinv), c1 = (int)floorf((xmax + margin - map.rx0) * map.rinv);
-        c0 = max(c0, 0);
-        c1 = min(c1, map.rgx - 1);
-        if (xmin > xmax) { c0 = 0; c1 = -1; }
-        s_row_lo[tid] = c0;
-        s_row_hi[tid] = c1;
-    }
-    __syncthreads();
-    // ---- record ranges of every (slot, row)
-    const int ncell = map.rgx * map.rgy;
-    for (int i = tid; i < map.n_slots * nrows; i += nthr) {
-        const int s = i / nrows, r = i % nrows;
-        const int c0 = s_row_lo[r], c1 = s_row_hi[r];
-        int st = 0, cnt = 0;
-        if (c1 >= c0) {
-            const int base = s * ncell + (r0 + r) * map.rgx;
-            st = map.rcell[base + c0];
-            cnt = map.rcell[base + c1 + 1] - st;
+        if (xmin <= xmax) {
+            my_c0 = max((int)floorf((xmin - margin - map.rx0) * map.rinv), 0);
+            my_c1 = min((int)floorf((xmax + margin - map.rx0) * map.rinv), map.rgx - 1);
         }
-        s_start[s][r] = st;
-        s_pref[s][r + 1] = cnt;
     }
-    __syncthreads();
-    if (tid < map.n_slots) {
-        int acc = 0;
-        s_pref[tid][0] = 0;
-        for (int r = 0; r < nrows; r++) { acc += s_pref[tid][r + 1]; s_pref[tid][r + 1] = acc; }
-    }
-    __syncthreads();
+    group_sync<G>();
 
-    // ---- dynamic primitives of this environment
     const int T = a.T;
     const float* dtri = reinterpret_cast<const float*>(a.ws + (int64_t)b * ws_env_bytes(T));
     const uint8_t* dcls = reinterpret_cast<const uint8_t*>(dtri + (int64_t)T * 6);
     const uint8_t* pres = a.present ? (a.present_per_camera ? a.present + (int64_t)camid * a.N : a.present + (int64_t)b * a.N)
                                     : nullptr;
+    const int ncell = map.rgx * map.rgy;
 
-    // ---- painter's passes, first drawn = highest z
+    // ---- painter's passes, first drawn = highest z.  Each pass: stage 1 culls + projects candidates and
+    // appends the kept ones to the queue (warp-aggregated), stage 2 scan-converts the queue.
+    int parity = 0;
     for (int ph = 0; ph < pal.n_classes; ph++) {
         const int c = pal.order[ph];
         const uint8_t val = (uint8_t)(c + 1);
         const int slot = map.slot_of_class[c];
-        if (slot >= 0) {
-            const int total = s_pref[slot][nrows];
-            for (int i = tid; i < total; i += nthr) {
-                int r = 0;
-                while (i >= s_pref[slot][r + 1]) r++;
-                const int idx = s_start[slot][r] + (i - s_pref[slot][r]);
-                const float4 v01 = __ldg(map.rec + 2 * (int64_t)idx);
-                const float4 v2o = __ldg(map.rec + 2 * (int64_t)idx + 1);
-                raster_triangle(cam, img, val, v01.x, v01.y, v01.z, v01.w, v2o.x, v2o.y, __float_as_int(v2o.z));
+        int total_static = 0;
+        if (slot >= 0 && nrows > 0) {
+            // record range of every touched grid row for this class
+            if (tid < nrows) {
+                int st = 0, cnt = 0;
+                if (my_c1 >= my_c0) {
+                    const int cb = slot * ncell + (r0 + tid) * map.rgx;
+                    st = map.rcell[cb + my_c0];
+                    cnt = map.rcell[cb + my_c1 + 1] - st;
+                }
+                s_start[tid] = st;
+                s_pref[tid] = cnt;
             }
-        }
-        for (int t = tid; t < T; t += nthr) {
-            int tt = t;
-            bool degenerate = false;
-            if (t < 3 * a.N && pres && !pres[t / 3]) {
-                // absent agent: faces * 0 -> degenerate triangle at actor vertex 0, agent 0's class (mesh.py:1083-1089)
-                tt = 0;
-                degenerate = true;
+            group_sync<G>();
+            if (tid == 0) {
+                int acc = 0;
+                for (int r = 0; r < nrows; r++) { const int n = s_pref[r]; s_pref[r] = acc; acc += n; }
+                s_cnt[2] = acc;
             }
-            if (dcls[tt] != c) continue;
-            const float* p = dtri + (int64_t)tt * 6;
-            if (degenerate) raster_triangle(cam, img, val, p[0], p[1], p[0], p[1], p[0], p[1], 7);
-            else raster_triangle(cam, img, val, p[0], p[1], p[2], p[3], p[4], p[5], 7);
+            group_sync<G>();
+            total_static = s_cnt[2];
         }
-        __syncthreads();
+        const int ndyn = ((pal.dyn_mask >> c) & 1u) ? T : 0;
+        const int total = total_static + ndyn;
+        int row = 0;                                   // candidates are visited in increasing order
+        for (int c0 = 0; c0 < total; c0 += kQueue) {
+            const int cend = min(c0 + kQueue, total);
+            for (int i = c0 + tid; i < cend; i += G) {
+                float x0, y0, x1, y1, x2, y2;
+                int own = 7;
+                bool valid = true;
+                if (i < total_static) {
+                    while (row + 1 < nrows && i >= s_pref[row + 1]) row++;
+                    const int idx = s_start[row] + (i - s_pref[row]);
+                    const float4 v01 = __ldg(map.rec + 2 * (int64_t)idx);
+                    const float4 v2o = __ldg(map.rec + 2 * (int64_t)idx + 1);
+                    x0 = v01.x; y0 = v01.y; x1 = v01.z; y1 = v01.w; x2 = v2o.x; y2 = v2o.y;
+                    own = __float_as_int(v2o.z);
+                } else {
+                    // dynamic primitives (agents, direction triangles, traffic lights, signs)
+                    int t = i - total_static;
+                    bool degenerate = false;
+                    if (t < 3 * a.N && pres && !pres[t / 3]) {
+                        // absent agent: faces * 0 -> degenerate triangle at actor vertex 0 with agent 0's class
+                        // (mesh.py:1083-1089)
+                        t = 0;
+                        degenerate = true;
+                    }
+                    valid = dcls[t] == c;
+                    const float* p = dtri + (int64_t)t * 6;
+                    x0 = p[0]; y0 = p[1];
+                    x1 = degenerate ? x0 : p[2]; y1 = degenerate ? y0 : p[3];
+                    x2 = degenerate ? x0 : p[4]; y2 = degenerate ? y0 : p[5];
+                }
+                Item it;
+                int xy[6];
+                const int kind = valid ? setup_triangle(cam, x0, y0, x1, y1, x2, y2, own, it, xy) : 0;
+                if (kind == 2) draw_item_slow(img, res, val, xy);     // huge triangle: rare, drawn in place
+                const unsigned full = __activemask();
+                const unsigned m = __ballot_sync(full, kind == 1);
+                if (m != 0) {
+                    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                    int basepos = 0;
+                    if (lane == leader) basepos = atomicAdd(&s_cnt[parity], __popc(m));
+                    basepos = __shfl_sync(full, basepos, leader);
+                    if (kind == 1) {
+                        const int pos = basepos + __popc(m & ((1u << lane) - 1));
+                        queue[pos] = it.a; queue[kQueue + pos] = it.b; queue[2 * kQueue + pos] = it.c;
+                    }
+                }
+            }
+            group_sync<G>();
+            const int n = s_cnt[parity];
+            if (tid == 0) s_cnt[parity ^ 1] = 0;
+            for (int i = tid; i < n; i += G) {
+                Item it;
+                it.a = queue[i]; it.b = queue[kQueue + i]; it.c = queue[2 * kQueue + i];
+                draw_item(img, res, val, it);
+            }
+            group_sync<G>();
+            parity ^= 1;
+        }
     }
+    group_sync<G>();
 
     // ---- expand the tile through the colour LUT: out[cam][ch][x][y], 4 pixels per 128-bit store
-    const int nquad = res * res / 4;
-    float* outc = a.out + (int64_t)camid * 3 * res * res;
+    const int nquad = tile_bytes / 4;
+    float* outc = a.out + (int64_t)camid * 3 * tile_bytes;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(img);
-    for (int i = tid; i < nquad; i += nthr) {
+    for (int i = tid; i < nquad; i += G) {
         const uint32_t v = w[i];
         const int k0 = (v & 255u) * 3, k1 = ((v >> 8) & 255u) * 3, k2 = ((v >> 16) & 255u) * 3, k3 = (v >> 24) * 3;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             const float4 o = make_float4(s_lut[k0 + ch], s_lut[k1 + ch], s_lut[k2 + ch], s_lut[k3 + ch]);
-            tds::st_cs_f4(reinterpret_cast<float4*>(outc + (int64_t)ch * res * res) + i, o);
+            tds::st_cs_f4(reinterpret_cast<float4*>(outc + (int64_t)ch * tile_bytes) + i, o);
         }
     }
 }
@@ -400,6 +507,16 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     for (int t = 0; t < TDS_MAX_AGENT_TYPES; t++) pal.agent_type_class[t] = palette->agent_type_class[t];
     for (int t = 0; t < TDS_MAX_TL_STATES; t++) pal.tl_state_class[t] = palette->tl_state_class[t];
     pal.direction_class = palette->direction_class;
+    pal.dyn_mask = 0;
+    if (N > 0) {
+        for (int t = 0; t < TDS_MAX_AGENT_TYPES; t++)
+            if (pal.agent_type_class[t] >= 0 && pal.agent_type_class[t] < TDS_MAX_CLASSES) pal.dyn_mask |= 1u << pal.agent_type_class[t];
+        if (pal.direction_class >= 0 && pal.direction_class < TDS_MAX_CLASSES) pal.dyn_mask |= 1u << pal.direction_class;
+    }
+    if (L > 0)
+        for (int t = 0; t < TDS_MAX_TL_STATES; t++)
+            if (pal.tl_state_class[t] >= 0 && pal.tl_state_class[t] < TDS_MAX_CLASSES) pal.dyn_mask |= 1u << pal.tl_state_class[t];
+    if (R > 0) pal.dyn_mask = 0xffffffffu;     // extra rectangles carry arbitrary classes
 
     cudaStream_t st = (cudaStream_t)stream;
     if (T > 0) {
@@ -413,14 +530,21 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     a.env_map = d_env_map; a.cam_xy = d_cam_xy; a.cam_sc = d_cam_sc; a.present = d_present;
     a.ws = (const uint8_t*)d_workspace; a.out = d_out;
     a.B = B; a.Nc = Nc; a.N = N; a.T = T; a.present_per_camera = present_per_camera; a.res = res; a.scale = scale;
-    const size_t smem = (size_t)res * res;
-    const int threads = res <= 64 ? 128 : (res <= 128 ? 256 : 512);
-    if (smem > 40 * 1024) TDS_CUDA_OK(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ncam = (int64_t)B * Nc;
     TDS_REQUIRE(ncam <= 2147483647LL, "raster: too many cameras");
-    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
-    raster_kernel<<<(unsigned)ncam, threads, smem, st>>>(set, a, pal);
-    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
-    TDS_LAUNCH_OK();
-    return TDS_OK;
+    a.ncam = (int32_t)ncam;
+    const size_t group_bytes = (size_t)res * res + kQueue * 12 + kRows * 8 + 16;
+    auto launch = [&](auto kernel, int groups, int threads) -> int {
+        const size_t smem = group_bytes * groups;
+        if (smem > 40 * 1024) TDS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)((ncam + groups - 1) / groups);
+        if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
+        kernel<<<grid, threads, smem, st>>>(set, a, pal);
+        if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+        TDS_LAUNCH_OK();
+        return TDS_OK;
+    };
+    if (res <= 64) return launch(raster_kernel<32>, 4, 128);
+    if (res <= 128) return launch(raster_kernel<256>, 1, 256);
+    return launch(raster_kernel<512>, 1, 512);
 }

@@ -18,9 +18,10 @@ struct MapDev {
     int32_t rgx, rgy, n_slots;
     int32_t slot_of_class[TDS_MAX_CLASSES];   // -1: the map has no face of that class
     // ---- offroad grid: triangles binned by bounding box overlap
-    const float* tri;               // [nf][6] x0,y0,x1,y1,x2,y2
-    const int32_t* ocell;           // [ogx * ogy + 1]
-    const int32_t* oidx;            // face indices
+    const float* tri;               // [nf][6] x0,y0,x1,y1,x2,y2 (indexed by face, for the backward)
+    const int32_t* ocell;           // [ogx * ogy + 1] CSR offsets into orec (in records)
+    const float4* orec;             // per cell entry: (x0,y0,x1,y1), (x2,y2, face index bits, unused); within a
+                                    // cell the faces are sorted by decreasing area (a containing face is found early)
     float ox0, oy0, ocs, oinv;
     int32_t ogx, ogy, nf;
 };

@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define TDS_HD __host__ __device__ __forceinline__
+#define TDS_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define TDS_HD static inline
+#define TDS_HD_NOINLINE static
 #endif
 
 namespace tds {
@@ -25,7 +27,7 @@ namespace tds {
 // Integer division truncating toward zero reproduces OpenCV's (int64)(double * int / int)
 // exactly for |operands| < 2^26 (the quotient of two such integers is never within one
 // double ulp of an integer it does not equal).
-TDS_HD bool clip_line(int W, int H, long long& x1, long long& y1, long long& x2, long long& y2) {
+TDS_HD_NOINLINE bool clip_line(int W, int H, long long& x1, long long& y1, long long& x2, long long& y2) {
     const long long right = W - 1, bottom = H - 1;
     int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
     int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
@@ -139,6 +141,90 @@ TDS_HD void draw_triangle(int W, int H, int x0, int y0, int x1, int y1, int x2, 
     const bool small = xmin > -8192 && xmax < 8192 && ty > -8192 && by < 8192;
     if (small) fill_rows<int>(W, H, tx, ty, mx, my, bx, by, span);
     else fill_rows<long long>(W, H, tx, ty, mx, my, bx, by, span);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fast path used by the raster kernel: the same pixel set as draw_triangle for |coordinates| < 8192,
+// written for a linear target  index = x * sx + y * sy  (plot(index), span(index_of_first, count, sx)).
+//   * bounding box within 2x2 pixels: every edge joins two 8-adjacent pixels, so the outline is the set
+//     of vertices that lie inside the image, and there are no further fill pixels;
+//   * y_bottom - y_top <= 1: the single fill row is covered by the outline (the span joins two vertices
+//     of that row, or is one vertex), so only the outline is drawn;
+//   * otherwise outline + closed-form spans, all in 32-bit integers.
+template <class Plot>
+TDS_HD void draw_line8_fast(int W, int H, int sx, int sy, int xa, int ya, int xb, int yb, Plot&& plot) {
+    if ((unsigned)xa >= (unsigned)W || (unsigned)xb >= (unsigned)W ||
+        (unsigned)ya >= (unsigned)H || (unsigned)yb >= (unsigned)H) {
+        long long x1 = xa, y1 = ya, x2 = xb, y2 = yb;
+        if (!clip_line(W, H, x1, y1, x2, y2)) return;
+        xa = (int)x1; ya = (int)y1; xb = (int)x2; yb = (int)y2;
+    }
+    int dx = xb - xa, dy = yb - ya;
+    int idx = xa * sx + ya * sy;
+    if (dx < 0) { dx = -dx; dy = -dy; idx = xb * sx + yb * sy; }
+    int stepy = sy;
+    if (dy < 0) { dy = -dy; stepy = -sy; }
+    int major = sx, minor = stepy;
+    if (dy > dx) { const int t = dx; dx = dy; dy = t; major = stepy; minor = sx; }
+    int err = dx - (dy + dy);
+    const int plus = dx + dx, minus = -(dy + dy);
+    for (int i = dx; i >= 0; i--) {
+        plot(idx);
+        const bool m = err < 0;
+        err += minus + (m ? plus : 0);
+        idx += major + (m ? minor : 0);
+    }
+}
+
+template <class Plot, class Span>
+TDS_HD void draw_triangle_fast(int W, int H, int sx, int sy, int x0, int y0, int x1, int y1, int x2, int y2,
+                               Plot&& plot, Span&& span) {
+    int xmin = x0 < x1 ? x0 : x1; xmin = xmin < x2 ? xmin : x2;
+    int xmax = x0 > x1 ? x0 : x1; xmax = xmax > x2 ? xmax : x2;
+    int ymin = y0 < y1 ? y0 : y1; ymin = ymin < y2 ? ymin : y2;
+    int ymax = y0 > y1 ? y0 : y1; ymax = ymax > y2 ? ymax : y2;
+    if (xmax - xmin <= 1 && ymax - ymin <= 1) {
+        if ((unsigned)x0 < (unsigned)W && (unsigned)y0 < (unsigned)H) plot(x0 * sx + y0 * sy);
+        if ((unsigned)x1 < (unsigned)W && (unsigned)y1 < (unsigned)H) plot(x1 * sx + y1 * sy);
+        if ((unsigned)x2 < (unsigned)W && (unsigned)y2 < (unsigned)H) plot(x2 * sx + y2 * sy);
+        return;
+    }
+    {   // outline v2->v0, v0->v1, v1->v2: one rolled loop keeps the code small (instruction cache)
+        int ax = x2, ay = y2, bx = x0, by = y0, cx = x1, cy = y1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int e = 0; e < 3; e++) {
+            draw_line8_fast(W, H, sx, sy, ax, ay, bx, by, plot);
+            const int tx_ = ax, ty_ = ay;
+            ax = bx; ay = by; bx = cx; by = cy; cx = tx_; cy = ty_;
+        }
+    }
+    if (ymax - ymin <= 1) return;
+    if (xmax < 0 || ymax < 0 || xmin >= W || ymin >= H) return;
+    int tx = x0, ty = y0, mx = x1, my = y1, bx = x2, by = y2, t;
+    if (my < ty) { t = tx; tx = mx; mx = t; t = ty; ty = my; my = t; }
+    if (by < my) { t = mx; mx = bx; bx = t; t = my; my = by; by = t; }
+    if (my < ty) { t = tx; tx = mx; mx = t; t = ty; ty = my; my = t; }
+    const int ylo = ty > 0 ? ty : 0;
+    const int yhi = (by - 1) < (H - 1) ? (by - 1) : (H - 1);
+    if (ylo > yhi) return;
+    const int dTB = edge_dx<int>(tx, ty, bx, by);
+    const int dTM = my > ty ? edge_dx<int>(tx, ty, mx, my) : 0;
+    const int dMB = by > my ? edge_dx<int>(mx, my, bx, by) : 0;
+    int xa = (tx << 16) + (ylo - ty) * dTB;
+    for (int y = ylo; y <= yhi; y++) {
+        const int xb = y < my ? (tx << 16) + (y - ty) * dTM : (mx << 16) + (y - my) * dMB;
+        const int xl = xa < xb ? xa : xb, xr = xa < xb ? xb : xa;
+        int c1 = (xl + 32768) >> 16, c2 = (xr + 32768) >> 16;
+        if (c2 >= 0 && c1 < W) {
+            if (c1 < 0) c1 = 0;
+            if (c2 >= W) c2 = W - 1;
+            span(c1 * sx + y * sy, c2 - c1 + 1, sx);
+        }
+        xa += dTB;
+    }
 }
 
 }  // namespace tds
