@@ -1,0 +1,133 @@
+"""Host-side logic of the Python layer on CPU: palette, map loading, generator / simulator plumbing, error
+behaviour without a GPU (the product path must fail loudly, never fall back)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import torchdrivesim_b200 as tds
+from torchdrivesim_b200 import palette as P
+from tests import util
+
+
+def test_palette_ranks_and_colors():
+    pal = P.build_palette(P.get_default_color_map(), P.get_default_rendering_levels(),
+                          ["road", "left_lane", "right_lane", "vehicle", "direction", "traffic_light_red",
+                           "traffic_light_green", "traffic_light_yellow"], ["vehicle"], True, ["red", "yellow", "green"])
+    cid = P.class_id
+    rank = lambda n: pal.rank[cid(n)]
+    assert rank("road") < rank("right_lane") < rank("left_lane") < rank("traffic_light_green") \
+        < rank("traffic_light_yellow") < rank("traffic_light_red") < rank("vehicle") < rank("direction")
+    assert tuple(pal.rgb[cid("road")]) == (155, 155, 155) and tuple(pal.rgb[cid("vehicle")]) == (32, 74, 135)
+    assert pal.active[cid("road")] == 1 and pal.active[cid("pedestrian")] == 0
+    assert pal.agent_type_class[0] == cid("vehicle") and pal.agent_type_class[1] == -1
+    assert [pal.tl_state_class[i] for i in range(3)] == [cid("traffic_light_red"), cid("traffic_light_yellow"),
+                                                         cid("traffic_light_green")]
+    # every default colour survives the cv2 quantisation floor(c/255*0.999*256) unchanged
+    for rgb in P.get_default_color_map().values():
+        assert P.quantize_color(rgb) == tuple(rgb)
+
+
+def test_static_map_loading_and_categories():
+    m = tds.StaticMap.from_npz(util.map_path("carla_Town01"))
+    assert m.verts.shape == (46233, 2) and m.faces.shape == (30750, 3) and m.left_handed
+    assert sorted(set(m.face_category_names)) == ["left_lane", "right_lane", "road"]
+    assert m.traffic_light_poses().shape == (36, 5)
+    c = m.world_center
+    assert 150 < c[0] < 250 and 100 < c[1] < 220
+    with pytest.raises(tds._lib.TdsError):
+        m.handle("cpu")
+
+
+@pytest.mark.needs_reference
+def test_mesh_json_loader_matches_npz_fixture():
+    root = "/root/reference/torchdrivesim/resources/maps/carla_Town02"
+    a = tds.StaticMap.from_mesh_json(os.path.join(root, "carla_Town02_mesh.json"),
+                                     os.path.join(root, "carla_Town02_stoplines.json"), left_handed=True)
+    b = tds.StaticMap.from_npz(util.map_path("carla_Town02"))
+    assert np.array_equal(a.verts, b.verts) and np.array_equal(a.faces, b.faces)
+    assert a.face_category_names == b.face_category_names and np.array_equal(a.stoplines, b.stoplines)
+
+
+def _sim(B=4, A=3, lights=True):
+    m = tds.StaticMap.from_npz(util.map_path("carla_Town02"))
+    km = tds.KinematicBicycle(left_handed=True)
+    km.set_params(lr=torch.full((B, A), 1.96))
+    km.set_state(torch.arange(B * A * 4, dtype=torch.float32).reshape(B, A, 4))
+    tc = None
+    if lights:
+        pos = torch.tensor(m.traffic_light_poses())[None].expand(B, -1, -1).contiguous()
+        tc = {"traffic_light": tds.TrafficLightControl(pos, replay_states=torch.arange(3).repeat(B, pos.shape[1], 2))}
+    return tds.Simulator(m, km, torch.ones(B, A, 2), torch.ones(B, A, dtype=torch.bool),
+                         tds.TorchDriveConfig(left_handed_coordinates=True), traffic_controls=tc)
+
+
+def test_simulator_plumbing_without_gpu():
+    sim = _sim()
+    assert sim.batch_size == 4 and sim.agent_count == 3 and sim.action_size == 2
+    assert sim.kinematic_model.left_handed
+    assert sim.get_world_center().shape == (4, 2)
+    scene = sim.birdview_mesh_generator.generate(
+        3, agent_state=sim.get_state()[:, None].expand(-1, 3, -1, -1),
+        present_mask=sim.get_present_mask()[:, None].expand(-1, 3, -1), traffic_lights=sim.traffic_controls["traffic_light"])
+    assert scene.agent_state.shape == (4, 3, 4) and scene.present.shape == (4, 3) and scene.tl_corners.shape == (4, 24, 4, 2)
+    assert scene.slice(1, 3).agent_state.shape == (2, 3, 4)
+    sub = sim.select_batch_elements(torch.tensor([2, 0]), in_place=False)
+    assert sub.batch_size == 2 and torch.equal(sub.get_state(), sim.get_state()[[2, 0]])
+    assert sub.traffic_controls["traffic_light"].corners.shape[0] == 2 and sim.batch_size == 4
+    cp = sim.copy()
+    cp.set_state(sim.get_state() + 1)
+    assert not torch.equal(cp.get_state(), sim.get_state())
+    # traffic light replay advances with the step counter (traffic_controls.py:127-136)
+    tl = sim.traffic_controls["traffic_light"]
+    tl.step(4)
+    assert int(tl.state[0, 0]) == 1
+    # there is no CPU fallback: compute on CPU tensors raises
+    for call in (lambda: sim.step(torch.zeros(4, 3, 2)), sim.compute_collision, sim.compute_offroad, sim.render_egocentric):
+        with pytest.raises(tds._lib.TdsError):
+            call()
+    with pytest.raises(tds._lib.TdsError):
+        sim.step(torch.zeros(4, 2, 2))
+
+
+def test_generator_rejects_unsupported_inputs():
+    sim = _sim(lights=False)
+    gen = sim.birdview_mesh_generator
+    st = sim.get_state()
+    per_cam = st[:, None].repeat(1, 3, 1, 1)                      # materialised per-camera states
+    with pytest.raises(tds._lib.TdsError):
+        gen.generate(3, agent_state=per_cam, present_mask=None)
+    with pytest.raises(NotImplementedError):
+        gen.generate(1, agent_state=st[:, None], waypoints=torch.zeros(4, 1, 2, 2))
+    big = gen.expand(2)
+    assert big.agent_size.shape[0] == 8 and big.world_center.shape[0] == 8
+
+
+def test_fit_action_inverts_the_oracle_step():
+    from oracle import kinematic as K
+    gen = torch.Generator().manual_seed(0)
+    st = torch.cat([torch.rand(5, 6, 2, generator=gen) * 100, torch.rand(5, 6, 1, generator=gen) * 6 - 3,
+                    torch.rand(5, 6, 1, generator=gen) * 5 + 1], -1)
+    act = torch.rand(5, 6, 2, generator=gen) * 0.8 - 0.4
+    lr = torch.full((5, 6), 1.96)
+    for lh in (False, True):
+        km = tds.KinematicBicycle(left_handed=lh)
+        km.set_params(lr=lr)
+        km.set_state(st)
+        nxt = K.bicycle_step(st, act, lr, 0.1, lh)
+        np.testing.assert_allclose(km.fit_action(nxt).numpy(), act.numpy(), atol=2e-4)
+    km2 = km.copy()
+    assert torch.equal(km2.get_state(), km.get_state()) and torch.equal(km2.lr, km.lr) and km2.left_handed
+    km2.extend(2)
+    assert km2.get_state().shape[0] == 10 and km2.lr.shape[0] == 10
+
+
+def test_traffic_control_corners_and_masking():
+    pos = torch.tensor([[[10.0, 5.0, 1.0, 4.0, 0.3], [0.0, 0.0, 2.0, 2.0, 0.0]]])
+    tc = tds.TrafficLightControl(pos, mask=torch.tensor([[True, False]]))
+    from oracle.raster import box_corners
+    np.testing.assert_allclose(tc.corners[0, 0].numpy(), box_corners(pos[0, :1].numpy())[0], rtol=1e-6, atol=1e-6)
+    assert float(tc.corners[0, 1].max()) == -1000.0          # masked controls sit at -1000 (traffic_controls.py:33)
+    assert tc.allowed_states == ["red", "yellow", "green"]
+    assert tc.extend(3, in_place=False).corners.shape[0] == 3
