@@ -47,6 +47,8 @@ const char* tds_last_error(void);
 #define TDS_MODEL_BICYCLE 0
 #define TDS_MODEL_BICYCLE_NO_REVERSING 1
 #define TDS_MODEL_UNICYCLE 2
+#define TDS_MODEL_SIMPLE 3   /* SimpleKinematicModel.step, kinematic.py:362-367 (action = d state / dt, 4 values) */
+#define TDS_MODEL_ORIENTED 4 /* OrientedKinematicModel.step, kinematic.py:384-389 (action xy in the agent frame)  */
 
 typedef struct {
     float dt;               /* seconds */
@@ -54,17 +56,21 @@ typedef struct {
     float max_steering;     /* action[1] scale for the bicycle, float32(pi/2) by default */
     float max_yaw_rate;     /* action[1] scale for the unicycle */
     int32_t left_handed;    /* negate steering / yaw rate (kinematic.py:466-467) */
+    float max_dx;           /* SIMPLE / ORIENTED action scales (kinematic.py:338-345): x, y */
+    float max_dpsi;         /*   orientation */
+    float max_dv;           /*   speed */
 } tds_kinematic_params_t;
 
-/* d_state [n,4] (x,y,psi,v), d_action [n,2], d_lr [n], d_model [n] int32 or NULL (then
- * uniform_model applies to every agent), d_out_state [n,4] (may alias d_state). */
-int tds_kinematic_step_fwd(const float* d_state, const float* d_action, const float* d_lr,
+/* d_state [n,4] (x,y,psi,v), d_action [n,action_dim] with action_dim 2 or 4 (models 0-2 read the first two
+ * values, models 3-4 need 4), d_lr [n], d_model [n] int32 or NULL (then uniform_model applies to every
+ * agent), d_out_state [n,4] (may alias d_state). */
+int tds_kinematic_step_fwd(const float* d_state, const float* d_action, int32_t action_dim, const float* d_lr,
                            const int32_t* d_model, int32_t uniform_model, int64_t n,
                            const tds_kinematic_params_t* params, float* d_out_state, void* stream);
 
-/* Backward of the above.  d_grad_out [n,4]; outputs d_grad_state [n,4], d_grad_action [n,2],
+/* Backward of the above.  d_grad_out [n,4]; outputs d_grad_state [n,4], d_grad_action [n,action_dim],
  * d_grad_lr [n] (any may be NULL). */
-int tds_kinematic_step_bwd(const float* d_state, const float* d_action, const float* d_lr,
+int tds_kinematic_step_bwd(const float* d_state, const float* d_action, int32_t action_dim, const float* d_lr,
                            const int32_t* d_model, int32_t uniform_model, int64_t n,
                            const tds_kinematic_params_t* params, const float* d_grad_out,
                            float* d_grad_state, float* d_grad_action, float* d_grad_lr, void* stream);
@@ -78,10 +84,11 @@ int tds_kinematic_step_bwd(const float* d_state, const float* d_action, const fl
 /* Element-wise API of the reference functions: d_box1, d_box2 [p,5] -> d_out [p]. */
 int tds_collision_pairwise_fwd(const float* d_box1, const float* d_box2, int64_t p, int32_t metric,
                                float* d_out, void* stream);
-/* discs only: d_grad_out [p] -> d_grad_box1, d_grad_box2 [p,5] */
-int tds_collision_discs_pairwise_bwd(const float* d_box1, const float* d_box2, int64_t p,
-                                     const float* d_grad_out, float* d_grad_box1, float* d_grad_box2,
-                                     void* stream);
+/* d_grad_out [p] -> d_grad_box1, d_grad_box2 [p,5] (either may be NULL).  The IoU gradient is the exact
+ * gradient of intersection / union (boundary-integral form), which is what the reference's autograd
+ * through its vertex formula evaluates. */
+int tds_collision_pairwise_bwd(const float* d_box1, const float* d_box2, int64_t p, int32_t metric,
+                               const float* d_grad_out, float* d_grad_box1, float* d_grad_box2, void* stream);
 
 /* Fused Simulator.compute_collision (simulator.py:1161-1194, 1064-1109):
  *   out[b,i] = sum_j o(ego_i, all_j) m[b,j] - max_j o(ego_i, all_j) m[b,j]
@@ -92,12 +99,12 @@ int tds_collision_discs_pairwise_bwd(const float* d_box1, const float* d_box2, i
 int tds_collision_allpairs_fwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
                                int32_t B, int32_t A, int32_t N, int32_t metric, int32_t ego_is_prefix,
                                float* d_out, int32_t* d_argmax, void* stream);
-/* discs only.  d_grad_ego [B,A,5] is overwritten, d_grad_all [B,N,5] is ACCUMULATED into
- * (the caller zero-fills it). */
-int tds_collision_discs_allpairs_bwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
-                                     int32_t B, int32_t A, int32_t N, const float* d_grad_out,
-                                     const int32_t* d_argmax, float* d_grad_ego, float* d_grad_all,
-                                     void* stream);
+/* Backward of the above (both metrics).  d_grad_ego [B,A,5] is overwritten, d_grad_all [B,N,5] is
+ * ACCUMULATED into (the caller zero-fills it). */
+int tds_collision_allpairs_bwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
+                               int32_t B, int32_t A, int32_t N, int32_t metric, int32_t ego_is_prefix,
+                               const float* d_grad_out, const int32_t* d_argmax, float* d_grad_ego,
+                               float* d_grad_all, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Static map: triangle mesh + uniform grids, built once per map per GPU.  Replaces the

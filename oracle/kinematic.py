@@ -13,6 +13,8 @@ import torch
 MODEL_BICYCLE = 0
 MODEL_BICYCLE_NO_REVERSING = 1
 MODEL_UNICYCLE = 2
+MODEL_SIMPLE = 3
+MODEL_ORIENTED = 4
 
 
 def bicycle_step(state, action, lr, dt=0.1, left_handed=False, max_acceleration=5.0, max_steering=math.pi / 2,
@@ -55,13 +57,29 @@ def unicycle_step(state, action, dt=0.1, max_acceleration=5.0, max_yaw_rate=math
     return torch.stack([x, y, psi, v], dim=-1)
 
 
+def simple_step(state, action, dt=0.1, max_dx=20.0, max_dpsi=10 * math.pi, max_dv=5.0, oriented=False):
+    """kinematic.py:362-367 (SimpleKinematicModel.step) and :384-389 (OrientedKinematicModel.step)."""
+    if oriented:
+        psi = state[..., 2:3]
+        c, s = torch.cos(psi), torch.sin(psi)
+        xy = torch.cat([c * action[..., 0:1] + (-s) * action[..., 1:2], s * action[..., 0:1] + c * action[..., 1:2]], -1)
+        action = torch.cat([xy, action[..., 2:]], dim=-1)
+    norm = torch.tensor([max_dx, max_dx, max_dpsi, max_dv], dtype=state.dtype)
+    return state + (action * norm) * dt
+
+
 def compound_step(state, action, lr, model, dt=0.1, left_handed=False, max_acceleration=5.0,
                   max_steering=math.pi / 2, max_yaw_rate=math.pi / 2):
     """Per-agent model id dispatch (what CompoundKinematicModel.step, kinematic.py:197-201, does by
     boolean-mask splitting).  model [...] int in {0 bicycle, 1 no-reversing bicycle, 2 unicycle}."""
-    lr_safe = torch.where(model == MODEL_UNICYCLE, torch.ones_like(lr), lr)
+    lr_safe = torch.where(model >= MODEL_UNICYCLE, torch.ones_like(lr), lr)
+    full_action, action = action, action[..., :2]
     b0 = bicycle_step(state, action, lr_safe, dt, left_handed, max_acceleration, max_steering, False)
     b1 = bicycle_step(state, action, lr_safe, dt, left_handed, max_acceleration, max_steering, True)
     u = unicycle_step(state, action, dt, max_acceleration, max_yaw_rate, left_handed)
     m = model.unsqueeze(-1)
-    return torch.where(m == MODEL_BICYCLE, b0, torch.where(m == MODEL_BICYCLE_NO_REVERSING, b1, u))
+    out = torch.where(m == MODEL_BICYCLE, b0, torch.where(m == MODEL_BICYCLE_NO_REVERSING, b1, u))
+    if full_action.shape[-1] == 4:
+        out = torch.where(m == MODEL_SIMPLE, simple_step(state, full_action, dt), out)
+        out = torch.where(m == MODEL_ORIENTED, simple_step(state, full_action, dt, oriented=True), out)
+    return out

@@ -59,9 +59,9 @@ def test_sass_is_sm100a_only():
 def test_invalid_arguments_are_reported_not_crashed():
     from torchdrivesim_b200 import _lib
     lib = _lib.load()
-    p = _lib.KinematicParams(0.1, 5.0, 1.57, 1.57, 0)
+    p = _lib.KinematicParams(0.1, 5.0, 1.57, 1.57, 0, 20.0, 31.4, 5.0)
     # null pointers with n > 0 -> error code + message, no launch
-    rc = lib.tds_kinematic_step_fwd(None, None, None, None, 0, 10, ctypes.byref(p), None, None)
+    rc = lib.tds_kinematic_step_fwd(None, None, 2, None, None, 0, 10, ctypes.byref(p), None, None)
     assert rc == 1 and b"null" in lib.tds_last_error()
     rc = lib.tds_collision_allpairs_fwd(None, None, None, 1, 1, 1, 7, 1, None, None, None)
     assert rc == 1

@@ -126,3 +126,54 @@ def test_simulator_collision_properties_full_size():
     pm = tds.collision_detection_with_discs(e, o).reshape(8, N, N)
     np.testing.assert_allclose(pm.cpu().numpy(), pm.transpose(1, 2).cpu().numpy(), rtol=0, atol=1e-6)
     assert float((torch.diagonal(pm, dim1=1, dim2=2) - 1).abs().max()) == 0.0
+
+
+def test_iou_backward_matches_float64_finite_differences():
+    """IoU backward (pairwise and fused all-pairs) against central differences of the float64 oracle."""
+    from oracle import iou as I
+    import torchdrivesim_b200 as tds
+    rng = np.random.default_rng(17)
+    P = 300
+    b1 = _boxes(1, P, rng, spread=2.0)[0]
+    b2 = _boxes(1, P, rng, spread=2.0)[0]
+    b2[:, :2] = b1[:, :2] + rng.normal(0, 1.5, (P, 2)).astype(np.float32)
+    t1 = torch.tensor(b1).cuda().requires_grad_(True)
+    t2 = torch.tensor(b2).cuda().requires_grad_(True)
+    out = tds.iou_differentiable(t1[None], t2[None])
+    out.sum().backward()
+    base = I.iou_pairwise(b1, b2)
+    np.testing.assert_allclose(out[0].detach().cpu().numpy(), base, rtol=IOU_RTOL, atol=IOU_ATOL)
+    eps = 1e-6
+    for which, (grad, arr) in enumerate(((t1.grad, b1), (t2.grad, b2))):
+        g = grad.cpu().numpy()
+        for k in range(5):
+            hi, lo = arr.astype(np.float64).copy(), arr.astype(np.float64).copy()
+            hi[:, k] += eps; lo[:, k] -= eps
+            args_hi = (hi, b2.astype(np.float64)) if which == 0 else (b1.astype(np.float64), hi)
+            args_lo = (lo, b2.astype(np.float64)) if which == 0 else (b1.astype(np.float64), lo)
+            fd = (I.iou_pairwise(*args_hi) - I.iou_pairwise(*args_lo)) / (2 * eps)
+            fd2 = (I.iou_pairwise(*[a if i != which else arr.astype(np.float64) + (np.arange(5) == k) * 10 * eps
+                                    for i, a in enumerate((b1.astype(np.float64), b2.astype(np.float64)))]) - base) / (10 * eps)
+            smooth = np.abs(fd - fd2) < 1e-3 + 1e-2 * np.abs(fd)     # skip kinks (a vertex crossing an edge)
+            ok = smooth & (base > 1e-4)
+            assert ok.sum() > 100
+            np.testing.assert_allclose(g[ok, k], fd[ok], rtol=2e-3, atol=2e-4)
+    assert float(t1.grad[out[0] == 0].abs().max()) == 0.0
+    # fused aggregate: gradient equals the sum of the pairwise gradients with the arg-max column removed
+    B, N = 2, 20
+    allb = _boxes(B, N, rng, spread=3.0)
+    mask = rng.uniform(size=(B, N)) > 0.2
+    a_g = torch.tensor(allb).cuda().requires_grad_(True)
+    w = torch.tensor(rng.standard_normal((B, N)).astype(np.float32)).cuda()
+    agg = tds.collision_allpairs(a_g, a_g, torch.tensor(mask).cuda(), "iou")
+    (agg * w).sum().backward()
+    a_p = torch.tensor(allb).cuda().requires_grad_(True)
+    e = a_p.unsqueeze(2).expand(-1, -1, N, -1).reshape(B, N * N, 5)
+    o = a_p.unsqueeze(1).expand(-1, N, -1, -1).reshape(B, N * N, 5)
+    pm = tds.iou_differentiable(e, o).reshape(B, N, N)
+    eye = torch.eye(N, dtype=torch.bool).cuda()
+    pm = torch.where(eye, torch.ones_like(pm), pm) * torch.tensor(mask).cuda()[:, None, :]
+    ref = pm.sum(-1) - pm.max(-1)[0]
+    (ref * w).sum().backward()
+    np.testing.assert_allclose(agg.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(a_g.grad.cpu().numpy(), a_p.grad.cpu().numpy(), rtol=1e-3, atol=1e-4)

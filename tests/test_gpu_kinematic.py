@@ -104,3 +104,37 @@ def test_edge_cases():
     km.set_state(torch.zeros(1, 3, 4))
     with pytest.raises(tds._lib.TdsError):        # CPU tensors: no fallback
         km.step(torch.zeros(1, 3, 2))
+
+
+def test_simple_and_oriented_models_and_padded_compound():
+    """SimpleKinematicModel / OrientedKinematicModel (kinematic.py:328-397) and a compound batch whose action
+    is padded to 4 values, forward and backward."""
+    from oracle import kinematic as K
+    import torchdrivesim_b200 as tds
+    gen = torch.Generator().manual_seed(5)
+    B, A = 4, 21
+    state, _, lr = _rand(B, A, gen)
+    act4 = torch.rand(B, A, 4, generator=gen) * 2 - 1
+    for cls, oriented in ((tds.SimpleKinematicModel, False), (tds.OrientedKinematicModel, True)):
+        km = cls()
+        km.set_state(state.cuda())
+        km.step(act4.cuda())
+        ref = K.simple_step(state, act4, oriented=oriented)
+        np.testing.assert_allclose(km.get_state().cpu().numpy(), ref.numpy(), rtol=RTOL, atol=ATOL)
+        nxt = km.get_state()
+        km.set_state(state.cuda())
+        np.testing.assert_allclose(km.fit_action(nxt).cpu().numpy(), act4.numpy(), atol=5e-4)
+    model = torch.randint(0, 5, (B, A), generator=gen)
+    w = torch.randn(B, A, 4, generator=gen)
+    s_o, a_o = state.clone().requires_grad_(True), act4.clone().requires_grad_(True)
+    out_o = K.compound_step(s_o, a_o, lr, model, 0.1, True)
+    (out_o * w).sum().backward()
+    km = tds.FusedCompoundKinematicModel(model.cuda(), left_handed=True, action_size=4)
+    s_g, a_g = state.clone().cuda().requires_grad_(True), act4.clone().cuda().requires_grad_(True)
+    km.set_params(lr=lr.cuda())
+    km.set_state(s_g)
+    km.step(a_g)
+    (km.get_state() * w.cuda()).sum().backward()
+    np.testing.assert_allclose(km.get_state().detach().cpu().numpy(), out_o.detach().numpy(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(s_g.grad.cpu().numpy(), s_o.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(a_g.grad.cpu().numpy(), a_o.grad.numpy(), rtol=1e-4, atol=1e-5)

@@ -6,7 +6,7 @@ CUDA device; there is no CPU fallback and every op raises if either is missing.
 """
 from . import _lib  # noqa: F401
 from .kinematic import (BicycleNoReversing, FusedCompoundKinematicModel, KinematicBicycle,  # noqa: F401
-                        KinematicModel, KinematicUnicycle)
+                        KinematicModel, KinematicUnicycle, OrientedKinematicModel, SimpleKinematicModel)
 from .maps import MapSet, StaticMap  # noqa: F401
 from .mesh import B200BirdviewMeshGenerator, BirdviewScene  # noqa: F401
 from .rendering import (B200Renderer, B200RendererConfig, BirdviewRenderer, RendererConfig,  # noqa: F401
@@ -14,6 +14,8 @@ from .rendering import (B200Renderer, B200RendererConfig, BirdviewRenderer, Rend
 from .infractions import (collision_allpairs, collision_detection_with_discs, iou_differentiable,  # noqa: F401
                           offroad_infraction_loss)
 from .simulator import CollisionMetric, Simulator, TorchDriveConfig  # noqa: F401
+from .graph import GraphedHotPath  # noqa: F401
+from . import distributed, ops  # noqa: F401
 from .traffic_controls import BaseTrafficControl, StopSignControl, TrafficLightControl, YieldControl  # noqa: F401
 
 __version__ = "0.1.0"

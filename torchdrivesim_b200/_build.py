@@ -35,16 +35,20 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = None) -> str:
+    """extra_flags / out_path build an experimental variant next to the default library (profiling aid)."""
+    lib_path = out_path or LIB_PATH
+    if not force and out_path is None and not _stale():
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
+    tag = "" if out_path is None else "." + os.path.basename(out_path)
     for src in SOURCES:
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(OUT_DIR, src.replace(".cu", tag + ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
@@ -53,8 +57,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-lcudart"])
-    return LIB_PATH
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs + ["-lcudart"])
+    return lib_path
 
 
 if __name__ == "__main__":

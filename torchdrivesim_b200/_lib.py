@@ -19,6 +19,8 @@ MAX_MAPS = 8
 MODEL_BICYCLE = 0
 MODEL_BICYCLE_NO_REVERSING = 1
 MODEL_UNICYCLE = 2
+MODEL_SIMPLE = 3
+MODEL_ORIENTED = 4
 METRIC_DISCS = 0
 METRIC_IOU = 1
 
@@ -29,7 +31,8 @@ class TdsError(RuntimeError):
 
 class KinematicParams(ctypes.Structure):
     _fields_ = [("dt", c_float), ("max_acceleration", c_float), ("max_steering", c_float),
-                ("max_yaw_rate", c_float), ("left_handed", c_int32)]
+                ("max_yaw_rate", c_float), ("left_handed", c_int32), ("max_dx", c_float), ("max_dpsi", c_float),
+                ("max_dv", c_float)]
 
 
 class Palette(ctypes.Structure):
@@ -50,16 +53,16 @@ class MapInfo(ctypes.Structure):
 SIGNATURES = {
     "tds_version": (c_int32, []),
     "tds_last_error": (c_char_p, []),
-    "tds_kinematic_step_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
+    "tds_kinematic_step_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int64,
                                          POINTER(KinematicParams), c_void_p, c_void_p]),
-    "tds_kinematic_step_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
+    "tds_kinematic_step_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int64,
                                          POINTER(KinematicParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tds_collision_pairwise_fwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
-    "tds_collision_discs_pairwise_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tds_collision_pairwise_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tds_collision_allpairs_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                              c_void_p, c_void_p, c_void_p]),
-    "tds_collision_discs_allpairs_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
-                                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tds_collision_allpairs_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tds_map_create": (c_void_p, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_float, c_float]),
     "tds_map_destroy": (None, [c_void_p]),
     "tds_map_info": (c_int32, [c_void_p, POINTER(MapInfo)]),
@@ -79,7 +82,8 @@ _LIB = None
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # TDS_B200_LIB selects an experimental build of the same ABI (profiling aid); default: the in-tree build
+    return os.environ.get("TDS_B200_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> ctypes.CDLL:

@@ -147,6 +147,107 @@ __device__ float iou_pair(const Box& p, const Box& q) {
     return iou == iou ? iou : 0.0f;               // nan_to_num, simulator.py:1103
 }
 
+// ---- IoU backward.  d(intersection area) is the boundary integral of the normal velocity: every edge of
+// the clipped polygon lies either on a face of box q (it moves with q's pose and size) or on a face of box p
+// (it moves with p's size).  Each polygon vertex carries the tag of the edge that leaves it:
+//   0..3 = q's edge k (corner k -> k+1: faces +y_q, -x_q, -y_q, +x_q), 4..7 = p's faces +x, -x, +y, -y.
+struct TaggedPoly {
+    float x[10], y[10];
+    int tag[10];
+    int n;
+};
+
+__device__ __forceinline__ void clip_axis_tagged(const TaggedPoly& in, TaggedPoly& out, int axis, float sign, float bound,
+                                                 int plane_tag) {
+    int m = 0;
+    for (int i = 0; i < in.n; i++) {
+        const int j = (i + 1 == in.n) ? 0 : i + 1;
+        const float ax = in.x[i], ay = in.y[i], bx = in.x[j], by = in.y[j];
+        const float da = sign * (axis ? ay : ax) - bound;
+        const float db = sign * (axis ? by : bx) - bound;
+        const bool ina = da <= 0.0f, inb = db <= 0.0f;
+        if (ina) { out.x[m] = ax; out.y[m] = ay; out.tag[m] = in.tag[i]; m++; }
+        if (ina != inb) {
+            const float t = da / (da - db);
+            out.x[m] = ax + t * (bx - ax);
+            out.y[m] = ay + t * (by - ay);
+            // leaving the half-plane: the next edge runs along the clip line; entering: it continues on edge i
+            out.tag[m] = ina ? plane_tag : in.tag[i];
+            m++;
+        }
+    }
+    out.n = m;
+}
+
+// accumulates wgt * d IoU / d(box p), d(box q) into gp, gq (x, y, l, w, psi).  Returns false for no overlap.
+__device__ bool iou_pair_grad(const float* praw, const float* qraw, float wgt, float* gp, float* gq) {
+    const Box p = make_box(praw[0], praw[1], praw[2], praw[3], praw[4]);
+    const Box q = make_box(qraw[0], qraw[1], qraw[2], qraw[3], qraw[4]);
+    const float dx = q.x - p.x, dy = q.y - p.y;
+    const float rp = 0.5f * sqrtf(p.l * p.l + p.w * p.w), rq = 0.5f * sqrtf(q.l * q.l + q.w * q.w);
+    const float reach = rp + rq;
+    if (dx * dx + dy * dy > reach * reach * 1.0001f + 1e-6f) return false;
+    const float cr = p.c * q.c + p.s * q.s, sr = p.c * q.s - p.s * q.c;     // rotation of q in p's frame
+    const float tx = p.c * dx + p.s * dy, ty = p.c * dy - p.s * dx;         // centre of q in p's frame
+    const float hx = 0.5f * q.l, hy = 0.5f * q.w;
+    TaggedPoly a, b;
+    const float sx[4] = {1.f, -1.f, -1.f, 1.f}, sy[4] = {1.f, 1.f, -1.f, -1.f};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float ux = sx[k] * hx, uy = sy[k] * hy;
+        a.x[k] = tx + (ux * cr - uy * sr);
+        a.y[k] = ty + (ux * sr + uy * cr);
+        a.tag[k] = k;
+    }
+    a.n = 4;
+    const float bx = 0.5f * p.l, by = 0.5f * p.w;
+    clip_axis_tagged(a, b, 0, 1.f, bx, 4);
+    clip_axis_tagged(b, a, 0, -1.f, bx, 5);
+    clip_axis_tagged(a, b, 1, 1.f, by, 6);
+    clip_axis_tagged(b, a, 1, -1.f, by, 7);
+    if (a.n < 3) return false;
+    float tot = 0.0f;
+    // gradients of the intersection area in p's frame
+    float g_tx = 0.f, g_ty = 0.f, g_rot = 0.f, g_lq = 0.f, g_wq = 0.f, g_lp = 0.f, g_wp = 0.f;
+    // outward normals of q's faces in p's frame: +y_q, -x_q, -y_q, +x_q
+    const float nqx[4] = {-sr, -cr, sr, cr}, nqy[4] = {cr, -sr, -cr, sr};
+    for (int i = 0; i < a.n; i++) {
+        const int j = (i + 1 == a.n) ? 0 : i + 1;
+        tot += a.x[i] * a.y[j] - a.y[i] * a.x[j];
+        const float ex = a.x[j] - a.x[i], ey = a.y[j] - a.y[i];
+        const float len = sqrtf(ex * ex + ey * ey);
+        const int tg = a.tag[i];
+        if (tg < 4) {
+            const float nx = nqx[tg], ny = nqy[tg];
+            g_tx += nx * len;
+            g_ty += ny * len;
+            const float mx = 0.5f * (a.x[i] + a.x[j]) - tx, my = 0.5f * (a.y[i] + a.y[j]) - ty;
+            g_rot += (nx * (-my) + ny * mx) * len;          // n . (z x (m - t))
+            if (tg == 0 || tg == 2) g_wq += 0.5f * len; else g_lq += 0.5f * len;
+        } else if (tg < 6) {
+            g_lp += 0.5f * len;
+        } else {
+            g_wp += 0.5f * len;
+        }
+    }
+    const float inter = 0.5f * fabsf(tot);
+    const float a1 = p.l * p.w, a2 = q.l * q.w;
+    const float U = a1 + a2 - inter;
+    if (!(U > 0.0f) || !(inter > 0.0f)) return false;
+    // IoU = A / U, U = a1 + a2 - A:  dIoU = kA dA - kU d(a1 + a2)
+    const float kA = wgt * (1.0f / U + inter / (U * U));
+    const float kU = wgt * inter / (U * U);
+    // chain to world parameters: t = R(-psi_p) (c_q - c_p), rot = psi_q - psi_p
+    const float wx = p.c * g_tx - p.s * g_ty, wy = p.s * g_tx + p.c * g_ty;   // R(psi_p) g_t
+    gq[0] += kA * wx; gq[1] += kA * wy;
+    gp[0] -= kA * wx; gp[1] -= kA * wy;
+    gq[4] += kA * g_rot;
+    gp[4] += kA * (-g_rot + g_tx * ty - g_ty * tx);
+    gq[2] += kA * g_lq - kU * q.w; gq[3] += kA * g_wq - kU * q.l;
+    gp[2] += kA * g_lp - kU * p.w; gp[3] += kA * g_wp - kU * p.l;
+    return true;
+}
+
 // ---------------------------------------------------------------- element-wise API
 __global__ void __launch_bounds__(256) pairwise_fwd_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
                                                            int64_t n, int metric, float* __restrict__ out) {
@@ -206,13 +307,14 @@ __device__ __forceinline__ bool discs_pair_grad(const float* p, const float* q, 
     return true;
 }
 
-__global__ void __launch_bounds__(256) discs_pairwise_bwd_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
-                                                                 int64_t n, const float* __restrict__ gout,
-                                                                 float* __restrict__ g1, float* __restrict__ g2) {
+__global__ void __launch_bounds__(256) pairwise_bwd_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
+                                                           int64_t n, int metric, const float* __restrict__ gout,
+                                                           float* __restrict__ g1, float* __restrict__ g2) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     BoxGrad gp = {}, gq = {};
-    discs_pair_grad(b1 + 5 * i, b2 + 5 * i, gout[i], gp, gq);
+    if (metric == TDS_METRIC_DISCS) discs_pair_grad(b1 + 5 * i, b2 + 5 * i, gout[i], gp, gq);
+    else iou_pair_grad(b1 + 5 * i, b2 + 5 * i, gout[i], gp.g, gq.g);
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         if (g1) g1[5 * i + k] = gp.g[k];
@@ -302,9 +404,10 @@ __global__ void __launch_bounds__(kWarps * 32) allpairs_fwd_kernel(const float* 
     }
 }
 
-__global__ void __launch_bounds__(kWarps * 32) discs_allpairs_bwd_kernel(const float* __restrict__ ego, const float* __restrict__ all,
-                                                                        const uint8_t* __restrict__ mask, int A, int N,
-                                                                        const float* __restrict__ gout,
+template <int METRIC>
+__global__ void __launch_bounds__(kWarps * 32) allpairs_bwd_kernel(const float* __restrict__ ego, const float* __restrict__ all,
+                                                                  const uint8_t* __restrict__ mask, int A, int N,
+                                                                  int ego_is_prefix, const float* __restrict__ gout,
                                                                         const int32_t* __restrict__ argmax,
                                                                         float* __restrict__ g_ego, float* __restrict__ g_all) {
     extern __shared__ float gcol[];              // [N][5] column gradients of this CTA
@@ -326,8 +429,11 @@ __global__ void __launch_bounds__(kWarps * 32) discs_allpairs_bwd_kernel(const f
             // d out_i / d o_ij = m_j (1 - [j == argmax_i])
             const float wgt = (mb[j] && j != am) ? g : 0.0f;
             if (wgt == 0.0f) continue;
+            if (METRIC == TDS_METRIC_IOU && ego_is_prefix && j == i) continue;   // o(i,i) := 1, a constant
             BoxGrad gq = {};
-            if (discs_pair_grad(p, allb + 5 * j, wgt, gp, gq)) {
+            const bool hit = METRIC == TDS_METRIC_DISCS ? discs_pair_grad(p, allb + 5 * j, wgt, gp, gq)
+                                                        : iou_pair_grad(p, allb + 5 * j, wgt, gp.g, gq.g);
+            if (hit) {
 #pragma unroll
                 for (int k = 0; k < 5; k++) atomicAdd(&gcol[5 * j + k], gq.g[k]);
             }
@@ -358,14 +464,15 @@ extern "C" int tds_collision_pairwise_fwd(const float* d_box1, const float* d_bo
     return TDS_OK;
 }
 
-extern "C" int tds_collision_discs_pairwise_bwd(const float* d_box1, const float* d_box2, int64_t p,
-                                                const float* d_grad_out, float* d_grad_box1, float* d_grad_box2,
-                                                void* stream) {
-    TDS_REQUIRE(d_box1 && d_box2 && d_grad_out, "collision_pairwise_bwd: null pointer");
+extern "C" int tds_collision_pairwise_bwd(const float* d_box1, const float* d_box2, int64_t p, int32_t metric,
+                                          const float* d_grad_out, float* d_grad_box1, float* d_grad_box2,
+                                          void* stream) {
     TDS_REQUIRE(p >= 0, "collision_pairwise_bwd: negative size");
     if (p == 0) return TDS_OK;
-    discs_pairwise_bwd_kernel<<<(unsigned)((p + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_box1, d_box2, p, d_grad_out,
-                                                                                             d_grad_box1, d_grad_box2);
+    TDS_REQUIRE(d_box1 && d_box2 && d_grad_out, "collision_pairwise_bwd: null pointer");
+    TDS_REQUIRE(metric == TDS_METRIC_DISCS || metric == TDS_METRIC_IOU, "collision_pairwise_bwd: unknown metric %d", metric);
+    pairwise_bwd_kernel<<<(unsigned)((p + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_box1, d_box2, p, metric, d_grad_out,
+                                                                                       d_grad_box1, d_grad_box2);
     TDS_LAUNCH_OK();
     return TDS_OK;
 }
@@ -399,10 +506,11 @@ extern "C" int tds_collision_allpairs_fwd(const float* d_ego_box, const float* d
     return TDS_OK;
 }
 
-extern "C" int tds_collision_discs_allpairs_bwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
-                                                int32_t B, int32_t A, int32_t N, const float* d_grad_out,
-                                                const int32_t* d_argmax, float* d_grad_ego, float* d_grad_all,
-                                                void* stream) {
+extern "C" int tds_collision_allpairs_bwd(const float* d_ego_box, const float* d_all_box, const uint8_t* d_mask,
+                                          int32_t B, int32_t A, int32_t N, int32_t metric, int32_t ego_is_prefix,
+                                          const float* d_grad_out, const int32_t* d_argmax, float* d_grad_ego,
+                                          float* d_grad_all, void* stream) {
+    TDS_REQUIRE(metric == TDS_METRIC_DISCS || metric == TDS_METRIC_IOU, "collision_allpairs_bwd: unknown metric %d", metric);
     TDS_REQUIRE(B >= 0 && A >= 0 && N >= 0, "collision_allpairs_bwd: negative size");
     if (B == 0 || A == 0 || N == 0) return TDS_OK;
     TDS_REQUIRE(d_ego_box && d_all_box && d_mask && d_grad_out && d_argmax && d_grad_ego && d_grad_all,
@@ -411,10 +519,17 @@ extern "C" int tds_collision_discs_allpairs_bwd(const float* d_ego_box, const fl
     const dim3 grid((A + kRowsPerCta - 1) / kRowsPerCta, B);
     const size_t smem = (size_t)N * 5 * sizeof(float);
     TDS_REQUIRE(smem <= 200 * 1024, "collision_allpairs_bwd: N=%d does not fit shared memory", N);
-    if (smem > 48 * 1024)
-        TDS_CUDA_OK(cudaFuncSetAttribute(discs_allpairs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    discs_allpairs_bwd_kernel<<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(d_ego_box, d_all_box, d_mask, A, N,
-                                                                                d_grad_out, d_argmax, d_grad_ego, d_grad_all);
+    if (metric == TDS_METRIC_DISCS) {
+        if (smem > 48 * 1024)
+            TDS_CUDA_OK(cudaFuncSetAttribute(allpairs_bwd_kernel<TDS_METRIC_DISCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allpairs_bwd_kernel<TDS_METRIC_DISCS><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
+            d_ego_box, d_all_box, d_mask, A, N, ego_is_prefix, d_grad_out, d_argmax, d_grad_ego, d_grad_all);
+    } else {
+        if (smem > 48 * 1024)
+            TDS_CUDA_OK(cudaFuncSetAttribute(allpairs_bwd_kernel<TDS_METRIC_IOU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allpairs_bwd_kernel<TDS_METRIC_IOU><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
+            d_ego_box, d_all_box, d_mask, A, N, ego_is_prefix, d_grad_out, d_argmax, d_grad_ego, d_grad_all);
+    }
     TDS_LAUNCH_OK();
     return TDS_OK;
 }

@@ -10,19 +10,27 @@
 namespace {
 
 struct KinIn {
-    float x, y, psi, v, a0, a1, lr;
+    float x, y, psi, v, a0, a1, a2, a3, lr;
     int model;
 };
 
-__device__ __forceinline__ KinIn load_agent(const float* state, const float* action, const float* lr,
+__device__ __forceinline__ bool is_free_model(int model) { return model == TDS_MODEL_SIMPLE || model == TDS_MODEL_ORIENTED; }
+
+__device__ __forceinline__ KinIn load_agent(const float* state, const float* action, int action_dim, const float* lr,
                                             const int32_t* model, int uniform_model, int64_t i) {
     const float4 s = reinterpret_cast<const float4*>(state)[i];
-    const float2 a = reinterpret_cast<const float2*>(action)[i];
     KinIn k;
     k.x = s.x; k.y = s.y; k.psi = s.z; k.v = s.w;
-    k.a0 = a.x; k.a1 = a.y;
+    k.a2 = k.a3 = 0.0f;
+    if (action_dim == 4) {
+        const float4 a = reinterpret_cast<const float4*>(action)[i];
+        k.a0 = a.x; k.a1 = a.y; k.a2 = a.z; k.a3 = a.w;
+    } else {
+        const float2 a = reinterpret_cast<const float2*>(action)[i];
+        k.a0 = a.x; k.a1 = a.y;
+    }
     k.model = model ? model[i] : uniform_model;
-    k.lr = (k.model == TDS_MODEL_UNICYCLE || lr == nullptr) ? 1.0f : lr[i];
+    k.lr = (k.model >= TDS_MODEL_UNICYCLE || lr == nullptr) ? 1.0f : lr[i];
     return k;
 }
 
@@ -50,12 +58,29 @@ __device__ __forceinline__ Controls controls(const KinIn& k, const tds_kinematic
 }
 
 __global__ void __launch_bounds__(256) kin_fwd_kernel(const float* __restrict__ state, const float* __restrict__ action,
-                                                      const float* __restrict__ lr, const int32_t* __restrict__ model,
-                                                      int uniform_model, int64_t n, tds_kinematic_params_t p,
-                                                      float* __restrict__ out) {
+                                                      int action_dim, const float* __restrict__ lr,
+                                                      const int32_t* __restrict__ model, int uniform_model, int64_t n,
+                                                      tds_kinematic_params_t p, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const KinIn k = load_agent(state, action, lr, model, uniform_model, i);
+    const KinIn k = load_agent(state, action, action_dim, lr, model, uniform_model, i);
+    if (is_free_model(k.model)) {
+        // state += (action * [max_dx, max_dx, max_dpsi, max_dv]) * dt; ORIENTED rotates the xy action by psi first
+        float ax = k.a0, ay = k.a1;
+        if (k.model == TDS_MODEL_ORIENTED) {
+            float s, co;
+            tds::sincos_cr(k.psi, s, co);
+            ax = co * k.a0 + (-s) * k.a1;
+            ay = s * k.a0 + co * k.a1;
+        }
+        float4 o;
+        o.x = k.x + (ax * p.max_dx) * p.dt;
+        o.y = k.y + (ay * p.max_dx) * p.dt;
+        o.z = k.psi + (k.a2 * p.max_dpsi) * p.dt;
+        o.w = k.v + (k.a3 * p.max_dv) * p.dt;
+        reinterpret_cast<float4*>(out)[i] = o;
+        return;
+    }
     const Controls c = controls(k, p);
     const float v = k.v + c.acc * p.dt;
     float4 o;
@@ -77,16 +102,40 @@ __global__ void __launch_bounds__(256) kin_fwd_kernel(const float* __restrict__ 
     reinterpret_cast<float4*>(out)[i] = o;
 }
 
+__device__ __forceinline__ void store_action_grad(float* g_action, int action_dim, int64_t i, float g0, float g1, float g2,
+                                                  float g3) {
+    if (!g_action) return;
+    if (action_dim == 4) reinterpret_cast<float4*>(g_action)[i] = make_float4(g0, g1, g2, g3);
+    else reinterpret_cast<float2*>(g_action)[i] = make_float2(g0, g1);
+}
+
 __global__ void __launch_bounds__(256) kin_bwd_kernel(const float* __restrict__ state, const float* __restrict__ action,
-                                                      const float* __restrict__ lr, const int32_t* __restrict__ model,
-                                                      int uniform_model, int64_t n, tds_kinematic_params_t p,
-                                                      const float* __restrict__ grad_out, float* __restrict__ g_state,
-                                                      float* __restrict__ g_action, float* __restrict__ g_lr) {
+                                                      int action_dim, const float* __restrict__ lr,
+                                                      const int32_t* __restrict__ model, int uniform_model, int64_t n,
+                                                      tds_kinematic_params_t p, const float* __restrict__ grad_out,
+                                                      float* __restrict__ g_state, float* __restrict__ g_action,
+                                                      float* __restrict__ g_lr) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const KinIn k = load_agent(state, action, lr, model, uniform_model, i);
-    const Controls c = controls(k, p);
+    const KinIn k = load_agent(state, action, action_dim, lr, model, uniform_model, i);
     const float4 g = reinterpret_cast<const float4*>(grad_out)[i];   // d/d(x', y', psi', v')
+    if (is_free_model(k.model)) {
+        const float sx = p.max_dx * p.dt;
+        float gpsi = g.z, ga0 = g.x * sx, ga1 = g.y * sx;
+        if (k.model == TDS_MODEL_ORIENTED) {
+            float s, co;
+            tds::sincos_cr(k.psi, s, co);
+            const float xr = co * k.a0 - s * k.a1, yr = s * k.a0 + co * k.a1;
+            gpsi += (g.y * xr - g.x * yr) * sx;
+            ga0 = (g.x * co + g.y * s) * sx;
+            ga1 = (g.y * co - g.x * s) * sx;
+        }
+        if (g_state) reinterpret_cast<float4*>(g_state)[i] = make_float4(g.x, g.y, gpsi, g.w);
+        store_action_grad(g_action, action_dim, i, ga0, ga1, g.z * p.max_dpsi * p.dt, g.w * p.max_dv * p.dt);
+        if (g_lr) g_lr[i] = 0.0f;
+        return;
+    }
+    const Controls c = controls(k, p);
     const float v = k.v + c.acc * p.dt;
     const float dt = p.dt;
     float gv, gpsi, gang, glr = 0.0f;
@@ -114,46 +163,50 @@ __global__ void __launch_bounds__(256) kin_bwd_kernel(const float* __restrict__ 
     if (p.left_handed) gang = -gang;
     const float ang_scale = k.model == TDS_MODEL_UNICYCLE ? p.max_yaw_rate : p.max_steering;
     if (g_state) reinterpret_cast<float4*>(g_state)[i] = make_float4(g.x, g.y, gpsi, gv_in);
-    if (g_action) reinterpret_cast<float2*>(g_action)[i] = make_float2(gacc * p.max_acceleration, gang * ang_scale);
+    store_action_grad(g_action, action_dim, i, gacc * p.max_acceleration, gang * ang_scale, 0.0f, 0.0f);
     if (g_lr) g_lr[i] = glr;
 }
 
-int check(const float* state, const float* action, int64_t n, const tds_kinematic_params_t* p, int32_t uniform_model) {
+int check(const float* state, const float* action, int action_dim, const int32_t* model, int64_t n,
+          const tds_kinematic_params_t* p, int32_t uniform_model) {
     TDS_REQUIRE(state && action && p, "kinematic: null pointer");
     TDS_REQUIRE(n >= 0, "kinematic: negative n");
-    TDS_REQUIRE(uniform_model >= 0 && uniform_model <= TDS_MODEL_UNICYCLE, "kinematic: unknown model %d", uniform_model);
+    TDS_REQUIRE(action_dim == 2 || action_dim == 4, "kinematic: action_dim must be 2 or 4, got %d", action_dim);
+    TDS_REQUIRE(uniform_model >= 0 && uniform_model <= TDS_MODEL_ORIENTED, "kinematic: unknown model %d", uniform_model);
+    TDS_REQUIRE(action_dim == 4 || (model == nullptr && uniform_model <= TDS_MODEL_UNICYCLE) || model != nullptr,
+                "kinematic: models 3/4 need a 4-value action");
     TDS_REQUIRE(p->dt > 0.0f, "kinematic: dt must be positive");
     return TDS_OK;
 }
 
 }  // namespace
 
-extern "C" int tds_kinematic_step_fwd(const float* d_state, const float* d_action, const float* d_lr,
+extern "C" int tds_kinematic_step_fwd(const float* d_state, const float* d_action, int32_t action_dim, const float* d_lr,
                                       const int32_t* d_model, int32_t uniform_model, int64_t n,
                                       const tds_kinematic_params_t* params, float* d_out_state, void* stream) {
     if (n == 0) return TDS_OK;
-    if (int e = check(d_state, d_action, n, params, uniform_model)) return e;
+    if (int e = check(d_state, d_action, action_dim, d_model, n, params, uniform_model)) return e;
     TDS_REQUIRE(d_out_state, "kinematic: null output");
     if (n == 0) return TDS_OK;
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    kin_fwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_state, d_action, d_lr, d_model, uniform_model, n,
+    kin_fwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_state, d_action, action_dim, d_lr, d_model, uniform_model, n,
                                                                 *params, d_out_state);
     TDS_LAUNCH_OK();
     return TDS_OK;
 }
 
-extern "C" int tds_kinematic_step_bwd(const float* d_state, const float* d_action, const float* d_lr,
+extern "C" int tds_kinematic_step_bwd(const float* d_state, const float* d_action, int32_t action_dim, const float* d_lr,
                                       const int32_t* d_model, int32_t uniform_model, int64_t n,
                                       const tds_kinematic_params_t* params, const float* d_grad_out,
                                       float* d_grad_state, float* d_grad_action, float* d_grad_lr, void* stream) {
     if (n == 0) return TDS_OK;
-    if (int e = check(d_state, d_action, n, params, uniform_model)) return e;
+    if (int e = check(d_state, d_action, action_dim, d_model, n, params, uniform_model)) return e;
     TDS_REQUIRE(d_grad_out, "kinematic: null grad_out");
     if (n == 0) return TDS_OK;
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    kin_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_state, d_action, d_lr, d_model, uniform_model, n,
+    kin_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_state, d_action, action_dim, d_lr, d_model, uniform_model, n,
                                                                 *params, d_grad_out, d_grad_state, d_grad_action,
                                                                 d_grad_lr);
     TDS_LAUNCH_OK();

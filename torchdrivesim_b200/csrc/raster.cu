@@ -113,12 +113,12 @@ __global__ void __launch_bounds__(128) dyn_prep_kernel(int B, int N, int L, int 
 struct Camera {
     float ncx, ncy;            // -camera position
     float S, C, scale, fmin, half;
-    float ea[4], eb[4], ec[4]; // view-quad edge functions (utils.py:99-122)
+    const float* edges;        // view-quad edge functions a[4], b[4], c[4] (utils.py:99-122), in shared memory
     int res;
 };
 
 __device__ __forceinline__ void make_camera(Camera& cam, float cx, float cy, float S, float C, float scale, int res,
-                                            float qx[4], float qy[4]) {
+                                            float qx[4], float qy[4], float* edges, bool write_edges) {
     cam.ncx = -cx; cam.ncy = -cy; cam.S = S; cam.C = C; cam.scale = scale; cam.res = res;
     cam.fmin = (float)res;
     cam.half = (float)res / 2.0f;
@@ -140,19 +140,23 @@ __device__ __forceinline__ void make_camera(Camera& cam, float cx, float cy, flo
         qx[i] = mx + (qx[i] - mx) * 1.05f;
         qy[i] = my + (qy[i] - my) * 1.05f;
     }
+    cam.edges = edges;
+    if (write_edges) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int j = (i + 1) & 3;
-        cam.ea[i] = qy[j] - qy[i];
-        cam.eb[i] = qx[i] - qx[j];
-        cam.ec[i] = (-cam.ea[i]) * qx[i] - cam.eb[i] * qy[i];
+        for (int i = 0; i < 4; i++) {
+            const int j = (i + 1) & 3;
+            const float ea = qy[j] - qy[i], eb = qx[i] - qx[j];
+            edges[i] = ea;
+            edges[4 + i] = eb;
+            edges[8 + i] = (-ea) * qx[i] - eb * qy[i];
+        }
     }
 }
 
 __device__ __forceinline__ bool inside_quad(const Camera& cam, float x, float y) {
     int nr = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) nr += ((cam.ea[i] * x + cam.eb[i] * y) + cam.ec[i]) >= 0.0f;
+    for (int i = 0; i < 4; i++) nr += ((cam.edges[i] * x + cam.edges[4 + i] * y) + cam.edges[8 + i]) >= 0.0f;
     return nr == 4 || nr == 0;
 }
 
@@ -246,8 +250,9 @@ struct RasterArgs {
     float scale;
 };
 
-constexpr int kQueue = 256;          // items per group queue (3 KB)
+constexpr int kQueue = 128;          // items per group queue (1.5 KB)
 constexpr int kRows = tds::kMaxRasterRows;
+constexpr int kGroupExtra = kRows * 8 + 16 + 48;   // row tables, counters, view-quad edge functions
 
 // G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras per CTA, no block barriers)
 // for tiles up to 64x64, or the whole CTA for larger tiles.
@@ -257,8 +262,11 @@ __device__ __forceinline__ void group_sync() {
     else __syncthreads();
 }
 
+#ifndef TDS_RASTER_MINB
+#define TDS_RASTER_MINB 8
+#endif
 template <int G>
-__global__ void __launch_bounds__(G == 32 ? 128 : G) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
+__global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB : 1) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int GROUPS = G == 32 ? 4 : 1;
     const int res = a.res;
@@ -269,13 +277,14 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G) raster_kernel(MapSetDev map
 
     // per-group shared memory: tile | queue | row tables
     const int tile_bytes = res * res;
-    const int group_bytes = tile_bytes + kQueue * 12 + kRows * 8 + 16;
+    const int group_bytes = tile_bytes + kQueue * 12 + kGroupExtra;
     uint8_t* base = smem_raw + (size_t)group * group_bytes;
     uint8_t* img = base;
     uint32_t* queue = reinterpret_cast<uint32_t*>(base + tile_bytes);      // [3][kQueue]
     int* s_start = reinterpret_cast<int*>(base + tile_bytes + kQueue * 12);
     int* s_pref = s_start + kRows;                                         // exclusive prefix of the row counts
     int* s_cnt = s_pref + kRows;                                           // [0],[1] queue counts (ping-pong), [2] total
+    float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
     __shared__ float s_lut[(TDS_MAX_CLASSES + 1) * 3];
     for (int i = threadIdx.x; i < (TDS_MAX_CLASSES + 1) * 3; i += blockDim.x) s_lut[i] = pal.rgb[i / 3][i % 3];
     __syncthreads();
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G) raster_kernel(MapSetDev map
     float qx[4], qy[4];
     const float2 cxy = reinterpret_cast<const float2*>(a.cam_xy)[camid];
     const float2 csc = reinterpret_cast<const float2*>(a.cam_sc)[camid];
-    make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy);
+    make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy, s_edges, tid == 0);
 
     {   // clear the tile
         uint32_t* w = reinterpret_cast<uint32_t*>(img);
@@ -533,7 +542,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     const int64_t ncam = (int64_t)B * Nc;
     TDS_REQUIRE(ncam <= 2147483647LL, "raster: too many cameras");
     a.ncam = (int32_t)ncam;
-    const size_t group_bytes = (size_t)res * res + kQueue * 12 + kRows * 8 + 16;
+    const size_t group_bytes = (size_t)res * res + kQueue * 12 + kGroupExtra;
     auto launch = [&](auto kernel, int groups, int threads) -> int {
         const size_t smem = group_bytes * groups;
         if (smem > 40 * 1024) TDS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

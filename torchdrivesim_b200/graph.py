@@ -1,0 +1,84 @@
+"""CUDA-graph replay of the whole hot path.
+
+`GraphedHotPath` records ONE step of a `Simulator` (kinematic step -> egocentric birdviews -> collisions ->
+offroad) into a CUDA graph over static buffers and replays it with new actions.  The step consists of ~5 of
+our kernels plus a dozen tiny torch kernels; replaying a graph removes the eager-mode launch gaps between
+them (the reference has no equivalent: it is eager PyTorch + a Python loop per triangle).
+
+Inference-only (no autograd tape is recorded); use the eager `Simulator` methods for differentiable rollouts.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .rendering import Resolution
+from .simulator import Simulator
+
+
+class GraphedHotPath:
+    def __init__(self, sim: Simulator, res: Optional[Resolution] = None, fov: Optional[float] = None,
+                 render: bool = True, warmup: int = 2):
+        self.sim = sim
+        state = sim.get_state()
+        if not state.is_cuda:
+            raise _lib.TdsError("GraphedHotPath needs a Simulator on a CUDA device")
+        dev = state.device
+        B, A = state.shape[0], state.shape[1]
+        res = sim.renderer.res if res is None else res
+        self.action = torch.zeros(B, A, sim.action_size, dtype=torch.float32, device=dev)
+        self.state = state.detach().clone()
+        self.images = torch.empty(B, A, 3, res.height, res.width, dtype=torch.float32, device=dev) if render else None
+        self.collision = torch.empty(B, A, dtype=torch.float32, device=dev)
+        self.offroad = torch.empty(B, A, dtype=torch.float32, device=dev)
+        self._res, self._fov, self._render = res, fov, render
+        # traffic-control states change between steps: the graph reads them from static buffers
+        self._control_state = {}
+        for name, control in (sim.traffic_controls or {}).items():
+            buf = control.state.detach().clone()
+            control.set_state(buf)
+            self._control_state[name] = buf
+        sim.kinematic_model.set_state(self.state)
+        # warm up on a side stream (allocator, lazily built map handles), then capture
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        saved = self.state.clone()
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(max(warmup, 1)):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.state.copy_(saved)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self._body()
+        self.state.copy_(saved)
+
+    def _body(self) -> None:
+        sim = self.sim
+        sim.kinematic_model.set_state(self.state)
+        sim.kinematic_model.step(self.action)        # Simulator.step minus the host-side control stepping
+        self.state.copy_(sim.get_state())           # the graph chains steps through this static buffer
+        sim.kinematic_model.set_state(self.state)
+        if self._render:
+            sim.render_egocentric(res=self._res, fov=self._fov, out=self.images)
+        self.collision.copy_(sim.compute_collision())
+        self.offroad.copy_(sim.compute_offroad())
+
+    def run(self, action: Tensor) -> Tuple[Optional[Tensor], Tensor, Tensor]:
+        """One step with `action` [B,A,Ac] (device or pinned host tensor).  Returns the static output
+        buffers (images, collision, offroad); they are overwritten by the next call."""
+        self.action.copy_(action, non_blocking=True)
+        self.sim.internal_time += 1
+        for name, control in (self.sim.traffic_controls or {}).items():
+            control.step(self.sim.internal_time)     # host-side rule (replay tensor or compute_state) ...
+            buf = self._control_state[name]
+            if control.state is not buf:
+                buf.copy_(control.state)             # ... lands in the buffer the graph reads
+                control.set_state(buf)
+        self.graph.replay()
+        return self.images, self.collision, self.offroad
+
+    def set_state(self, state: Tensor) -> None:
+        self.state.copy_(state)

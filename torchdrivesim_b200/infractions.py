@@ -25,7 +25,7 @@ def collision_detection_with_discs(box1: Tensor, box2: Tensor, num_discs: int = 
 
 
 def iou_differentiable(box1: Tensor, box2: Tensor, fast: bool = True) -> Tensor:
-    """Rotated-box IoU between corresponding boxes, BxAx5 -> BxA.  Forward only for now."""
+    """Rotated-box IoU between corresponding boxes, BxAx5 -> BxA (differentiable)."""
     if not fast:
         raise _lib.TdsError("only the `fast` IoU of the reference is implemented")
     return ops.collision_pairwise(box1, box2, _lib.METRIC_IOU)

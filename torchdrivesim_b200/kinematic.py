@@ -214,22 +214,70 @@ class KinematicUnicycle(KinematicModel):
         return self.normalize_action(torch.stack([(fv - cv) / dt, om], dim=-1))
 
 
+class SimpleKinematicModel(KinematicModel):
+    """The action is the time derivative of the state in units of (max_dx, max_dx, max_dpsi, max_dv)
+    (kinematic.py:328-376)."""
+    action_size: int = 4
+    _model_id = _lib.MODEL_SIMPLE
+
+    def __init__(self, max_dx=20, max_dpsi=10 * math.pi, max_dv=5, dt=0.1):
+        super().__init__(dt=dt)
+        self.max_dx, self.max_dpsi, self.max_dv = max_dx, max_dpsi, max_dv
+        self._normalization_factor = torch.tensor([max_dx, max_dx, max_dpsi, max_dv])
+
+    def copy(self, other=None):
+        if other is None:
+            other = self.__class__(max_dx=self.max_dx, max_dpsi=self.max_dpsi, max_dv=self.max_dv, dt=self.dt)
+        return super().copy(other)
+
+    def normalize_action(self, action):
+        return action / self._normalization_factor.to(action.device)
+
+    def denormalize_action(self, action):
+        return action * self._normalization_factor.to(action.device)
+
+    def step(self, action, dt=None):
+        assert action.shape[-1] == self.action_size
+        p = ops.kinematic_params(self.dt if dt is None else dt, max_dx=self.max_dx, max_dpsi=self.max_dpsi,
+                                 max_dv=self.max_dv)
+        self.set_state(ops.kinematic_step(self.get_state(), action, None, None, self._model_id, p))
+
+    def fit_action(self, future_state, current_state=None, dt=None):
+        dt = self.dt if dt is None else dt
+        current_state = self.get_state() if current_state is None else current_state
+        return self.normalize_action((future_state - current_state) / dt)
+
+
+class OrientedKinematicModel(SimpleKinematicModel):
+    """Like SimpleKinematicModel with the xy action expressed in the agent frame (kinematic.py:379-397)."""
+    _model_id = _lib.MODEL_ORIENTED
+
+    def fit_action(self, future_state, current_state=None, dt=None):
+        act = super().fit_action(future_state, current_state=current_state, dt=dt)
+        psi = (self.get_state() if current_state is None else current_state)[..., 2:3]
+        c, s = torch.cos(-psi), torch.sin(-psi)
+        xy = torch.cat([c * act[..., 0:1] - s * act[..., 1:2], s * act[..., 0:1] + c * act[..., 1:2]], dim=-1)
+        return torch.cat([xy, act[..., 2:]], dim=-1)
+
+
 class FusedCompoundKinematicModel(KinematicBicycle):
     """Heterogeneous agents in one launch: `model_assignments` [B,A] holds a model id per agent
-    (0 bicycle, 1 no-reversing bicycle, 2 unicycle).  Replaces CompoundKinematicModel
-    (kinematic.py:160-314), whose step splits the batch with boolean masks (a host sync per step)."""
+    (0 bicycle, 1 no-reversing bicycle, 2 unicycle, 3 simple, 4 oriented).  Replaces CompoundKinematicModel
+    (kinematic.py:160-314), whose step splits the batch with boolean masks (a host sync per step).  As there,
+    the action is padded to the largest action size (`action_size=4` when simple/oriented agents are present)."""
 
     def __init__(self, model_assignments: Tensor, max_acceleration=5, max_steering=math.pi / 2,
-                 max_yaw_rate=math.pi / 2, dt=0.1, left_handed=False):
+                 max_yaw_rate=math.pi / 2, dt=0.1, left_handed=False, action_size: int = 2):
         super().__init__(max_acceleration=max_acceleration, max_steering=max_steering, dt=dt, left_handed=left_handed)
         self.max_yaw_rate = max_yaw_rate
         self.model_assignments = model_assignments
+        self.action_size = action_size
 
     def copy(self, other=None):
         if other is None:
             other = self.__class__(self.model_assignments, max_acceleration=self.max_acceleration,
                                    max_steering=self.max_steering, max_yaw_rate=self.max_yaw_rate, dt=self.dt,
-                                   left_handed=self.left_handed)
+                                   left_handed=self.left_handed, action_size=self.action_size)
         return super().copy(other)
 
     def to(self, device):
@@ -247,7 +295,7 @@ class FusedCompoundKinematicModel(KinematicBicycle):
         super().select_batch_elements(idx)
 
     def step(self, action, dt=None):
-        assert action.shape[-1] == 2
+        assert action.shape[-1] == self.action_size
         p = ops.kinematic_params(self.dt if dt is None else dt, self.max_acceleration, self.max_steering,
                                  self.max_yaw_rate, self.left_handed)
         self.set_state(ops.kinematic_step(self.get_state(), action, self.lr, self.model_assignments, 0, p))

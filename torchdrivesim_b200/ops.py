@@ -16,8 +16,10 @@ _F32_HALF_PI = 1.5707963705062866  # float32(pi / 2), the reference's _normaliza
 
 
 def kinematic_params(dt: float = 0.1, max_acceleration: float = 5.0, max_steering: float = math.pi / 2,
-                     max_yaw_rate: float = math.pi / 2, left_handed: bool = False) -> "_lib.KinematicParams":
-    return _lib.KinematicParams(dt, max_acceleration, max_steering, max_yaw_rate, 1 if left_handed else 0)
+                     max_yaw_rate: float = math.pi / 2, left_handed: bool = False, max_dx: float = 20.0,
+                     max_dpsi: float = 10 * math.pi, max_dv: float = 5.0) -> "_lib.KinematicParams":
+    return _lib.KinematicParams(dt, max_acceleration, max_steering, max_yaw_rate, 1 if left_handed else 0,
+                                max_dx, max_dpsi, max_dv)
 
 
 # ------------------------------------------------------------------------------------ kinematics
@@ -27,14 +29,17 @@ class _KinematicStep(torch.autograd.Function):
         lib = _lib.load()
         shape = state.shape
         s = _lib.as_f32(state).reshape(-1, 4)
-        a = _lib.as_f32(action).reshape(-1, 2)
+        adim = action.shape[-1]
+        if adim not in (2, 4):
+            raise _lib.TdsError("kinematic_step: the action must have 2 or 4 values per agent")
+        a = _lib.as_f32(action).reshape(-1, adim)
         l = None if lr is None else _lib.as_f32(lr).reshape(-1)
         m = None if model is None else _lib.as_i32(model).reshape(-1)
         n = s.shape[0]
         if a.shape[0] != n or (l is not None and l.shape[0] != n) or (m is not None and m.shape[0] != n):
             raise _lib.TdsError("kinematic_step: state, action, lr and model must agree on the batch shape")
         out = torch.empty_like(s)
-        _lib.check(lib.tds_kinematic_step_fwd(_lib.ptr(s), _lib.ptr(a), _lib.ptr(l), _lib.ptr(m), uniform_model, n,
+        _lib.check(lib.tds_kinematic_step_fwd(_lib.ptr(s), _lib.ptr(a), adim, _lib.ptr(l), _lib.ptr(m), uniform_model, n,
                                               ctypes.byref(params), _lib.ptr(out), _lib.stream_ptr(s.device)))
         ctx.save_for_backward(s, a, l, m)
         ctx.meta = (uniform_model, params, shape, action.shape, None if lr is None else lr.shape)
@@ -50,7 +55,7 @@ class _KinematicStep(torch.autograd.Function):
         gs = torch.empty_like(s)
         ga = torch.empty_like(a)
         gl = None if l is None else torch.empty_like(l)
-        _lib.check(lib.tds_kinematic_step_bwd(_lib.ptr(s), _lib.ptr(a), _lib.ptr(l), _lib.ptr(m), uniform_model, n,
+        _lib.check(lib.tds_kinematic_step_bwd(_lib.ptr(s), _lib.ptr(a), a.shape[-1], _lib.ptr(l), _lib.ptr(m), uniform_model, n,
                                               ctypes.byref(params), _lib.ptr(g), _lib.ptr(gs), _lib.ptr(ga), _lib.ptr(gl),
                                               _lib.stream_ptr(s.device)))
         return gs.reshape(sshape), ga.reshape(ashape), (None if gl is None else gl.reshape(lshape)), None, None, None
@@ -59,22 +64,22 @@ class _KinematicStep(torch.autograd.Function):
 def kinematic_step(state: torch.Tensor, action: torch.Tensor, lr: Optional[torch.Tensor],
                    model: Optional[torch.Tensor] = None, uniform_model: int = _lib.MODEL_BICYCLE,
                    params: Optional["_lib.KinematicParams"] = None) -> torch.Tensor:
-    """state [...,4], action [...,2], lr [...], model [...] int (or None: `uniform_model`) -> new state."""
+    """state [...,4], action [...,2|4], lr [...], model [...] int (or None: `uniform_model`) -> new state."""
     return _KinematicStep.apply(state, action, lr, model, uniform_model, params or kinematic_params())
 
 
 # ------------------------------------------------------------------------------------ collisions
-class _DiscsPairwise(torch.autograd.Function):
+class _Pairwise(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, box1, box2):
+    def forward(ctx, box1, box2, metric):
         lib = _lib.load()
         b1 = _lib.as_f32(box1).reshape(-1, 5)
         b2 = _lib.as_f32(box2).reshape(-1, 5)
         out = torch.empty(b1.shape[0], dtype=torch.float32, device=b1.device)
-        _lib.check(lib.tds_collision_pairwise_fwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], _lib.METRIC_DISCS,
+        _lib.check(lib.tds_collision_pairwise_fwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], metric,
                                                   _lib.ptr(out), _lib.stream_ptr(b1.device)))
         ctx.save_for_backward(b1, b2)
-        ctx.shapes = (box1.shape, box2.shape)
+        ctx.meta = (box1.shape, box2.shape, metric)
         return out.reshape(box1.shape[:-1])
 
     @staticmethod
@@ -83,29 +88,21 @@ class _DiscsPairwise(torch.autograd.Function):
         b1, b2 = ctx.saved_tensors
         g = _lib.as_f32(grad_out).reshape(-1)
         g1, g2 = torch.empty_like(b1), torch.empty_like(b2)
-        _lib.check(lib.tds_collision_discs_pairwise_bwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], _lib.ptr(g),
-                                                        _lib.ptr(g1), _lib.ptr(g2), _lib.stream_ptr(b1.device)))
-        return g1.reshape(ctx.shapes[0]), g2.reshape(ctx.shapes[1])
+        _lib.check(lib.tds_collision_pairwise_bwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], ctx.meta[2], _lib.ptr(g),
+                                                  _lib.ptr(g1), _lib.ptr(g2), _lib.stream_ptr(b1.device)))
+        return g1.reshape(ctx.meta[0]), g2.reshape(ctx.meta[1]), None
 
 
 def collision_pairwise(box1: torch.Tensor, box2: torch.Tensor, metric: int = _lib.METRIC_DISCS) -> torch.Tensor:
-    """Element-wise overlap of box1[...,5] and box2[...,5] (same shape) -> [...]."""
+    """Element-wise overlap of box1[...,5] and box2[...,5] (same shape) -> [...], differentiable."""
     if box1.shape != box2.shape or box1.shape[-1] != 5:
         raise _lib.TdsError("collision_pairwise: boxes must have identical shape [...,5]")
-    if metric == _lib.METRIC_DISCS:
-        return _DiscsPairwise.apply(box1, box2)
-    lib = _lib.load()
-    b1 = _lib.as_f32(box1).reshape(-1, 5)
-    b2 = _lib.as_f32(box2).reshape(-1, 5)
-    out = torch.empty(b1.shape[0], dtype=torch.float32, device=b1.device)
-    _lib.check(lib.tds_collision_pairwise_fwd(_lib.ptr(b1), _lib.ptr(b2), b1.shape[0], metric, _lib.ptr(out),
-                                              _lib.stream_ptr(b1.device)))
-    return out.reshape(box1.shape[:-1])
+    return _Pairwise.apply(box1, box2, metric)
 
 
-class _DiscsAllPairs(torch.autograd.Function):
+class _AllPairs(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ego_box, all_box, mask, ego_is_prefix):
+    def forward(ctx, ego_box, all_box, mask, metric, ego_is_prefix):
         lib = _lib.load()
         e = _lib.as_f32(ego_box)
         a = _lib.as_f32(all_box)
@@ -113,10 +110,11 @@ class _DiscsAllPairs(torch.autograd.Function):
         B, A, N = e.shape[0], e.shape[1], a.shape[1]
         out = torch.zeros(B, A, dtype=torch.float32, device=e.device)
         arg = torch.zeros(B, A, dtype=torch.int32, device=e.device)
-        _lib.check(lib.tds_collision_allpairs_fwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, _lib.METRIC_DISCS,
+        _lib.check(lib.tds_collision_allpairs_fwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, metric,
                                                   1 if ego_is_prefix else 0, _lib.ptr(out), _lib.ptr(arg),
                                                   _lib.stream_ptr(e.device)))
         ctx.save_for_backward(e, a, m, arg)
+        ctx.meta = (metric, 1 if ego_is_prefix else 0)
         return out
 
     @staticmethod
@@ -127,28 +125,22 @@ class _DiscsAllPairs(torch.autograd.Function):
         g = _lib.as_f32(grad_out)
         ge = torch.zeros_like(e)
         ga = torch.zeros_like(a)
-        _lib.check(lib.tds_collision_discs_allpairs_bwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, _lib.ptr(g),
-                                                        _lib.ptr(arg), _lib.ptr(ge), _lib.ptr(ga),
-                                                        _lib.stream_ptr(e.device)))
-        return ge, ga, None, None
+        _lib.check(lib.tds_collision_allpairs_bwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, ctx.meta[0], ctx.meta[1],
+                                                  _lib.ptr(g), _lib.ptr(arg), _lib.ptr(ge), _lib.ptr(ga),
+                                                  _lib.stream_ptr(e.device)))
+        return ge, ga, None, None, None
 
 
 def collision_allpairs(ego_box: torch.Tensor, all_box: torch.Tensor, mask: torch.Tensor,
                        metric: int = _lib.METRIC_DISCS, ego_is_prefix: bool = True) -> torch.Tensor:
-    """Fused Simulator.compute_collision: ego_box [B,A,5], all_box [B,N,5], mask [B,N] -> [B,A]."""
+    """Fused Simulator.compute_collision: ego_box [B,A,5], all_box [B,N,5], mask [B,N] -> [B,A], differentiable."""
     if ego_box.dim() != 3 or all_box.dim() != 3 or ego_box.shape[-1] != 5 or all_box.shape[-1] != 5:
         raise _lib.TdsError("collision_allpairs: expected ego_box [B,A,5] and all_box [B,N,5]")
     if ego_box.shape[0] != all_box.shape[0] or tuple(mask.shape) != tuple(all_box.shape[:2]):
         raise _lib.TdsError("collision_allpairs: batch / mask shape mismatch")
-    if metric == _lib.METRIC_DISCS:
-        return _DiscsAllPairs.apply(ego_box, all_box, mask, ego_is_prefix)
-    lib = _lib.load()
-    e, a, m = _lib.as_f32(ego_box), _lib.as_f32(all_box), _lib.as_u8(mask)
-    B, A, N = e.shape[0], e.shape[1], a.shape[1]
-    out = torch.zeros(B, A, dtype=torch.float32, device=e.device)
-    _lib.check(lib.tds_collision_allpairs_fwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, metric,
-                                              1 if ego_is_prefix else 0, _lib.ptr(out), None, _lib.stream_ptr(e.device)))
-    return out
+    if metric not in (_lib.METRIC_DISCS, _lib.METRIC_IOU):
+        raise _lib.TdsError(f"collision_allpairs: unknown metric {metric}")
+    return _AllPairs.apply(ego_box, all_box, mask, metric, ego_is_prefix)
 
 
 # ------------------------------------------------------------------------------------ offroad
