@@ -16,3 +16,11 @@ extern "C" void tds_host_draw_triangle_fast(uint8_t* img, int W, int H, const in
         [&](int idx) { img[idx] = 1; },
         [&](int idx, int n, int step) { for (int i = 0; i < n; i++) img[idx + i * step] = 1; });
 }
+
+// thin path: returns 0 when the triangle does not qualify (not drawn), 1 when drawn
+extern "C" int tds_host_draw_triangle_thin(uint8_t* img, int W, int H, const int32_t* p) {
+    if (!tds::is_thin_inside(W, H, p[0], p[1], p[2], p[3], p[4], p[5])) return 0;
+    tds::draw_triangle_thin(1, W, p[0], p[1], p[2], p[3], p[4], p[5],
+        [&](int idx, int n, int step) { for (int i = 0; i < n; i++) img[idx + i * step] = 1; });
+    return 1;
+}

@@ -169,8 +169,6 @@ struct Item {
     uint32_t a, b, c;       // (x0,y0), (x1,y1), (x2,y2) as int16 pairs
 };
 
-__device__ __noinline__ bool inside_quad_exact(const Camera& cam, float x, float y) { return inside_quad(cam, x, y); }
-
 __device__ __forceinline__ int classify(float u, float v, float lo, float hi, float m) {
     // 1 inside, 0 outside, -1 undecided
     const bool in = (u > lo + m) & (u < hi - m) & (v > lo + m) & (v < hi - m);
@@ -187,7 +185,8 @@ __device__ __forceinline__ void project_f(const Camera& cam, float x, float y, f
     u0 = u0 + cam.half;     u1 = u1 + cam.half;
 }
 
-// returns 0: culled, 1: item valid (|coords| < 8192), 2: kept but needs the 64-bit slow path (ints in xy[])
+// returns 0: culled / invisible, 1: thin item, 3: general item (|coords| < 8192), 2: kept but needs the 64-bit
+// slow path (ints in xy[])
 __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float y0, float x1, float y1, float x2,
                                               float y2, int own, Item& it, int xy[6]) {
     const float px0 = x0 + cam.ncx, py0 = y0 + cam.ncy;
@@ -202,9 +201,15 @@ __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float
     const float band = 0.01f + 0.002f * (cam.scale * cam.half);
     int c0 = classify(u0, v0, lo, hi, band), c1 = classify(u1, v1, lo, hi, band), c2 = classify(u2, v2, lo, hi, band);
     if ((c0 | c1 | c2) < 0) {       // some vertex is within the band around the quad boundary (or NaN): exact test
-        if (c0 < 0) c0 = inside_quad_exact(cam, px0, py0);
-        if (c1 < 0) c1 = inside_quad_exact(cam, px1, py1);
-        if (c2 < 0) c2 = inside_quad_exact(cam, px2, py2);
+        // one rolled loop over the three vertices keeps this rare path small; the edge functions live in smem
+        float ex = px0, ey = py0;
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+            const int r = inside_quad(cam, ex, ey) ? 1 : 0;
+            if (k == 0) { if (c0 < 0) c0 = r; ex = px1; ey = py1; }
+            else if (k == 1) { if (c1 < 0) c1 = r; ex = px2; ey = py2; }
+            else { if (c2 < 0) c2 = r; }
+        }
     }
     if (!(c0 | c1 | c2)) return 0;
     const int first = c0 ? 0 : (c1 ? 1 : 2);
@@ -216,10 +221,17 @@ __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float
 #pragma unroll
     for (int k = 0; k < 6; k++) big |= (xy[k] <= -8192) | (xy[k] >= 8192);
     if (big) return 2;
+    // integer bounding box entirely off the image: clipLine rejects all three edges and the fill returns early
+    const int res = cam.res;
+    const int xmin = min(min(xy[0], xy[2]), xy[4]), xmax = max(max(xy[0], xy[2]), xy[4]);
+    const int ymin = min(min(xy[1], xy[3]), xy[5]), ymax = max(max(xy[1], xy[3]), xy[5]);
+    if (xmax < 0 || ymax < 0 || xmin >= res || ymin >= res) return 0;
     it.a = (uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16);
     it.b = (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16);
     it.c = (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16);
-    return 1;
+    // thin = at most two rows and fully inside the image: closed-form runs (tds_raster_tri.h)
+    const bool thin = (ymax - ymin <= 1) & (xmin >= 0) & (ymin >= 0) & (xmax < res) & (ymax < res);
+    return thin ? 1 : 3;
 }
 
 // ---- stage 2: scan-convert.  The tile is x-major (img[x * res + y]) which IS the transpose of cv2.py:61
@@ -229,6 +241,21 @@ __device__ __forceinline__ void draw_item(uint8_t* img, int res, uint8_t val, co
     const int x2 = (int16_t)(it.c & 0xffff), y2 = (int32_t)it.c >> 16;
     tds::draw_triangle_fast(res, res, res, 1, x0, y0, x1, y1, x2, y2,
         [&](int idx) { img[idx] = val; },
+        [&](int idx, int n, int step) { for (; n > 0; n--, idx += step) img[idx] = val; });
+}
+
+__device__ __forceinline__ void draw_item_thin(uint8_t* img, int res, uint8_t val, const Item& it) {
+    const int x0 = (int16_t)(it.a & 0xffff), y0 = (int32_t)it.a >> 16;
+    const int x1 = (int16_t)(it.b & 0xffff), y1 = (int32_t)it.b >> 16;
+    const int x2 = (int16_t)(it.c & 0xffff), y2 = (int32_t)it.c >> 16;
+    const int xmin = min(min(x0, x1), x2), xmax = max(max(x0, x1), x2);
+    if (xmax - xmin <= 1) {      // within 2x2 pixels: the outline is the three vertices
+        img[x0 * res + y0] = val;
+        img[x1 * res + y1] = val;
+        img[x2 * res + y2] = val;
+        return;
+    }
+    tds::draw_triangle_thin(res, 1, x0, y0, x1, y1, x2, y2,
         [&](int idx, int n, int step) { for (; n > 0; n--, idx += step) img[idx] = val; });
 }
 
@@ -250,9 +277,14 @@ struct RasterArgs {
     float scale;
 };
 
-constexpr int kQueue = 128;          // items per group queue (1.5 KB)
+// per-group item queue: thin items grow from the front, general items from the back; a chunk of kChunk candidates
+// can never overflow it.  12 B per item.
+template <int G>
+struct QCfg {
+    static constexpr int total = G == 32 ? 128 : 2 * G;      // = candidates per chunk
+};
 constexpr int kRows = tds::kMaxRasterRows;
-constexpr int kGroupExtra = kRows * 8 + 16 + 48;   // row tables, counters, view-quad edge functions
+constexpr int kGroupExtra = kRows * 8 + 32 + 48;   // row tables, counters, view-quad edge functions
 
 // G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras per CTA, no block barriers)
 // for tiles up to 64x64, or the whole CTA for larger tiles.
@@ -263,13 +295,13 @@ __device__ __forceinline__ void group_sync() {
 }
 
 #ifndef TDS_RASTER_MINB
-#define TDS_RASTER_MINB 8
+#define TDS_RASTER_MINB 6
 #endif
-template <int G>
+template <int G, int RES>
 __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB : 1) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int GROUPS = G == 32 ? 4 : 1;
-    const int res = a.res;
+    const int res = RES ? RES : a.res;          // RES = 64 is compiled with constant strides
     const int group = G == 32 ? (threadIdx.x >> 5) : 0;
     const int tid = G == 32 ? (threadIdx.x & 31) : threadIdx.x;
     const int camid = blockIdx.x * GROUPS + group;
@@ -277,14 +309,15 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
 
     // per-group shared memory: tile | queue | row tables
     const int tile_bytes = res * res;
+    constexpr int kQueue = QCfg<G>::total;
     const int group_bytes = tile_bytes + kQueue * 12 + kGroupExtra;
     uint8_t* base = smem_raw + (size_t)group * group_bytes;
     uint8_t* img = base;
     uint32_t* queue = reinterpret_cast<uint32_t*>(base + tile_bytes);      // [3][kQueue]
     int* s_start = reinterpret_cast<int*>(base + tile_bytes + kQueue * 12);
     int* s_pref = s_start + kRows;                                         // exclusive prefix of the row counts
-    int* s_cnt = s_pref + kRows;                                           // [0],[1] queue counts (ping-pong), [2] total
-    float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
+    int* s_cnt = s_pref + kRows;                   // [0] thin count, [1] general count, [4] total
+    float* s_edges = reinterpret_cast<float*>(s_cnt + 6);                   // [12]
     __shared__ float s_lut[(TDS_MAX_CLASSES + 1) * 3];
     for (int i = threadIdx.x; i < (TDS_MAX_CLASSES + 1) * 3; i += blockDim.x) s_lut[i] = pal.rgb[i / 3][i % 3];
     __syncthreads();
@@ -301,7 +334,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     {   // clear the tile
         uint32_t* w = reinterpret_cast<uint32_t*>(img);
         for (int i = tid; i < tile_bytes / 4; i += G) w[i] = 0u;
-        if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+        if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; }
     }
     // ---- grid rows touched by the view quad (world coordinates), with a 5 cm safety margin
     const float margin = 0.05f;
@@ -353,7 +386,6 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
 
     // ---- painter's passes, first drawn = highest z.  Each pass: stage 1 culls + projects candidates and
     // appends the kept ones to the queue (warp-aggregated), stage 2 scan-converts the queue.
-    int parity = 0;
     for (int ph = 0; ph < pal.n_classes; ph++) {
         const int c = pal.order[ph];
         const uint8_t val = (uint8_t)(c + 1);
@@ -375,14 +407,17 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
             if (tid == 0) {
                 int acc = 0;
                 for (int r = 0; r < nrows; r++) { const int n = s_pref[r]; s_pref[r] = acc; acc += n; }
-                s_cnt[2] = acc;
+                s_cnt[4] = acc;
             }
             group_sync<G>();
-            total_static = s_cnt[2];
+            total_static = s_cnt[4];
         }
         const int ndyn = ((pal.dyn_mask >> c) & 1u) ? T : 0;
         const int total = total_static + ndyn;
         int row = 0;                                   // candidates are visited in increasing order
+        // chunks of kQueue candidates: stage 1 (cull + project + classify) appends to the two-ended queue, stage 2
+        // scan-converts it.  There is exactly ONE copy of each scan-conversion routine in the kernel: the
+        // instruction-cache footprint matters more than anything else here.
         for (int c0 = 0; c0 < total; c0 += kQueue) {
             const int cend = min(c0 + kQueue, total);
             for (int i = c0 + tid; i < cend; i += G) {
@@ -416,34 +451,48 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 int xy[6];
                 const int kind = valid ? setup_triangle(cam, x0, y0, x1, y1, x2, y2, own, it, xy) : 0;
                 if (kind == 2) draw_item_slow(img, res, val, xy);     // huge triangle: rare, drawn in place
+                // thin items grow from the front of the queue, general items from the back (warp-aggregated)
                 const unsigned full = __activemask();
-                const unsigned m = __ballot_sync(full, kind == 1);
-                if (m != 0) {
-                    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                    int basepos = 0;
-                    if (lane == leader) basepos = atomicAdd(&s_cnt[parity], __popc(m));
-                    basepos = __shfl_sync(full, basepos, leader);
-                    if (kind == 1) {
-                        const int pos = basepos + __popc(m & ((1u << lane) - 1));
-                        queue[pos] = it.a; queue[kQueue + pos] = it.b; queue[2 * kQueue + pos] = it.c;
+                const int lane = threadIdx.x & 31, leader = __ffs(full) - 1;
+                const unsigned mt = __ballot_sync(full, kind == 1), mg = __ballot_sync(full, kind == 3);
+                if (mt | mg) {
+                    int base_t = 0, base_g = 0;
+                    if (lane == leader) {
+                        if (mt) base_t = atomicAdd(&s_cnt[0], __popc(mt));
+                        if (mg) base_g = atomicAdd(&s_cnt[1], __popc(mg));
                     }
+                    base_t = __shfl_sync(full, base_t, leader);
+                    base_g = __shfl_sync(full, base_g, leader);
+                    const unsigned below = (1u << lane) - 1;
+                    int pos = -1;
+                    if (kind == 1) pos = base_t + __popc(mt & below);
+                    else if (kind == 3) pos = kQueue - 1 - (base_g + __popc(mg & below));
+                    if (pos >= 0) { queue[pos] = it.a; queue[kQueue + pos] = it.b; queue[2 * kQueue + pos] = it.c; }
                 }
             }
             group_sync<G>();
-            const int n = s_cnt[parity];
-            if (tid == 0) s_cnt[parity ^ 1] = 0;
-            for (int i = tid; i < n; i += G) {
-                Item it;
-                it.a = queue[i]; it.b = queue[kQueue + i]; it.c = queue[2 * kQueue + i];
-                draw_item(img, res, val, it);
+            const int n_thin = s_cnt[0], n_gen = s_cnt[1];
+            for (int k = tid; k < n_thin; k += G) {
+                Item q;
+                q.a = queue[k]; q.b = queue[kQueue + k]; q.c = queue[2 * kQueue + k];
+                draw_item_thin(img, res, val, q);
+            }
+            for (int k = kQueue - 1 - tid; k >= kQueue - n_gen; k -= G) {
+                Item q;
+                q.a = queue[k]; q.b = queue[kQueue + k]; q.c = queue[2 * kQueue + k];
+                draw_item(img, res, val, q);
             }
             group_sync<G>();
-            parity ^= 1;
+            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+            group_sync<G>();
         }
     }
     group_sync<G>();
 
     // ---- expand the tile through the colour LUT: out[cam][ch][x][y], 4 pixels per 128-bit store
+#ifdef TDS_EXP_NOOUT
+    if (img[tid] != 77) return;
+#endif
     const int nquad = tile_bytes / 4;
     float* outc = a.out + (int64_t)camid * 3 * tile_bytes;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(img);
@@ -542,9 +591,10 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     const int64_t ncam = (int64_t)B * Nc;
     TDS_REQUIRE(ncam <= 2147483647LL, "raster: too many cameras");
     a.ncam = (int32_t)ncam;
-    const size_t group_bytes = (size_t)res * res + kQueue * 12 + kGroupExtra;
-    auto launch = [&](auto kernel, int groups, int threads) -> int {
+    auto launch = [&](auto kernel, int groups, int threads, int queue_items) -> int {
+        const size_t group_bytes = (size_t)res * res + (size_t)queue_items * 12 + kGroupExtra;
         const size_t smem = group_bytes * groups;
+        TDS_REQUIRE(smem <= 227 * 1024, "raster: res=%d needs %zu bytes of shared memory", res, smem);
         if (smem > 40 * 1024) TDS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)((ncam + groups - 1) / groups);
         if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
@@ -553,7 +603,8 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
         TDS_LAUNCH_OK();
         return TDS_OK;
     };
-    if (res <= 64) return launch(raster_kernel<32>, 4, 128);
-    if (res <= 128) return launch(raster_kernel<256>, 1, 256);
-    return launch(raster_kernel<512>, 1, 512);
+    if (res == 64) return launch(raster_kernel<32, 64>, 4, 128, QCfg<32>::total);
+    if (res < 64) return launch(raster_kernel<32, 0>, 4, 128, QCfg<32>::total);
+    if (res <= 128) return launch(raster_kernel<256, 0>, 1, 256, QCfg<256>::total);
+    return launch(raster_kernel<512, 0>, 1, 512, QCfg<512>::total);
 }

@@ -227,4 +227,52 @@ TDS_HD void draw_triangle_fast(int W, int H, int sx, int sy, int x0, int y0, int
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Thin triangles: all three vertices INSIDE the image and spanning at most two adjacent rows.  Then no edge
+// is clipped, the fill adds nothing to the outline (see draw_triangle_fast; this does NOT hold for two
+// adjacent columns, where the fixed-point spans can leave the Bresenham outline), and every edge is at most
+// two axis-aligned runs, because an 8-connected LineIterator segment that moves by one along its minor axis
+// takes that step after  i0 = (d + 2) >> 1  pixels (d = extent along the major axis,
+// k_i = floor((2 i + d - 1) / (2 d)) flips at i0), always starting from the LEFT endpoint.
+// run(index_of_first, count, step) writes `count` pixels starting at a linear index with the given stride.
+TDS_HD bool is_thin_inside(int W, int H, int x0, int y0, int x1, int y1, int x2, int y2) {
+    const bool inside = ((unsigned)x0 < (unsigned)W) & ((unsigned)x1 < (unsigned)W) & ((unsigned)x2 < (unsigned)W) &
+                        ((unsigned)y0 < (unsigned)H) & ((unsigned)y1 < (unsigned)H) & ((unsigned)y2 < (unsigned)H);
+    int ymin = y0 < y1 ? y0 : y1; ymin = ymin < y2 ? ymin : y2;
+    int ymax = y0 > y1 ? y0 : y1; ymax = ymax > y2 ? ymax : y2;
+    return inside && (ymax - ymin <= 1);
+}
+
+template <class Run>
+TDS_HD void draw_thin_edge(int sx, int sy, int xa, int ya, int xb, int yb, Run&& run) {
+    // order the endpoints left to right (LineIterator leftToRight; a vertical edge keeps its order, which
+    // does not matter for the pixel set)
+    if (xb < xa) { int t = xa; xa = xb; xb = t; t = ya; ya = yb; yb = t; }
+    const int dx = xb - xa;
+    int dy = yb - ya, stepy = sy;
+    if (dy < 0) { dy = -dy; stepy = -sy; }
+    const int base = xa * sx + ya * sy;
+    if (dy <= 1 && dx >= dy) {
+        // x-major, at most one step in y: i0 pixels on the left endpoint's row, the rest on the other row
+        const int n = dx + 1;
+        const int i0 = dy == 0 ? n : ((dx + 2) >> 1);
+        run(base, i0, sx);
+        if (i0 < n) run(base + i0 * sx + stepy, n - i0, sx);
+    } else {
+        // y-major with dx <= 1: i0 pixels in the left endpoint's column, the rest in the next column
+        const int n = dy + 1;
+        const int i0 = dx == 0 ? n : ((dy + 2) >> 1);
+        run(base, i0, stepy);
+        if (i0 < n) run(base + i0 * stepy + sx, n - i0, stepy);
+    }
+}
+
+template <class Run>
+TDS_HD void draw_triangle_thin(int sx, int sy, int x0, int y0, int x1, int y1, int x2, int y2, Run&& run) {
+    draw_thin_edge(sx, sy, x2, y2, x0, y0, run);
+    draw_thin_edge(sx, sy, x0, y0, x1, y1, run);
+    draw_thin_edge(sx, sy, x1, y1, x2, y2, run);
+}
+
 }  // namespace tds
