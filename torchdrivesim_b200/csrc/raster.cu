@@ -255,8 +255,10 @@ __device__ __forceinline__ void draw_item_thin(uint8_t* img, int res, uint8_t va
         img[x2 * res + y2] = val;
         return;
     }
-    tds::draw_triangle_thin(res, 1, x0, y0, x1, y1, x2, y2,
-        [&](int idx, int n, int step) { for (; n > 0; n--, idx += step) img[idx] = val; });
+    tds::draw_triangle_thin(res, 1, x0, y0, x1, y1, x2, y2, [&](int idx, int n, int step) {
+#pragma unroll 2
+        for (; n > 0; n--, idx += step) img[idx] = val;
+    });
 }
 
 __device__ __noinline__ void draw_item_slow(uint8_t* img, int res, uint8_t val, const int* xy) {

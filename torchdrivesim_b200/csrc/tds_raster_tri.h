@@ -63,6 +63,43 @@ TDS_HD_NOINLINE bool clip_line(int W, int H, long long& x1, long long& y1, long 
     return (c1 | c2) == 0;
 }
 
+// Same rule in 32-bit integers, valid while |coordinates| < 8192 (products < 2^28): used by the fast path.
+TDS_HD_NOINLINE bool clip_line32(int W, int H, int& x1, int& y1, int& x2, int& y2) {
+    const int right = W - 1, bottom = H - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        int a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += ((a - y1) * (x2 - x1)) / (y2 - y1);
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += ((a - y2) * (x2 - x1)) / (y2 - y1);
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += ((a - x1) * (y2 - y1)) / (x2 - x1);
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += ((a - x2) * (y2 - y1)) / (x2 - x1);
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
 // 8-connected line from (xa,ya) to (xb,yb), both endpoints inclusive.  plot(x, y).
 template <class Plot>
 TDS_HD void draw_line8(int W, int H, int xa, int ya, int xb, int yb, Plot&& plot) {
@@ -156,9 +193,7 @@ template <class Plot>
 TDS_HD void draw_line8_fast(int W, int H, int sx, int sy, int xa, int ya, int xb, int yb, Plot&& plot) {
     if ((unsigned)xa >= (unsigned)W || (unsigned)xb >= (unsigned)W ||
         (unsigned)ya >= (unsigned)H || (unsigned)yb >= (unsigned)H) {
-        long long x1 = xa, y1 = ya, x2 = xb, y2 = yb;
-        if (!clip_line(W, H, x1, y1, x2, y2)) return;
-        xa = (int)x1; ya = (int)y1; xb = (int)x2; yb = (int)y2;
+        if (!clip_line32(W, H, xa, ya, xb, yb)) return;
     }
     int dx = xb - xa, dy = yb - ya;
     int idx = xa * sx + ya * sy;
@@ -245,34 +280,33 @@ TDS_HD bool is_thin_inside(int W, int H, int x0, int y0, int x1, int y1, int x2,
 }
 
 template <class Run>
-TDS_HD void draw_thin_edge(int sx, int sy, int xa, int ya, int xb, int yb, Run&& run) {
-    // order the endpoints left to right (LineIterator leftToRight; a vertical edge keeps its order, which
-    // does not matter for the pixel set)
-    if (xb < xa) { int t = xa; xa = xb; xb = t; t = ya; ya = yb; yb = t; }
-    const int dx = xb - xa;
-    int dy = yb - ya, stepy = sy;
-    if (dy < 0) { dy = -dy; stepy = -sy; }
-    const int base = xa * sx + ya * sy;
-    if (dy <= 1 && dx >= dy) {
-        // x-major, at most one step in y: i0 pixels on the left endpoint's row, the rest on the other row
-        const int n = dx + 1;
-        const int i0 = dy == 0 ? n : ((dx + 2) >> 1);
-        run(base, i0, sx);
-        if (i0 < n) run(base + i0 * sx + stepy, n - i0, sx);
-    } else {
-        // y-major with dx <= 1: i0 pixels in the left endpoint's column, the rest in the next column
-        const int n = dy + 1;
-        const int i0 = dx == 0 ? n : ((dy + 2) >> 1);
-        run(base, i0, stepy);
-        if (i0 < n) run(base + i0 * stepy + sx, n - i0, stepy);
-    }
-}
-
-template <class Run>
 TDS_HD void draw_triangle_thin(int sx, int sy, int x0, int y0, int x1, int y1, int x2, int y2, Run&& run) {
-    draw_thin_edge(sx, sy, x2, y2, x0, y0, run);
-    draw_thin_edge(sx, sy, x0, y0, x1, y1, run);
-    draw_thin_edge(sx, sy, x1, y1, x2, y2, run);
+    // edges v2->v0, v0->v1, v1->v2 in one rolled loop (code size), each as two runs of a common stride
+    int xa = x2, ya = y2, xb = x0, yb = y0, xc = x1, yc = y1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int e = 0; e < 3; e++) {
+        // endpoints left to right (LineIterator leftToRight; a vertical edge keeps its order, which does not
+        // change its pixel set)
+        const bool swap = xb < xa;
+        const int lx = swap ? xb : xa, ly = swap ? yb : ya, rx = swap ? xa : xb, ry = swap ? ya : yb;
+        const int dx = rx - lx;
+        int dy = ry - ly, stepy = sy;
+        if (dy < 0) { dy = -dy; stepy = -sy; }
+        const int base = lx * sx + ly * sy;
+        // x-major (dy <= 1 <= dx or a horizontal edge): i0 pixels on the left endpoint's row, the rest on the
+        // other row; y-major (dx <= 1): i0 pixels in the left endpoint's column, the rest in the next column
+        const bool xmajor = dx >= dy;
+        const int major = xmajor ? dx : dy, minor = xmajor ? dy : dx;
+        const int stride = xmajor ? sx : stepy, jump = xmajor ? stepy : sx;
+        const int n = major + 1;
+        const int i0 = minor == 0 ? n : ((major + 2) >> 1);
+        run(base, i0, stride);
+        run(base + i0 * stride + jump, n - i0, stride);
+        const int tx_ = xa, ty_ = ya;
+        xa = xb; ya = yb; xb = xc; yb = yc; xc = tx_; yc = ty_;
+    }
 }
 
 }  // namespace tds
