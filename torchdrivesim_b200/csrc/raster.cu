@@ -297,7 +297,7 @@ __device__ __forceinline__ void group_sync() {
 }
 
 #ifndef TDS_RASTER_MINB
-#define TDS_RASTER_MINB 6
+#define TDS_RASTER_MINB 7
 #endif
 template <int G, int RES>
 __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB : 1) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     int* s_cnt = s_pref + kRows;                   // [0] thin count, [1] general count, [4] total
     float* s_edges = reinterpret_cast<float*>(s_cnt + 6);                   // [12]
     __shared__ float s_lut[(TDS_MAX_CLASSES + 1) * 3];
-    for (int i = threadIdx.x; i < (TDS_MAX_CLASSES + 1) * 3; i += blockDim.x) s_lut[i] = pal.rgb[i / 3][i % 3];
+    for (int i = threadIdx.x; i < (TDS_MAX_CLASSES + 1) * 3; i += blockDim.x) s_lut[i] = (&pal.rgb[0][0])[i];
     __syncthreads();
     if (!active) return;                        // no block barrier is used below when G == 32
 
