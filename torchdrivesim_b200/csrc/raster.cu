@@ -169,11 +169,10 @@ struct Item {
     uint32_t a, b, c;       // (x0,y0), (x1,y1), (x2,y2) as int16 pairs
 };
 
-__device__ __forceinline__ int classify(float u, float v, float lo, float hi, float m) {
-    // 1 inside, 0 outside, -1 undecided
-    const bool in = (u > lo + m) & (u < hi - m) & (v > lo + m) & (v < hi - m);
-    const bool out = (u < lo - m) | (u > hi + m) | (v < lo - m) | (v > hi + m);
-    return in ? 1 : (out ? 0 : -1);
+__device__ __forceinline__ int classify(float u, float v, float mid, float r_in, float r_out) {
+    // 1 inside, 0 outside, -1 undecided: the quad is the max-norm ball of radius 1.05 res / 2 around the image centre
+    const float d = fmaxf(fabsf(u - mid), fabsf(v - mid));
+    return d < r_in ? 1 : (d > r_out ? 0 : -1);        // NaN falls through to "undecided"
 }
 
 __device__ __forceinline__ void project_f(const Camera& cam, float x, float y, float& u0, float& u1) {
@@ -196,10 +195,11 @@ __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float
     project_f(cam, px0, py0, u0, v0);
     project_f(cam, px1, py1, u1, v1);
     project_f(cam, px2, py2, u2, v2);
-    const float lo = -0.025f * cam.fmin, hi = 1.025f * cam.fmin;
     // fp32 disagreement between the pixel-space and the edge-function test is < 1e-4 m; band = 0.01 px + 2e-3 m
     const float band = 0.01f + 0.002f * (cam.scale * cam.half);
-    int c0 = classify(u0, v0, lo, hi, band), c1 = classify(u1, v1, lo, hi, band), c2 = classify(u2, v2, lo, hi, band);
+    const float r_in = 0.525f * cam.fmin - band, r_out = 0.525f * cam.fmin + band;
+    int c0 = classify(u0, v0, cam.half, r_in, r_out), c1 = classify(u1, v1, cam.half, r_in, r_out),
+        c2 = classify(u2, v2, cam.half, r_in, r_out);
     if ((c0 | c1 | c2) < 0) {       // some vertex is within the band around the quad boundary (or NaN): exact test
         // one rolled loop over the three vertices keeps this rare path small; the edge functions live in smem
         float ex = px0, ey = py0;
@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
         const int ndyn = ((pal.dyn_mask >> c) & 1u) ? T : 0;
         const int total = total_static + ndyn;
         int row = 0;                                   // candidates are visited in increasing order
+        int n_thin_w = 0, n_gen_w = 0;                 // queue fill levels of a warp group
         // chunks of kQueue candidates: stage 1 (cull + project + classify) appends to the two-ended queue, stage 2
         // scan-converts it.  There is exactly ONE copy of each scan-conversion routine in the kernel: the
         // instruction-cache footprint matters more than anything else here.
@@ -459,12 +460,18 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 const unsigned mt = __ballot_sync(full, kind == 1), mg = __ballot_sync(full, kind == 3);
                 if (mt | mg) {
                     int base_t = 0, base_g = 0;
-                    if (lane == leader) {
-                        if (mt) base_t = atomicAdd(&s_cnt[0], __popc(mt));
-                        if (mg) base_g = atomicAdd(&s_cnt[1], __popc(mg));
+                    if (G == 32) {
+                        // one warp owns the queue: the counters live in (warp-uniform) registers
+                        base_t = n_thin_w; base_g = n_gen_w;
+                        n_thin_w += __popc(mt); n_gen_w += __popc(mg);
+                    } else {
+                        if (lane == leader) {
+                            if (mt) base_t = atomicAdd(&s_cnt[0], __popc(mt));
+                            if (mg) base_g = atomicAdd(&s_cnt[1], __popc(mg));
+                        }
+                        base_t = __shfl_sync(full, base_t, leader);
+                        base_g = __shfl_sync(full, base_g, leader);
                     }
-                    base_t = __shfl_sync(full, base_t, leader);
-                    base_g = __shfl_sync(full, base_g, leader);
                     const unsigned below = (1u << lane) - 1;
                     int pos = -1;
                     if (kind == 1) pos = base_t + __popc(mt & below);
@@ -472,8 +479,10 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                     if (pos >= 0) { queue[pos] = it.a; queue[kQueue + pos] = it.b; queue[2 * kQueue + pos] = it.c; }
                 }
             }
+            // lanes that ran fewer rounds missed the last ballots: take the counts of the lane that ran them all
+            if (G == 32) { n_thin_w = __shfl_sync(0xffffffffu, n_thin_w, 0); n_gen_w = __shfl_sync(0xffffffffu, n_gen_w, 0); }
             group_sync<G>();
-            const int n_thin = s_cnt[0], n_gen = s_cnt[1];
+            const int n_thin = G == 32 ? n_thin_w : s_cnt[0], n_gen = G == 32 ? n_gen_w : s_cnt[1];
             for (int k = tid; k < n_thin; k += G) {
                 Item q;
                 q.a = queue[k]; q.b = queue[kQueue + k]; q.c = queue[2 * kQueue + k];
@@ -485,8 +494,12 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 draw_item(img, res, val, q);
             }
             group_sync<G>();
-            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-            group_sync<G>();
+            if (G == 32) {
+                n_thin_w = 0; n_gen_w = 0;
+            } else {
+                if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+                group_sync<G>();
+            }
         }
     }
     group_sync<G>();
