@@ -24,3 +24,15 @@ extern "C" int tds_host_draw_triangle_thin(uint8_t* img, int W, int H, const int
         [&](int idx, int n, int step) { for (int i = 0; i < n; i++) img[idx + i * step] = 1; });
     return 1;
 }
+
+// row-run form used by the bitplane raster kernel (tds_raster_rows.h): rows visited in increasing order
+#include "tds_raster_rows.h"
+extern "C" void tds_host_draw_triangle_rows(uint8_t* img, int W, int H, const int32_t* p) {
+    tds::RowTri t;
+    tds::row_tri_setup(W, H, p[0], p[1], p[2], p[3], p[4], p[5], t, [](int dy) { return tds::row_rcp(dy); });
+    for (int y = t.ylo; y <= t.yhi; y++)
+        tds::row_tri_step(t, W, y, [&](int lo, int hi) {
+            if (lo < 0 || hi >= W || lo > hi) { img[0] = 99; return; }      // contract violation: flagged
+            for (int x = lo; x <= hi; x++) img[y * W + x] = 1;
+        });
+}

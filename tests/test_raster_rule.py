@@ -76,6 +76,18 @@ def test_kernel_rule_fast_path_matches_cv2(host_rule, res):
         assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
 
 
+@pytest.mark.parametrize("res", [8, 64, 256, 448])
+def test_kernel_rule_row_runs_match_cv2(host_rule, res):
+    """Closed-form LineIterator runs + fixed-point spans per row (tds_raster_rows.h), the rule of the bitplane kernel."""
+    rng = np.random.default_rng(res + 3)
+    for pts in _triangles(rng, res, 6000, max_abs=8000):
+        m = np.zeros((res, res), np.uint8)
+        host_rule.tds_host_draw_triangle_rows(m.ctypes.data_as(ctypes.c_void_p), res, res,
+                                              pts.ctypes.data_as(ctypes.c_void_p))
+        assert m.max() <= 1, pts.tolist()
+        assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
+
+
 def test_degenerate_and_collinear():
     for pts in ([[5, 5], [5, 5], [5, 5]], [[0, 0], [10, 10], [20, 20]], [[3, 7], [3, 7], [9, 7]], [[-5, -5], [-1, -1], [-3, -9]]):
         pts = np.array(pts, np.int32)

@@ -16,6 +16,17 @@ int fail(int code, const char* fmt, ...) {
     last_error() = buf;
     return code;
 }
+int sm_count() {
+    // per device, cached (cudaGetDeviceProperties is slow)
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
 }  // namespace tds
 
 extern "C" int tds_version(void) { return 100; }

@@ -74,20 +74,12 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     cudaGetDevice(&m->device);
     int64_t bytes = 0;
 
-    // ---------------- slots
+    // ---------------- distinct static classes (informational; the raster keeps the class in each record)
     int slot_of[TDS_MAX_CLASSES];
     std::fill(slot_of, slot_of + TDS_MAX_CLASSES, -1);
     int n_slots = 0;
-    for (int f = 0; f < nf; f++) {
-        if (slot_of[h_face_class[f]] < 0) {
-            if (n_slots == kMaxSlots) {
-                fail(TDS_ERR_UNSUPPORTED, "map_create: more than %d distinct static classes", kMaxSlots);
-                delete m;
-                return nullptr;
-            }
-            slot_of[h_face_class[f]] = n_slots++;
-        }
-    }
+    for (int f = 0; f < nf; f++)
+        if (slot_of[h_face_class[f]] < 0) slot_of[h_face_class[f]] = n_slots++;
     // ---------------- raster grid (vertex binning)
     d.rcs = raster_cell;
     d.rinv = 1.0f / raster_cell;
@@ -110,18 +102,22 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     for (int f = 0; f < nf; f++) {
         int cell[3];
         for (int k = 0; k < 3; k++) cell[k] = rcell_of(h_verts[2 * h_faces[3 * f + k]], h_verts[2 * h_faces[3 * f + k] + 1]);
-        const int slot = slot_of[h_face_class[f]];
         for (int k = 0; k < 3; k++) {
             bool seen = false;
             for (int j = 0; j < k; j++) seen |= cell[j] == cell[k];
             if (seen) continue;
             int own = 0;
             for (int j = 0; j < 3; j++) own |= (cell[j] == cell[k]) << j;
-            recs.push_back({slot * nc + cell[k], f, own});
+            recs.push_back({cell[k], f, own});
         }
     }
-    std::stable_sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.key < b.key; });
-    std::vector<int32_t> rcell((size_t)n_slots * nc + 1, 0);
+    // cell-major (all classes of a cell together: the kernel makes ONE pass over the candidates and keeps
+    // painter's order in per-class bitplanes); inside a cell by class, then by face
+    std::stable_sort(recs.begin(), recs.end(), [&](const Rec& a, const Rec& b) {
+        if (a.key != b.key) return a.key < b.key;
+        return h_face_class[a.face] < h_face_class[b.face];
+    });
+    std::vector<int32_t> rcell((size_t)nc + 1, 0);
     for (const Rec& r : recs) rcell[r.key + 1]++;
     for (size_t i = 0; i + 1 < rcell.size(); i++) rcell[i + 1] += rcell[i];
     std::vector<float> recdata(recs.size() * 8, 0.f);
@@ -131,7 +127,8 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
             recdata[8 * i + 2 * k] = h_verts[2 * h_faces[3 * f + k]];
             recdata[8 * i + 2 * k + 1] = h_verts[2 * h_faces[3 * f + k] + 1];
         }
-        memcpy(&recdata[8 * i + 6], &recs[i].own, sizeof(int));
+        const int meta = recs[i].own | ((int)h_face_class[f] << 8);
+        memcpy(&recdata[8 * i + 6], &meta, sizeof(int));
     }
     // ---------------- offroad grid (bounding-box binning)
     d.ocs = offroad_cell;

@@ -17,13 +17,15 @@
 //   * the tile is stored x-major, which IS the reference's final transpose (cv2.py:61), then expanded
 //     through a colour LUT to 3 float planes with coalesced streaming 128-bit stores.
 // HBM traffic per camera: 12 * res^2 bytes of image out (49 KB at 64x64); the map records are L2 hits.
+#include <algorithm>
+
 #include "tds_map.cuh"
 #include "tds_raster_tri.h"
+#include "tds_raster_rows.h"
 
 namespace {
 
 using tds::kMaxRasterRows;
-using tds::kMaxSlots;
 using tds::MapDev;
 using tds::MapSetDev;
 
@@ -165,10 +167,6 @@ __device__ __forceinline__ bool inside_quad(const Camera& cam, float x, float y)
 // centre, i.e. pixel coordinates in [-0.025 res, 1.025 res].  A projected vertex further than ~0.01 px from
 // that boundary is decided from its pixel coordinates; the thin band around the boundary falls back to
 // the reference's fp32 edge functions, so the decision is always the reference's.
-struct Item {
-    uint32_t a, b, c;       // (x0,y0), (x1,y1), (x2,y2) as int16 pairs
-};
-
 __device__ __forceinline__ int classify(float u, float v, float mid, float r_in, float r_out) {
     // 1 inside, 0 outside, -1 undecided: the quad is the max-norm ball of radius 1.05 res / 2 around the image centre
     const float d = fmaxf(fabsf(u - mid), fabsf(v - mid));
@@ -184,10 +182,11 @@ __device__ __forceinline__ void project_f(const Camera& cam, float x, float y, f
     u0 = u0 + cam.half;     u1 = u1 + cam.half;
 }
 
-// returns 0: culled / invisible, 1: thin item, 3: general item (|coords| < 8192), 2: kept but needs the 64-bit
-// slow path (ints in xy[])
+// kind of a candidate after cull + projection + truncation (rendering/cv2.py:52-56)
+enum { kCulled = 0, kVerts = 1, kGeneral = 2, kHuge = 3 };
+
 __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float y0, float x1, float y1, float x2,
-                                              float y2, int own, Item& it, int xy[6]) {
+                                              float y2, int own, int xy[6]) {
     const float px0 = x0 + cam.ncx, py0 = y0 + cam.ncy;
     const float px1 = x1 + cam.ncx, py1 = y1 + cam.ncy;
     const float px2 = x2 + cam.ncx, py2 = y2 + cam.ncy;
@@ -211,60 +210,62 @@ __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float
             else { if (c2 < 0) c2 = r; }
         }
     }
-    if (!(c0 | c1 | c2)) return 0;
+    if (!(c0 | c1 | c2)) return kCulled;
     const int first = c0 ? 0 : (c1 ? 1 : 2);
-    if (!((own >> first) & 1)) return 0;          // another cell's copy of this face draws it
+    if (!((own >> first) & 1)) return kCulled;    // another cell's copy of this face draws it
     xy[0] = __float2int_rz(u0); xy[1] = __float2int_rz(v0);
     xy[2] = __float2int_rz(u1); xy[3] = __float2int_rz(v1);
     xy[4] = __float2int_rz(u2); xy[5] = __float2int_rz(v2);
     int big = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++) big |= (xy[k] <= -8192) | (xy[k] >= 8192);
-    if (big) return 2;
+    if (big) return kHuge;
     // integer bounding box entirely off the image: clipLine rejects all three edges and the fill returns early
     const int res = cam.res;
     const int xmin = min(min(xy[0], xy[2]), xy[4]), xmax = max(max(xy[0], xy[2]), xy[4]);
     const int ymin = min(min(xy[1], xy[3]), xy[5]), ymax = max(max(xy[1], xy[3]), xy[5]);
-    if (xmax < 0 || ymax < 0 || xmin >= res || ymin >= res) return 0;
-    it.a = (uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16);
-    it.b = (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16);
-    it.c = (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16);
-    // thin = at most two rows and fully inside the image: closed-form runs (tds_raster_tri.h)
-    const bool thin = (ymax - ymin <= 1) & (xmin >= 0) & (ymin >= 0) & (xmax < res) & (ymax < res);
-    return thin ? 1 : 3;
+    if (xmax < 0 || ymax < 0 || xmin >= res || ymin >= res) return kCulled;
+    // bounding box within 2x2 pixels: the coverage is the set of in-image vertices (tds_raster_tri.h)
+    return ((xmax - xmin <= 1) & (ymax - ymin <= 1)) ? kVerts : kGeneral;
 }
 
-// ---- stage 2: scan-convert.  The tile is x-major (img[x * res + y]) which IS the transpose of cv2.py:61
-__device__ __forceinline__ void draw_item(uint8_t* img, int res, uint8_t val, const Item& it) {
-    const int x0 = (int16_t)(it.a & 0xffff), y0 = (int32_t)it.a >> 16;
-    const int x1 = (int16_t)(it.b & 0xffff), y1 = (int32_t)it.b >> 16;
-    const int x2 = (int16_t)(it.c & 0xffff), y2 = (int32_t)it.c >> 16;
-    tds::draw_triangle_fast(res, res, res, 1, x0, y0, x1, y1, x2, y2,
-        [&](int idx) { img[idx] = val; },
-        [&](int idx, int n, int step) { for (; n > 0; n--, idx += step) img[idx] = val; });
+// ---- bitplanes: one bit per pixel and draw rank; plane p, word column w, row y at  p * res * W32 + w * res + y
+__device__ __forceinline__ void or_bit(uint32_t* plane, int res, int x, int y) {
+    atomicOr(plane + (x >> 5) * res + y, 1u << (x & 31));
 }
 
-__device__ __forceinline__ void draw_item_thin(uint8_t* img, int res, uint8_t val, const Item& it) {
-    const int x0 = (int16_t)(it.a & 0xffff), y0 = (int32_t)it.a >> 16;
-    const int x1 = (int16_t)(it.b & 0xffff), y1 = (int32_t)it.b >> 16;
-    const int x2 = (int16_t)(it.c & 0xffff), y2 = (int32_t)it.c >> 16;
-    const int xmin = min(min(x0, x1), x2), xmax = max(max(x0, x1), x2);
-    if (xmax - xmin <= 1) {      // within 2x2 pixels: the outline is the three vertices
-        img[x0 * res + y0] = val;
-        img[x1 * res + y1] = val;
-        img[x2 * res + y2] = val;
-        return;
+__device__ __forceinline__ void or_span(uint32_t* plane, int res, int y, int lo, int hi) {
+    for (int w = lo >> 5; w <= (hi >> 5); w++) {
+        const int l = max(lo - 32 * w, 0), h = min(hi - 32 * w, 31);
+        atomicOr(plane + w * res + y, (0xffffffffu >> (31 - (h - l))) << l);
     }
-    tds::draw_triangle_thin(res, 1, x0, y0, x1, y1, x2, y2, [&](int idx, int n, int step) {
-#pragma unroll 2
-        for (; n > 0; n--, idx += step) img[idx] = val;
-    });
 }
 
-__device__ __noinline__ void draw_item_slow(uint8_t* img, int res, uint8_t val, const int* xy) {
+// stage 2: all rows of one triangle (|coordinates| < 8192), one atomic OR per row and 32-pixel word
+template <int RES>
+__device__ __forceinline__ void draw_rows(uint32_t* plane, int res, const uint32_t* s_rcp, int x0, int y0, int x1, int y1,
+                                          int x2, int y2) {
+    tds::RowTri t;
+    tds::row_tri_setup(res, res, x0, y0, x1, y1, x2, y2, t, [&](int dy) { return s_rcp[dy]; });
+#pragma unroll 1
+    for (int y = t.ylo; y <= t.yhi; y++) {
+        if (RES == 64) {
+            unsigned long long m = 0ull;
+            tds::row_tri_step(t, res, y, [&](int lo, int hi) { m |= (~0ull >> (63 - (hi - lo))) << lo; });
+            const uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
+            if (m0) atomicOr(plane + y, m0);
+            if (m1) atomicOr(plane + 64 + y, m1);
+        } else {
+            tds::row_tri_step(t, res, y, [&](int lo, int hi) { or_span(plane, res, y, lo, hi); });
+        }
+    }
+}
+
+// coordinates beyond +-8192 pixels (extreme zoom / giant rectangles): 64-bit rule, pixel by pixel.  Rare.
+__device__ __noinline__ void draw_huge(uint32_t* plane, int res, const int* xy) {
     tds::draw_triangle(res, res, xy[0], xy[1], xy[2], xy[3], xy[4], xy[5],
-        [&](int x, int y) { img[x * res + y] = val; },
-        [&](int y, int xa, int xb) { for (int x = xa; x <= xb; x++) img[x * res + y] = val; });
+        [&](int x, int y) { or_bit(plane, res, x, y); },
+        [&](int y, int xa, int xb) { or_span(plane, res, y, xa, xb); });
 }
 
 struct RasterArgs {
@@ -279,16 +280,15 @@ struct RasterArgs {
     float scale;
 };
 
-// per-group item queue: thin items grow from the front, general items from the back; a chunk of kChunk candidates
-// can never overflow it.  12 B per item.
-template <int G>
-struct QCfg {
-    static constexpr int total = G == 32 ? 128 : 2 * G;      // = candidates per chunk
-};
 constexpr int kRows = tds::kMaxRasterRows;
-constexpr int kGroupExtra = kRows * 8 + 32 + 48;   // row tables, counters, view-quad edge functions
+constexpr int kGroupExtra = kRows * 8 + 16 + 48;    // row tables, counters, view-quad edge functions
 
-// G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras per CTA, no block barriers)
+__host__ __device__ inline int raster_group_bytes(int res, int n_planes, int G) {
+    const int w32 = (res + 31) / 32;
+    return n_planes * res * w32 * 4 + 2 * G * 16 + kGroupExtra;
+}
+
+// G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras in flight per CTA, no block barriers)
 // for tiles up to 64x64, or the whole CTA for larger tiles.
 template <int G>
 __device__ __forceinline__ void group_sync() {
@@ -297,143 +297,144 @@ __device__ __forceinline__ void group_sync() {
 }
 
 #ifndef TDS_RASTER_MINB
-#define TDS_RASTER_MINB 7
+#define TDS_RASTER_MINB 6
 #endif
-template <int G, int RES>
+// NS = bits of the per-pixel draw rank (0 = background): 3 for up to 7 active classes, 5 for up to 31
+template <int G, int RES, int NS>
 __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB : 1) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int GROUPS = G == 32 ? 4 : 1;
+    constexpr int QN = 2 * G;
     const int res = RES ? RES : a.res;          // RES = 64 is compiled with constant strides
+    const int W32 = RES ? RES / 32 : (res + 31) >> 5;
     const int group = G == 32 ? (threadIdx.x >> 5) : 0;
     const int tid = G == 32 ? (threadIdx.x & 31) : threadIdx.x;
-    const int camid = blockIdx.x * GROUPS + group;
-    const bool active = camid < a.ncam;         // whole group is inactive together
+    const int lane = threadIdx.x & 31;
+    const int K = pal.n_classes;                // planes = draw ranks of the active classes
 
-    // per-group shared memory: tile | queue | row tables
-    const int tile_bytes = res * res;
-    constexpr int kQueue = QCfg<G>::total;
-    const int group_bytes = tile_bytes + kQueue * 12 + kGroupExtra;
-    uint8_t* base = smem_raw + (size_t)group * group_bytes;
-    uint8_t* img = base;
-    uint32_t* queue = reinterpret_cast<uint32_t*>(base + tile_bytes);      // [3][kQueue]
-    int* s_start = reinterpret_cast<int*>(base + tile_bytes + kQueue * 12);
-    int* s_pref = s_start + kRows;                                         // exclusive prefix of the row counts
-    int* s_cnt = s_pref + kRows;                   // [0] thin count, [1] general count, [4] total
-    float* s_edges = reinterpret_cast<float*>(s_cnt + 6);                   // [12]
-    __shared__ float s_lut[(TDS_MAX_CLASSES + 1) * 3];
-    for (int i = threadIdx.x; i < (TDS_MAX_CLASSES + 1) * 3; i += blockDim.x) s_lut[i] = (&pal.rgb[0][0])[i];
+    // CTA-wide tables: colour per draw rank (0 = background), reciprocals of the row runs, class -> plane
+    __shared__ float4 s_lut[TDS_MAX_CLASSES + 1];
+    __shared__ int8_t s_plane_of_class[TDS_MAX_CLASSES];
+    uint32_t* s_rcp = reinterpret_cast<uint32_t*>(smem_raw);                 // [res + 1]
+    const int rcp_bytes = ((res + 1) * 4 + 15) & ~15;
+    for (int i = threadIdx.x; i <= K; i += blockDim.x) {
+        const float* c = pal.rgb[i == 0 ? 0 : pal.order[i - 1] + 1];
+        s_lut[i] = make_float4(c[0], c[1], c[2], 0.f);
+    }
+    for (int i = threadIdx.x; i < TDS_MAX_CLASSES; i += blockDim.x) {
+        int p = -1;
+        for (int k = 0; k < K; k++) p = pal.order[k] == i ? k : p;
+        s_plane_of_class[i] = (int8_t)p;
+    }
+    for (int i = threadIdx.x; i <= res; i += blockDim.x) s_rcp[i] = tds::row_rcp(i);
     __syncthreads();
-    if (!active) return;                        // no block barrier is used below when G == 32
 
-    const int b = camid / a.Nc;
-    const MapDev& map = maps.m[a.env_map ? a.env_map[b] : 0];
-    Camera cam;
-    float qx[4], qy[4];
-    const float2 cxy = reinterpret_cast<const float2*>(a.cam_xy)[camid];
-    const float2 csc = reinterpret_cast<const float2*>(a.cam_sc)[camid];
-    make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy, s_edges, tid == 0);
+    // per-group shared memory: planes | queue | row tables
+    const int plane_words = res * W32;
+    const int group_bytes = raster_group_bytes(res, K, G);
+    uint8_t* base = smem_raw + rcp_bytes + (size_t)group * group_bytes;
+    uint32_t* planes = reinterpret_cast<uint32_t*>(base);
+    uint4* queue = reinterpret_cast<uint4*>(base + (size_t)K * plane_words * 4);          // [QN]
+    int* s_start = reinterpret_cast<int*>(queue + QN);
+    int* s_pref = s_start + kRows;                                         // exclusive prefix of the row counts
+    int* s_cnt = s_pref + kRows;                   // [0] queue fill, [1] total static candidates
+    float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
 
-    {   // clear the tile
-        uint32_t* w = reinterpret_cast<uint32_t*>(img);
-        for (int i = tid; i < tile_bytes / 4; i += G) w[i] = 0u;
-        if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; }
-    }
-    // ---- grid rows touched by the view quad (world coordinates), with a 5 cm safety margin
-    const float margin = 0.05f;
-    float wqx[4], wqy[4];
+    // cameras are dealt round-robin to the groups of a persistent grid
+    for (int camid = blockIdx.x * GROUPS + group; camid < a.ncam; camid += gridDim.x * GROUPS) {
+        const int b = camid / a.Nc;
+        const MapDev& map = maps.m[a.env_map ? a.env_map[b] : 0];
+        Camera cam;
+        float qx[4], qy[4];
+        const float2 cxy = reinterpret_cast<const float2*>(a.cam_xy)[camid];
+        const float2 csc = reinterpret_cast<const float2*>(a.cam_sc)[camid];
+        group_sync<G>();                            // previous camera of this group is completely done
+        make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy, s_edges, tid == 0);
+        for (int i = tid; i < K * plane_words; i += G) planes[i] = 0u;
+        if (tid == 0) s_cnt[0] = 0;
+
+        // ---- grid rows touched by the view quad (world coordinates), with a 5 cm safety margin
+        const float margin = 0.05f;
+        float wqx[4], wqy[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { wqx[i] = qx[i] + cxy.x; wqy[i] = qy[i] + cxy.y; }
-    const float ymin = fminf(fminf(wqy[0], wqy[1]), fminf(wqy[2], wqy[3])) - margin;
-    const float ymax = fmaxf(fmaxf(wqy[0], wqy[1]), fmaxf(wqy[2], wqy[3])) + margin;
-    int r0 = (int)floorf((ymin - map.ry0) * map.rinv), r1 = (int)floorf((ymax - map.ry0) * map.rinv);
-    r0 = max(r0, 0);
-    r1 = min(r1, map.rgy - 1);
-    const int nrows = min(max(r1 - r0 + 1, 0), kRows);
-    // column interval of row (r0 + tid), kept in registers of lane/thread tid < nrows
-    int my_c0 = 0, my_c1 = -1;
-    if (tid < nrows) {
-        const int r = r0 + tid;
-        const float ylo = map.ry0 + (float)r * map.rcs - margin, yhi = map.ry0 + (float)(r + 1) * map.rcs + margin;
-        float xmin = 3.0e38f, xmax = -3.0e38f;
+        for (int i = 0; i < 4; i++) { wqx[i] = qx[i] + cxy.x; wqy[i] = qy[i] + cxy.y; }
+        const float ymin = fminf(fminf(wqy[0], wqy[1]), fminf(wqy[2], wqy[3])) - margin;
+        const float ymax = fmaxf(fmaxf(wqy[0], wqy[1]), fmaxf(wqy[2], wqy[3])) + margin;
+        int r0 = (int)floorf((ymin - map.ry0) * map.rinv), r1 = (int)floorf((ymax - map.ry0) * map.rinv);
+        r0 = max(r0, 0);
+        r1 = min(r1, map.rgy - 1);
+        const int nrows = min(max(r1 - r0 + 1, 0), kRows);
+        // column interval of grid row (r0 + tid) -> one contiguous record range (all classes)
+        if (tid < nrows) {
+            const int r = r0 + tid;
+            const float ylo = map.ry0 + (float)r * map.rcs - margin, yhi = map.ry0 + (float)(r + 1) * map.rcs + margin;
+            float xmin = 3.0e38f, xmax = -3.0e38f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int j = (i + 1) & 3;
-            const float y0 = wqy[i], y1 = wqy[j], x0 = wqx[i], x1 = wqx[j];
-            if (fmaxf(y0, y1) < ylo || fminf(y0, y1) > yhi) continue;
-            float t0 = 0.f, t1 = 1.f;
-            const float dy = y1 - y0;
-            if (dy != 0.f) {
-                float ta = (ylo - y0) / dy, tb = (yhi - y0) / dy;
-                if (ta > tb) { const float t = ta; ta = tb; tb = t; }
-                t0 = fmaxf(t0, ta);
-                t1 = fminf(t1, tb);
-            }
-            const float xa = x0 + t0 * (x1 - x0), xb = x0 + t1 * (x1 - x0);
-            xmin = fminf(xmin, fminf(xa, xb));
-            xmax = fmaxf(xmax, fmaxf(xa, xb));
-        }
-        if (xmin <= xmax) {
-            my_c0 = max((int)floorf((xmin - margin - map.rx0) * map.rinv), 0);
-            my_c1 = min((int)floorf((xmax + margin - map.rx0) * map.rinv), map.rgx - 1);
-        }
-    }
-    group_sync<G>();
-
-    const int T = a.T;
-    const float* dtri = reinterpret_cast<const float*>(a.ws + (int64_t)b * ws_env_bytes(T));
-    const uint8_t* dcls = reinterpret_cast<const uint8_t*>(dtri + (int64_t)T * 6);
-    const uint8_t* pres = a.present ? (a.present_per_camera ? a.present + (int64_t)camid * a.N : a.present + (int64_t)b * a.N)
-                                    : nullptr;
-    const int ncell = map.rgx * map.rgy;
-
-    // ---- painter's passes, first drawn = highest z.  Each pass: stage 1 culls + projects candidates and
-    // appends the kept ones to the queue (warp-aggregated), stage 2 scan-converts the queue.
-    for (int ph = 0; ph < pal.n_classes; ph++) {
-        const int c = pal.order[ph];
-        const uint8_t val = (uint8_t)(c + 1);
-        const int slot = map.slot_of_class[c];
-        int total_static = 0;
-        if (slot >= 0 && nrows > 0) {
-            // record range of every touched grid row for this class
-            if (tid < nrows) {
-                int st = 0, cnt = 0;
-                if (my_c1 >= my_c0) {
-                    const int cb = slot * ncell + (r0 + tid) * map.rgx;
-                    st = map.rcell[cb + my_c0];
-                    cnt = map.rcell[cb + my_c1 + 1] - st;
+            for (int i = 0; i < 4; i++) {
+                const int j = (i + 1) & 3;
+                const float y0 = wqy[i], y1 = wqy[j], x0 = wqx[i], x1 = wqx[j];
+                if (fmaxf(y0, y1) < ylo || fminf(y0, y1) > yhi) continue;
+                float t0 = 0.f, t1 = 1.f;
+                const float dy = y1 - y0;
+                if (dy != 0.f) {
+                    float ta = (ylo - y0) / dy, tb = (yhi - y0) / dy;
+                    if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+                    t0 = fmaxf(t0, ta);
+                    t1 = fminf(t1, tb);
                 }
-                s_start[tid] = st;
-                s_pref[tid] = cnt;
+                const float xa = x0 + t0 * (x1 - x0), xb = x0 + t1 * (x1 - x0);
+                xmin = fminf(xmin, fminf(xa, xb));
+                xmax = fmaxf(xmax, fmaxf(xa, xb));
             }
-            group_sync<G>();
-            if (tid == 0) {
-                int acc = 0;
-                for (int r = 0; r < nrows; r++) { const int n = s_pref[r]; s_pref[r] = acc; acc += n; }
-                s_cnt[4] = acc;
+            int st = 0, cnt = 0;
+            if (xmin <= xmax) {
+                const int c0 = max((int)floorf((xmin - margin - map.rx0) * map.rinv), 0);
+                const int c1 = min((int)floorf((xmax + margin - map.rx0) * map.rinv), map.rgx - 1);
+                if (c1 >= c0) {
+                    st = map.rcell[r * map.rgx + c0];
+                    cnt = map.rcell[r * map.rgx + c1 + 1] - st;
+                }
             }
-            group_sync<G>();
-            total_static = s_cnt[4];
+            s_start[tid] = st;
+            s_pref[tid] = cnt;
         }
-        const int ndyn = ((pal.dyn_mask >> c) & 1u) ? T : 0;
-        const int total = total_static + ndyn;
+        group_sync<G>();
+        if (tid == 0) {
+            int acc = 0;
+            for (int r = 0; r < nrows; r++) { const int n = s_pref[r]; s_pref[r] = acc; acc += n; }
+            s_cnt[1] = acc;
+        }
+        group_sync<G>();
+        const int total_static = s_cnt[1];
+
+        const int T = a.T;
+        const float* dtri = reinterpret_cast<const float*>(a.ws + (int64_t)b * ws_env_bytes(T));
+        const uint8_t* dcls = reinterpret_cast<const uint8_t*>(dtri + (int64_t)T * 6);
+        const uint8_t* pres = a.present ? (a.present_per_camera ? a.present + (int64_t)camid * a.N : a.present + (int64_t)b * a.N)
+                                        : nullptr;
+        const int total = total_static + T;
+
+        // ---- ONE pass over the candidates.  Stage 1 (cull + project + truncate) plots the faces that are just
+        // their vertices and queues the others; whenever G faces are queued, stage 2 converts them to row runs,
+        // one face per thread, so that stage 2 always runs with full warps.
         int row = 0;                                   // candidates are visited in increasing order
-        int n_thin_w = 0, n_gen_w = 0;                 // queue fill levels of a warp group
-        // chunks of kQueue candidates: stage 1 (cull + project + classify) appends to the two-ended queue, stage 2
-        // scan-converts it.  There is exactly ONE copy of each scan-conversion routine in the kernel: the
-        // instruction-cache footprint matters more than anything else here.
-        for (int c0 = 0; c0 < total; c0 += kQueue) {
-            const int cend = min(c0 + kQueue, total);
-            for (int i = c0 + tid; i < cend; i += G) {
+        int nq = 0;                                    // queue fill (uniform over the group)
+        for (int c0 = 0; c0 < total; c0 += G) {
+            const int i = c0 + tid;
+            int kind = kCulled, plane = -1;
+            int xy[6];
+            if (i < total) {
                 float x0, y0, x1, y1, x2, y2;
-                int own = 7;
-                bool valid = true;
+                int own = 7, cls;
                 if (i < total_static) {
                     while (row + 1 < nrows && i >= s_pref[row + 1]) row++;
                     const int idx = s_start[row] + (i - s_pref[row]);
                     const float4 v01 = __ldg(map.rec + 2 * (int64_t)idx);
                     const float4 v2o = __ldg(map.rec + 2 * (int64_t)idx + 1);
                     x0 = v01.x; y0 = v01.y; x1 = v01.z; y1 = v01.w; x2 = v2o.x; y2 = v2o.y;
-                    own = __float_as_int(v2o.z);
+                    const int meta = __float_as_int(v2o.z);
+                    own = meta & 7;
+                    cls = (meta >> 8) & 255;
                 } else {
                     // dynamic primitives (agents, direction triangles, traffic lights, signs)
                     int t = i - total_static;
@@ -444,80 +445,117 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                         t = 0;
                         degenerate = true;
                     }
-                    valid = dcls[t] == c;
+                    cls = dcls[t];
                     const float* p = dtri + (int64_t)t * 6;
                     x0 = p[0]; y0 = p[1];
                     x1 = degenerate ? x0 : p[2]; y1 = degenerate ? y0 : p[3];
                     x2 = degenerate ? x0 : p[4]; y2 = degenerate ? y0 : p[5];
                 }
-                Item it;
-                int xy[6];
-                const int kind = valid ? setup_triangle(cam, x0, y0, x1, y1, x2, y2, own, it, xy) : 0;
-                if (kind == 2) draw_item_slow(img, res, val, xy);     // huge triangle: rare, drawn in place
-                // thin items grow from the front of the queue, general items from the back (warp-aggregated)
-                const unsigned full = __activemask();
-                const int lane = threadIdx.x & 31, leader = __ffs(full) - 1;
-                const unsigned mt = __ballot_sync(full, kind == 1), mg = __ballot_sync(full, kind == 3);
-                if (mt | mg) {
-                    int base_t = 0, base_g = 0;
-                    if (G == 32) {
-                        // one warp owns the queue: the counters live in (warp-uniform) registers
-                        base_t = n_thin_w; base_g = n_gen_w;
-                        n_thin_w += __popc(mt); n_gen_w += __popc(mg);
-                    } else {
-                        if (lane == leader) {
-                            if (mt) base_t = atomicAdd(&s_cnt[0], __popc(mt));
-                            if (mg) base_g = atomicAdd(&s_cnt[1], __popc(mg));
-                        }
-                        base_t = __shfl_sync(full, base_t, leader);
-                        base_g = __shfl_sync(full, base_g, leader);
+                plane = cls < TDS_MAX_CLASSES ? s_plane_of_class[cls] : -1;
+                if (plane >= 0) kind = setup_triangle(cam, x0, y0, x1, y1, x2, y2, own, xy);
+            }
+            uint32_t* pl = planes + plane * plane_words;
+            if (kind == kVerts) {
+                if ((unsigned)xy[0] < (unsigned)res && (unsigned)xy[1] < (unsigned)res) or_bit(pl, res, xy[0], xy[1]);
+                if ((xy[2] != xy[0] || xy[3] != xy[1]) && (unsigned)xy[2] < (unsigned)res && (unsigned)xy[3] < (unsigned)res)
+                    or_bit(pl, res, xy[2], xy[3]);
+                if ((xy[4] != xy[0] || xy[5] != xy[1]) && (xy[4] != xy[2] || xy[5] != xy[3]) &&
+                    (unsigned)xy[4] < (unsigned)res && (unsigned)xy[5] < (unsigned)res)
+                    or_bit(pl, res, xy[4], xy[5]);
+            } else if (kind == kHuge) {
+                draw_huge(pl, res, xy);
+            }
+            // queue the general faces (warp-aggregated append)
+            const unsigned mg = __ballot_sync(0xffffffffu, kind == kGeneral);
+            int qbase = nq;
+            if (G != 32) {
+                if (lane == 0 && mg) qbase = atomicAdd(&s_cnt[0], __popc(mg));
+                qbase = __shfl_sync(0xffffffffu, qbase, 0);
+            }
+            if (kind == kGeneral) {
+                const int pos = qbase + __popc(mg & ((1u << lane) - 1));
+                queue[pos] = make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
+                                        (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
+                                        (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
+            }
+            group_sync<G>();
+            if (G == 32) nq += __popc(mg);
+            else nq = s_cnt[0];
+            const bool last = c0 + G >= total;
+            if (nq >= G || (last && nq > 0)) {
+                // stage 2 on the newest min(nq, G) entries... (a full group unless this is the tail)
+                const int take = min(nq, G);
+                if (tid < take) {
+                    const uint4 q = queue[nq - take + tid];
+                    draw_rows<RES>(planes + (int)q.w * plane_words, res, s_rcp,
+                                   (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff), (int32_t)q.y >> 16,
+                                   (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
+                }
+                nq -= take;
+                group_sync<G>();
+                if (G != 32) {
+                    if (tid == 0) s_cnt[0] = nq;
+                    group_sync<G>();
+                }
+                if (last && nq > 0) {               // only when the tail left more than G entries (G != 32 cannot; G == 32: nq < G)
+                    if (tid < nq) {
+                        const uint4 q = queue[tid];
+                        draw_rows<RES>(planes + (int)q.w * plane_words, res, s_rcp,
+                                       (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff), (int32_t)q.y >> 16,
+                                       (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
                     }
-                    const unsigned below = (1u << lane) - 1;
-                    int pos = -1;
-                    if (kind == 1) pos = base_t + __popc(mt & below);
-                    else if (kind == 3) pos = kQueue - 1 - (base_g + __popc(mg & below));
-                    if (pos >= 0) { queue[pos] = it.a; queue[kQueue + pos] = it.b; queue[2 * kQueue + pos] = it.c; }
+                    nq = 0;
                 }
             }
-            // lanes that ran fewer rounds missed the last ballots: take the counts of the lane that ran them all
-            if (G == 32) { n_thin_w = __shfl_sync(0xffffffffu, n_thin_w, 0); n_gen_w = __shfl_sync(0xffffffffu, n_gen_w, 0); }
-            group_sync<G>();
-            const int n_thin = G == 32 ? n_thin_w : s_cnt[0], n_gen = G == 32 ? n_gen_w : s_cnt[1];
-            for (int k = tid; k < n_thin; k += G) {
-                Item q;
-                q.a = queue[k]; q.b = queue[kQueue + k]; q.c = queue[2 * kQueue + k];
-                draw_item_thin(img, res, val, q);
-            }
-            for (int k = kQueue - 1 - tid; k >= kQueue - n_gen; k -= G) {
-                Item q;
-                q.a = queue[k]; q.b = queue[kQueue + k]; q.c = queue[2 * kQueue + k];
-                draw_item(img, res, val, q);
-            }
-            group_sync<G>();
-            if (G == 32) {
-                n_thin_w = 0; n_gen_w = 0;
-            } else {
-                if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-                group_sync<G>();
-            }
         }
-    }
-    group_sync<G>();
+        group_sync<G>();
 
-    // ---- expand the tile through the colour LUT: out[cam][ch][x][y], 4 pixels per 128-bit store
-#ifdef TDS_EXP_NOOUT
-    if (img[tid] != 77) return;
-#endif
-    const int nquad = tile_bytes / 4;
-    float* outc = a.out + (int64_t)camid * 3 * tile_bytes;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(img);
-    for (int i = tid; i < nquad; i += G) {
-        const uint32_t v = w[i];
-        const int k0 = (v & 255u) * 3, k1 = ((v >> 8) & 255u) * 3, k2 = ((v >> 16) & 255u) * 3, k3 = (v >> 24) * 3;
+        // ---- resolve painter's order and expand through the colour LUT: out[cam][ch][x][y].
+        // A thread owns 4 image rows y of one 32-pixel word column: it folds the K planes of those rows into bit
+        // slices of the top-most draw rank (registers), then walks the 32 columns, one 128-bit store per channel.
+        float* outc = a.out + (int64_t)camid * 3 * res * res;
+        const int nyq = res >> 2;
+        for (int item = tid; item < W32 * nyq; item += G) {
+            const int w = item / nyq, yq = item - w * nyq;
+            uint32_t sl[NS][4];
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const float4 o = make_float4(s_lut[k0 + ch], s_lut[k1 + ch], s_lut[k2 + ch], s_lut[k3 + ch]);
-            tds::st_cs_f4(reinterpret_cast<float4*>(outc + (int64_t)ch * tile_bytes) + i, o);
+            for (int s = 0; s < NS; s++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) sl[s][k] = 0u;
+            uint32_t rem[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll 1
+            for (int p = K - 1; p >= 0; p--) {          // last drawn = on top
+                const uint4 v = *reinterpret_cast<const uint4*>(planes + p * plane_words + w * res + 4 * yq);
+                const uint32_t pw[4] = {v.x, v.y, v.z, v.w};
+                const int id = p + 1;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t e = pw[k] & rem[k];
+                    rem[k] &= ~e;
+#pragma unroll
+                    for (int s = 0; s < NS; s++) sl[s][k] |= ((id >> s) & 1) ? e : 0u;
+                }
+            }
+            const int nx = min(32, res - 32 * w);
+            float* o = outc + (int64_t)(32 * w) * res + 4 * yq;
+            const int plane_stride = res * res;
+#pragma unroll 1
+            for (int x = 0; x < nx; x++) {
+                float4 c[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t v = sl[0][k] & 1u;
+#pragma unroll
+                    for (int s = 1; s < NS; s++) v |= (sl[s][k] & 1u) << s;
+#pragma unroll
+                    for (int s = 0; s < NS; s++) sl[s][k] >>= 1;
+                    c[k] = s_lut[v];
+                }
+                tds::st_cs_f4(reinterpret_cast<float4*>(o), make_float4(c[0].x, c[1].x, c[2].x, c[3].x));
+                tds::st_cs_f4(reinterpret_cast<float4*>(o + plane_stride), make_float4(c[0].y, c[1].y, c[2].y, c[3].y));
+                tds::st_cs_f4(reinterpret_cast<float4*>(o + 2 * plane_stride), make_float4(c[0].z, c[1].z, c[2].z, c[3].z));
+                o += res;
+            }
         }
     }
 }
@@ -606,20 +644,34 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     const int64_t ncam = (int64_t)B * Nc;
     TDS_REQUIRE(ncam <= 2147483647LL, "raster: too many cameras");
     a.ncam = (int32_t)ncam;
-    auto launch = [&](auto kernel, int groups, int threads, int queue_items) -> int {
-        const size_t group_bytes = (size_t)res * res + (size_t)queue_items * 12 + kGroupExtra;
-        const size_t smem = group_bytes * groups;
-        TDS_REQUIRE(smem <= 227 * 1024, "raster: res=%d needs %zu bytes of shared memory", res, smem);
+    const int K = pal.n_classes;
+    TDS_REQUIRE(K <= 31, "raster: at most 31 active classes (got %d)", K);
+    const int sms = tds::sm_count();
+    auto launch = [&](auto kernel, int groups, int threads) -> int {
+        const size_t rcp_bytes = (((size_t)res + 1) * 4 + 15) & ~(size_t)15;
+        const size_t smem = rcp_bytes + (size_t)raster_group_bytes(res, K, threads / groups) * groups;
+        TDS_REQUIRE(smem <= 227 * 1024, "raster: res=%d with %d active classes needs %zu bytes of shared memory", res, K, smem);
         if (smem > 40 * 1024) TDS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)((ncam + groups - 1) / groups);
+        int per_sm = 0;
+        TDS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+        TDS_REQUIRE(per_sm >= 1, "raster: kernel does not fit an SM (res=%d, %d classes)", res, K);
+        // persistent grid: every resident CTA slot of the GPU, cameras dealt round-robin
+        const int64_t want = (ncam + groups - 1) / groups;
+        const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per_sm);
         if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
         kernel<<<grid, threads, smem, st>>>(set, a, pal);
         if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
         TDS_LAUNCH_OK();
         return TDS_OK;
     };
-    if (res == 64) return launch(raster_kernel<32, 64>, 4, 128, QCfg<32>::total);
-    if (res < 64) return launch(raster_kernel<32, 0>, 4, 128, QCfg<32>::total);
-    if (res <= 128) return launch(raster_kernel<256, 0>, 1, 256, QCfg<256>::total);
-    return launch(raster_kernel<512, 0>, 1, 512, QCfg<512>::total);
+    if (K <= 7) {
+        if (res == 64) return launch(raster_kernel<32, 64, 3>, 4, 128);
+        if (res < 64) return launch(raster_kernel<32, 0, 3>, 4, 128);
+        if (res <= 128) return launch(raster_kernel<256, 0, 3>, 1, 256);
+        return launch(raster_kernel<512, 0, 3>, 1, 512);
+    }
+    if (res == 64) return launch(raster_kernel<32, 64, 5>, 4, 128);
+    if (res < 64) return launch(raster_kernel<32, 0, 5>, 4, 128);
+    if (res <= 128) return launch(raster_kernel<256, 0, 5>, 1, 256);
+    return launch(raster_kernel<512, 0, 5>, 1, 512);
 }

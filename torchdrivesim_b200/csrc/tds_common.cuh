@@ -14,6 +14,7 @@ namespace tds {
 
 std::string& last_error();
 int fail(int code, const char* fmt, ...);
+int sm_count();
 
 #define TDS_REQUIRE(cond, ...)                                            \
     do {                                                                  \

@@ -10,10 +10,10 @@ constexpr int kMaxRasterRows = 64;  // grid rows a single camera may touch
 struct MapDev {
     // ---- raster grid: triangles binned by the cell of each VERTEX (the reference keeps a face
     // iff any vertex is inside the view quad, mesh.py:311-313).  A record is two float4:
-    //   (x0, y0, x1, y1), (x2, y2, own_bits, unused); own bit i set = vertex i lies in this cell.
-    // Records are sorted by (slot, cell row-major) so one grid row is one contiguous range.
+    //   (x0, y0, x1, y1), (x2, y2, meta, unused); meta = own_bits | class << 8, own bit i set = vertex i lies
+    //   in this cell.  Records are sorted by cell (row-major), so one grid row is one contiguous range.
     const float4* rec;
-    const int32_t* rcell;           // [n_slots * rgx * rgy + 1] CSR offsets into rec (in records)
+    const int32_t* rcell;           // [rgx * rgy + 1] CSR offsets into rec (in records)
     float rx0, ry0, rcs, rinv;
     int32_t rgx, rgy, n_slots;
     int32_t slot_of_class[TDS_MAX_CLASSES];   // -1: the map has no face of that class

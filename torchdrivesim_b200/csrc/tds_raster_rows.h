@@ -1,0 +1,174 @@
+// Row-run form of the reference's triangle coverage rule (cv2.fillConvexPoly on int32 vertices,
+// torchdrivesim/rendering/cv2.py:59): for ONE image row y the covered pixels of a triangle are the union
+// of at most four intervals of columns —
+//   * the 16.16 fixed-point fill span of that row (rows [y_top, y_bottom - 1]);
+//   * for each of the three outline edges, the run of its 8-connected LineIterator segment in that row.
+// The raster kernel keeps one bit per pixel and class, so a row of a triangle is a handful of integer
+// operations and one atomic OR instead of a loop over pixels; painter's order is resolved once at the end.
+//
+// Closed form of the LineIterator runs (left-to-right Bresenham with err0 = dx - 2 dy, see draw_line8 in
+// tds_raster_tri.h).  After clipping and ordering the endpoints left to right, with dx = rx - lx >= 0,
+// dy = |ry - ly| and r = |y - ly| the row offset from the LEFT endpoint:
+//   x-major (dy <= dx): pixel i (x = lx + i) lies in row offset k_i = floor((2 dy i + dx - 1) / (2 dx)), hence
+//       row r holds i in [G(r), G(r+1) - 1],  G(0) = 0,  G(r) = floor((2 dx r - dx + 2 dy) / (2 dy)) for
+//       1 <= r <= dy,  G(dy + 1) = dx + 1;
+//   y-major (dy >  dx): row r holds the single pixel x = lx + floor((2 dx r + dy - 1) / (2 dy)).
+// Both divide by 2 dy: one multiply-high with rcp = ceil(2^32 / (2 dy)) is exact while numerator * 2 dy < 2^32,
+// i.e. for images up to 1024 pixels (clipped endpoints lie inside the image).
+//
+// Host/device code: tests/test_raster_rule.py checks exactly these functions against the live cv2 module.
+#pragma once
+#include "tds_raster_tri.h"
+
+namespace tds {
+
+TDS_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((unsigned long long)a * b) >> 32);
+#endif
+}
+
+// ceil(2^32 / (2 dy)) for dy >= 1 (2 dy >= 2, so the result fits 32 bits)
+TDS_HD uint32_t row_rcp(int dy) { return dy > 0 ? 0xffffffffu / (uint32_t)(2 * dy) + 1u : 0u; }
+
+// One outline edge in row-evaluable form.  Walked by increasing y: t = y - ylo in [0, dy].
+struct RowEdge {
+    int lx;          // column of the left endpoint
+    int ylo, yhi;    // rows covered (yhi < ylo: the edge was rejected by clipLine)
+    int n;           // numerator of the row that is evaluated next (advances by b1 per row)
+    int b1;          // +-2 dx (sign = direction of r as y grows)
+    int cur;         // x-major: boundary G(.) shared with the previous row
+    int gend;        // x-major: boundary after the last row (dx + 1 walking away from the left endpoint, else 0)
+    uint32_t rcp;
+    int xmajor;
+};
+
+// (xa,ya) -> (xb,yb) in the reference's drawing order (clipLine is not symmetric in its endpoints)
+template <class RcpFn>
+TDS_HD void row_edge_setup(int W, int H, int xa, int ya, int xb, int yb, RowEdge& e, RcpFn&& rcp_of) {
+    if ((unsigned)xa >= (unsigned)W || (unsigned)xb >= (unsigned)W ||
+        (unsigned)ya >= (unsigned)H || (unsigned)yb >= (unsigned)H) {
+        if (!clip_line32(W, H, xa, ya, xb, yb)) { e.ylo = 1; e.yhi = 0; e.lx = 0; e.n = 0; e.b1 = 0; e.cur = 0; e.gend = 0; e.rcp = 0; e.xmajor = 1; return; }
+    }
+    int dx = xb - xa, dy = yb - ya, lx = xa, ly = ya;
+    if (dx < 0) { dx = -dx; dy = -dy; lx = xb; ly = yb; }
+    const bool down = dy >= 0;           // r grows with y
+    if (dy < 0) dy = -dy;
+    e.lx = lx;
+    e.ylo = down ? ly : ly - dy;
+    e.yhi = down ? ly + dy : ly;
+    e.xmajor = dx >= dy;
+    e.rcp = rcp_of(dy);
+    const int a1 = 2 * dx;
+    if (e.xmajor) {
+        // boundary between row offsets r-1 and r: G(r) = mulhi(a1 r + (2 dy - dx), rcp), 1 <= r <= dy.
+        // Walking y upwards: down -> rows r = 0,1,..: row t needs G(t) (cur) and G(t+1) (next, from n);
+        //                    up   -> rows r = dy,dy-1,..: row t needs G(r+1) (cur) and G(r) (next, from n).
+        const int a0 = 2 * dy - dx;
+        e.cur = down ? 0 : dx + 1;
+        e.gend = down ? dx + 1 : 0;
+        e.n = down ? a1 + a0 : a1 * dy + a0;
+        e.b1 = down ? a1 : -a1;
+    } else {
+        const int a0 = dy - 1;
+        e.cur = 0; e.gend = 0;
+        e.n = down ? a0 : a1 * dy + a0;
+        e.b1 = down ? a1 : -a1;
+    }
+}
+
+// Run [lo, hi] of the edge in row y (ylo <= y <= yhi; rows must be visited in increasing order, each once).
+TDS_HD void row_edge_step(RowEdge& e, int y, int& lo, int& hi) {
+    const int q = (int)mulhi_u32((uint32_t)e.n, e.rcp);
+    e.n += e.b1;
+    if (e.xmajor) {
+        const int nxt = y == e.yhi ? e.gend : q;
+        const int a = e.cur < nxt ? e.cur : nxt, b = e.cur < nxt ? nxt : e.cur;
+        lo = e.lx + a;
+        hi = e.lx + b - 1;
+        e.cur = nxt;
+    } else {
+        lo = hi = e.lx + q;
+    }
+}
+
+// Fixed-point fill (FillConvexPoly): rows [fylo, fyhi], vertices sorted by y exactly as draw_triangle does.
+struct RowFill {
+    int fylo, fyhi;       // fyhi < fylo: nothing to fill
+    int my;
+    int xa, dTB;          // long edge T->B, evaluated incrementally
+    int xT, dTM, xM, dMB; // short edges: x = xT + (y - ty) dTM above my, xM + (y - my) dMB from my on
+    int ty;
+};
+
+TDS_HD void row_fill_setup(int W, int H, int x0, int y0, int x1, int y1, int x2, int y2, RowFill& f) {
+    int tx = x0, ty = y0, mx = x1, my = y1, bx = x2, by = y2, t;
+    if (my < ty) { t = tx; tx = mx; mx = t; t = ty; ty = my; my = t; }
+    if (by < my) { t = mx; mx = bx; bx = t; t = my; my = by; by = t; }
+    if (my < ty) { t = tx; tx = mx; mx = t; t = ty; ty = my; my = t; }
+    int xmin = x0 < x1 ? x0 : x1; xmin = xmin < x2 ? xmin : x2;
+    int xmax = x0 > x1 ? x0 : x1; xmax = xmax > x2 ? xmax : x2;
+    f.fylo = 1; f.fyhi = 0;
+    f.my = my; f.ty = ty; f.xa = 0; f.dTB = 0; f.xT = 0; f.dTM = 0; f.xM = 0; f.dMB = 0;
+    if (xmax < 0 || by < 0 || xmin >= W || ty >= H) return;   // bounding box misses the image: outline only
+    if (by == ty) return;                                     // no fill rows
+    const int ylo = ty > 0 ? ty : 0;
+    const int yhi = (by - 1) < (H - 1) ? (by - 1) : (H - 1);
+    if (ylo > yhi) return;
+    f.fylo = ylo; f.fyhi = yhi;
+    f.dTB = edge_dx<int>(tx, ty, bx, by);
+    f.dTM = my > ty ? edge_dx<int>(tx, ty, mx, my) : 0;
+    f.dMB = by > my ? edge_dx<int>(mx, my, bx, by) : 0;
+    f.xT = tx << 16;
+    f.xM = mx << 16;
+    f.xa = (tx << 16) + (ylo - ty) * f.dTB;
+}
+
+// Span of row y (fylo <= y <= fyhi, increasing order); returns false when the span misses the image.
+TDS_HD bool row_fill_step(RowFill& f, int W, int y, int& lo, int& hi) {
+    const int xb = y < f.my ? f.xT + (y - f.ty) * f.dTM : f.xM + (y - f.my) * f.dMB;
+    const int xa = f.xa;
+    f.xa += f.dTB;
+    const int xl = xa < xb ? xa : xb, xr = xa < xb ? xb : xa;
+    int c1 = (xl + 32768) >> 16, c2 = (xr + 32768) >> 16;
+    if (c2 < 0 || c1 >= W) return false;
+    lo = c1 < 0 ? 0 : c1;
+    hi = c2 >= W ? W - 1 : c2;
+    return true;
+}
+
+struct RowTri {
+    RowEdge e[3];
+    RowFill f;
+    int ylo, yhi;     // rows of the image that any part of the triangle can touch
+};
+
+// Valid for |coordinates| < 8192 (32-bit clipLine and slopes), like draw_triangle_fast.
+template <class RcpFn>
+TDS_HD void row_tri_setup(int W, int H, int x0, int y0, int x1, int y1, int x2, int y2, RowTri& t, RcpFn&& rcp_of) {
+    // outline v2->v0, v0->v1, v1->v2
+    row_edge_setup(W, H, x2, y2, x0, y0, t.e[0], rcp_of);
+    row_edge_setup(W, H, x0, y0, x1, y1, t.e[1], rcp_of);
+    row_edge_setup(W, H, x1, y1, x2, y2, t.e[2], rcp_of);
+    row_fill_setup(W, H, x0, y0, x1, y1, x2, y2, t.f);
+    int ymin = y0 < y1 ? y0 : y1; ymin = ymin < y2 ? ymin : y2;
+    int ymax = y0 > y1 ? y0 : y1; ymax = ymax > y2 ? ymax : y2;
+    t.ylo = ymin > 0 ? ymin : 0;
+    t.yhi = ymax < H - 1 ? ymax : H - 1;
+}
+
+// emit(lo, hi) for every interval of row y; rows must be visited from t.ylo to t.yhi in order.
+template <class Emit>
+TDS_HD void row_tri_step(RowTri& t, int W, int y, Emit&& emit) {
+    int lo, hi;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; k++)
+        if (y >= t.e[k].ylo && y <= t.e[k].yhi) { row_edge_step(t.e[k], y, lo, hi); emit(lo, hi); }
+    if (y >= t.f.fylo && y <= t.f.fyhi && row_fill_step(t.f, W, y, lo, hi)) emit(lo, hi);
+}
+
+}  // namespace tds
