@@ -14,7 +14,7 @@ def main(path, top=40):
     rows = list(csv.reader(open(path)))
     hdr, cur_file, data = None, None, []
     for r in rows:
-        if len(r) >= 2 and r[0] == "File Name":
+        if len(r) >= 2 and r[0] == "File Path":
             cur_file = r[1]
             continue
         if r and r[0] == "Line No":

@@ -36,3 +36,18 @@ extern "C" void tds_host_draw_triangle_rows(uint8_t* img, int W, int H, const in
             for (int x = lo; x <= hi; x++) img[y * W + x] = 1;
         });
 }
+
+// fast path of the bitplane kernel: all vertices inside the image, one interval per row.
+// small != 0 uses the reciprocal-table slopes (images up to 128 pixels).
+extern "C" int tds_host_draw_triangle_inside(uint8_t* img, int W, int H, const int32_t* p, int small) {
+    for (int k = 0; k < 6; k++) if (p[k] < 0 || p[k] >= ((k & 1) ? H : W)) return 0;
+    tds::FastTri t;
+    auto rcp = [](int dy) { return tds::row_rcp(dy); };
+    if (small) tds::fast_tri_setup<true>(p[0], p[1], p[2], p[3], p[4], p[5], t, rcp);
+    else tds::fast_tri_setup<false>(p[0], p[1], p[2], p[3], p[4], p[5], t, rcp);
+    tds::fast_tri_rows(t, [&](int y, int lo, int hi) {
+        if (lo < 0 || hi >= W || lo > hi || y < 0 || y >= H) { img[0] = 99; return; }
+        for (int x = lo; x <= hi; x++) img[y * W + x] = 1;
+    });
+    return 1;
+}

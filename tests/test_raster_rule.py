@@ -88,6 +88,30 @@ def test_kernel_rule_row_runs_match_cv2(host_rule, res):
         assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
 
 
+@pytest.mark.parametrize("res,small", [(8, 1), (64, 1), (128, 1), (64, 0), (256, 0), (448, 0)])
+def test_kernel_rule_inside_fast_path_matches_cv2(host_rule, res, small):
+    """Triangles with all vertices inside the image: one interval per row (tds_raster_rows.h, FastTri)."""
+    rng = np.random.default_rng(res + 5 + small)
+    n = 0
+    for k in range(30000):
+        mode = k % 4
+        if mode == 0:
+            pts = rng.integers(0, res, (3, 2))
+        elif mode == 1:
+            pts = rng.integers(0, res, (1, 2)) + rng.integers(-8, 9, (3, 2))
+        elif mode == 2:
+            pts = rng.integers(0, res, (1, 2)) + np.stack([rng.integers(-res, res, 3), rng.integers(-2, 3, 3)], 1)
+        else:
+            pts = rng.integers(0, res, (1, 2)) + np.stack([rng.integers(-2, 3, 3), rng.integers(-res, res, 3)], 1)
+        pts = np.ascontiguousarray(pts.clip(0, res - 1), np.int32)
+        m = np.zeros((res, res), np.uint8)
+        n += host_rule.tds_host_draw_triangle_inside(m.ctypes.data_as(ctypes.c_void_p), res, res,
+                                                     pts.ctypes.data_as(ctypes.c_void_p), small)
+        assert m.max() <= 1, pts.tolist()
+        assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
+    assert n == 30000
+
+
 def test_degenerate_and_collinear():
     for pts in ([[5, 5], [5, 5], [5, 5]], [[0, 0], [10, 10], [20, 20]], [[3, 7], [3, 7], [9, 7]], [[-5, -5], [-1, -1], [-3, -9]]):
         pts = np.array(pts, np.int32)

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(128) dyn_prep_kernel(int B, int N, int L, int 
 struct Camera {
     float ncx, ncy;            // -camera position
     float S, C, scale, fmin, half;
+    float kscale;              // -(scale * res / 2), exact for power-of-two res
+    float r_in, r_out;         // max-norm radii (pixels) deciding "inside / outside the 1.05x quad" away from its boundary
     const float* edges;        // view-quad edge functions a[4], b[4], c[4] (utils.py:99-122), in shared memory
     int res;
 };
@@ -124,6 +126,11 @@ __device__ __forceinline__ void make_camera(Camera& cam, float cx, float cy, flo
     cam.ncx = -cx; cam.ncy = -cy; cam.S = S; cam.C = C; cam.scale = scale; cam.res = res;
     cam.fmin = (float)res;
     cam.half = (float)res / 2.0f;
+    cam.kscale = -(scale * cam.half);
+    // fp32 disagreement between the pixel-space and the edge-function test is < 1e-4 m; band = 0.01 px + 2e-3 m
+    const float band = 0.01f + 0.002f * (scale * cam.half);
+    cam.r_in = 0.525f * cam.fmin - band;
+    cam.r_out = 0.525f * cam.fmin + band;
     // rendering/cv2.py:34-40 with base.py:117-130 (cameras.xy is zero after the translate)
     const float cxs[4] = {0.f, 0.f, (float)res, (float)res};
     const float cys[4] = {0.f, (float)res, (float)res, 0.f};
@@ -164,69 +171,75 @@ __device__ __forceinline__ bool inside_quad(const Camera& cam, float x, float y)
 
 // ---- stage 1: cull (mesh.py:311-313) + project one world-space triangle --------------------------
 // Pixel-space shortcut for the cull: the 1.05x view quad is the image square scaled by 1.05 about its
-// centre, i.e. pixel coordinates in [-0.025 res, 1.025 res].  A projected vertex further than ~0.01 px from
-// that boundary is decided from its pixel coordinates; the thin band around the boundary falls back to
-// the reference's fp32 edge functions, so the decision is always the reference's.
-__device__ __forceinline__ int classify(float u, float v, float mid, float r_in, float r_out) {
-    // 1 inside, 0 outside, -1 undecided: the quad is the max-norm ball of radius 1.05 res / 2 around the image centre
-    const float d = fmaxf(fabsf(u - mid), fabsf(v - mid));
-    return d < r_in ? 1 : (d > r_out ? 0 : -1);        // NaN falls through to "undecided"
-}
-
+// centre, i.e. the max-norm ball of radius 0.525 res around the image centre in pixel coordinates.  A
+// projected vertex further than ~0.01 px from that boundary is decided from its pixel coordinates; the
+// thin band around the boundary falls back to the reference's fp32 edge functions, so the decision is
+// always the reference's.
+template <bool POW2>
 __device__ __forceinline__ void project_f(const Camera& cam, float x, float y, float& u0, float& u1) {
     u0 = cam.C * x + cam.S * y;
     u1 = (-cam.S) * x + cam.C * y;
-    u0 = (-u0) * cam.scale; u1 = (-u1) * cam.scale;
-    u0 = u0 * cam.fmin;     u1 = u1 * cam.fmin;
-    u0 = u0 / 2.0f;         u1 = u1 / 2.0f;
-    u0 = u0 + cam.half;     u1 = u1 + cam.half;
+    if (POW2) {
+        // res is a power of two: the multiplications by res and by 1/2 are exact, so they commute with the
+        // rounding of (-u) * scale and fold into one constant (bit-identical to the chain below)
+        u0 = u0 * cam.kscale + cam.half;
+        u1 = u1 * cam.kscale + cam.half;
+    } else {
+        u0 = (-u0) * cam.scale; u1 = (-u1) * cam.scale;     // rendering/base.py:102-115, operation by operation
+        u0 = u0 * cam.fmin;     u1 = u1 * cam.fmin;
+        u0 = u0 / 2.0f;         u1 = u1 / 2.0f;
+        u0 = u0 + cam.half;     u1 = u1 + cam.half;
+    }
 }
 
 // kind of a candidate after cull + projection + truncation (rendering/cv2.py:52-56)
-enum { kCulled = 0, kVerts = 1, kGeneral = 2, kHuge = 3 };
+enum { kCulled = 0, kVerts = 1, kHuge = 2, kShort = 3, kTall = 4, kClipped = 5 };
+constexpr int kShortRows = 5;      // inside triangles spanning at most this many row steps go to the "short" queue
 
+template <bool POW2>
 __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float y0, float x1, float y1, float x2,
                                               float y2, int own, int xy[6]) {
     const float px0 = x0 + cam.ncx, py0 = y0 + cam.ncy;
     const float px1 = x1 + cam.ncx, py1 = y1 + cam.ncy;
     const float px2 = x2 + cam.ncx, py2 = y2 + cam.ncy;
     float u0, v0, u1, v1, u2, v2;
-    project_f(cam, px0, py0, u0, v0);
-    project_f(cam, px1, py1, u1, v1);
-    project_f(cam, px2, py2, u2, v2);
-    // fp32 disagreement between the pixel-space and the edge-function test is < 1e-4 m; band = 0.01 px + 2e-3 m
-    const float band = 0.01f + 0.002f * (cam.scale * cam.half);
-    const float r_in = 0.525f * cam.fmin - band, r_out = 0.525f * cam.fmin + band;
-    int c0 = classify(u0, v0, cam.half, r_in, r_out), c1 = classify(u1, v1, cam.half, r_in, r_out),
-        c2 = classify(u2, v2, cam.half, r_in, r_out);
-    if ((c0 | c1 | c2) < 0) {       // some vertex is within the band around the quad boundary (or NaN): exact test
+    project_f<POW2>(cam, px0, py0, u0, v0);
+    project_f<POW2>(cam, px1, py1, u1, v1);
+    project_f<POW2>(cam, px2, py2, u2, v2);
+    const float d0 = fmaxf(fabsf(u0 - cam.half), fabsf(v0 - cam.half));
+    const float d1 = fmaxf(fabsf(u1 - cam.half), fabsf(v1 - cam.half));
+    const float d2 = fmaxf(fabsf(u2 - cam.half), fabsf(v2 - cam.half));
+    if (fminf(fminf(d0, d1), d2) > cam.r_out) return kCulled;       // all vertices clearly outside (NaN: falls through)
+    bool c0 = d0 < cam.r_in, c1 = d1 < cam.r_in, c2 = d2 < cam.r_in;
+    const bool und0 = !c0 && !(d0 > cam.r_out), und1 = !c1 && !(d1 > cam.r_out), und2 = !c2 && !(d2 > cam.r_out);
+    if (und0 | und1 | und2) {       // some vertex is within the band around the quad boundary (or NaN): exact test
         // one rolled loop over the three vertices keeps this rare path small; the edge functions live in smem
         float ex = px0, ey = py0;
 #pragma unroll 1
         for (int k = 0; k < 3; k++) {
-            const int r = inside_quad(cam, ex, ey) ? 1 : 0;
-            if (k == 0) { if (c0 < 0) c0 = r; ex = px1; ey = py1; }
-            else if (k == 1) { if (c1 < 0) c1 = r; ex = px2; ey = py2; }
-            else { if (c2 < 0) c2 = r; }
+            const bool r = inside_quad(cam, ex, ey);
+            if (k == 0) { if (und0) c0 = r; ex = px1; ey = py1; }
+            else if (k == 1) { if (und1) c1 = r; ex = px2; ey = py2; }
+            else { if (und2) c2 = r; }
         }
+        if (!(c0 | c1 | c2)) return kCulled;
     }
-    if (!(c0 | c1 | c2)) return kCulled;
     const int first = c0 ? 0 : (c1 ? 1 : 2);
     if (!((own >> first) & 1)) return kCulled;    // another cell's copy of this face draws it
     xy[0] = __float2int_rz(u0); xy[1] = __float2int_rz(v0);
     xy[2] = __float2int_rz(u1); xy[3] = __float2int_rz(v1);
     xy[4] = __float2int_rz(u2); xy[5] = __float2int_rz(v2);
-    int big = 0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) big |= (xy[k] <= -8192) | (xy[k] >= 8192);
-    if (big) return kHuge;
+    // |coordinates| >= 8000 (or NaN): 64-bit rule
+    if (!(fmaxf(fmaxf(d0, d1), d2) < 8000.0f - cam.half)) return kHuge;
     // integer bounding box entirely off the image: clipLine rejects all three edges and the fill returns early
     const int res = cam.res;
     const int xmin = min(min(xy[0], xy[2]), xy[4]), xmax = max(max(xy[0], xy[2]), xy[4]);
     const int ymin = min(min(xy[1], xy[3]), xy[5]), ymax = max(max(xy[1], xy[3]), xy[5]);
-    if (xmax < 0 || ymax < 0 || xmin >= res || ymin >= res) return kCulled;
+    if (((xmax | ymax) < 0) | (xmin >= res) | (ymin >= res)) return kCulled;
     // bounding box within 2x2 pixels: the coverage is the set of in-image vertices (tds_raster_tri.h)
-    return ((xmax - xmin <= 1) & (ymax - ymin <= 1)) ? kVerts : kGeneral;
+    if (((xmax - xmin) | (ymax - ymin)) <= 1) return kVerts;
+    const bool inside = ((xmin | ymin) >= 0) & (xmax < res) & (ymax < res);
+    return !inside ? kClipped : (ymax - ymin <= kShortRows ? kShort : kTall);
 }
 
 // ---- bitplanes: one bit per pixel and draw rank; plane p, word column w, row y at  p * res * W32 + w * res + y
@@ -241,10 +254,28 @@ __device__ __forceinline__ void or_span(uint32_t* plane, int res, int y, int lo,
     }
 }
 
-// stage 2: all rows of one triangle (|coordinates| < 8192), one atomic OR per row and 32-pixel word
+__device__ __forceinline__ void or_mask64(uint32_t* plane, int y, unsigned long long m) {
+    const uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
+    if (m0) atomicOr(plane + y, m0);
+    if (m1) atomicOr(plane + 64 + y, m1);
+}
+
+// stage 2a: a triangle with all vertices inside the image: one interval and one atomic OR per row and word
+template <int RES, bool SMALL>
+__device__ __forceinline__ void draw_inside(uint32_t* plane, int res, const uint32_t* s_rcp, int x0, int y0, int x1, int y1,
+                                            int x2, int y2) {
+    tds::FastTri t;
+    tds::fast_tri_setup<SMALL>(x0, y0, x1, y1, x2, y2, t, [&](int dy) { return s_rcp[dy]; });
+    tds::fast_tri_rows(t, [&](int y, int lo, int hi) {
+        if (RES == 64) or_mask64(plane, y, (~0ull >> (63 - (hi - lo))) << lo);
+        else or_span(plane, res, y, lo, hi);
+    });
+}
+
+// stage 2b: a triangle that crosses the image border (|coordinates| < 8192): clipped outline runs + clamped spans
 template <int RES>
-__device__ __forceinline__ void draw_rows(uint32_t* plane, int res, const uint32_t* s_rcp, int x0, int y0, int x1, int y1,
-                                          int x2, int y2) {
+__device__ __forceinline__ void draw_clipped(uint32_t* plane, int res, const uint32_t* s_rcp, int x0, int y0, int x1, int y1,
+                                             int x2, int y2) {
     tds::RowTri t;
     tds::row_tri_setup(res, res, x0, y0, x1, y1, x2, y2, t, [&](int dy) { return s_rcp[dy]; });
 #pragma unroll 1
@@ -252,16 +283,14 @@ __device__ __forceinline__ void draw_rows(uint32_t* plane, int res, const uint32
         if (RES == 64) {
             unsigned long long m = 0ull;
             tds::row_tri_step(t, res, y, [&](int lo, int hi) { m |= (~0ull >> (63 - (hi - lo))) << lo; });
-            const uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
-            if (m0) atomicOr(plane + y, m0);
-            if (m1) atomicOr(plane + 64 + y, m1);
+            or_mask64(plane, y, m);
         } else {
             tds::row_tri_step(t, res, y, [&](int lo, int hi) { or_span(plane, res, y, lo, hi); });
         }
     }
 }
 
-// coordinates beyond +-8192 pixels (extreme zoom / giant rectangles): 64-bit rule, pixel by pixel.  Rare.
+// coordinates beyond +-8000 pixels (extreme zoom / giant rectangles): 64-bit rule, pixel by pixel.  Rare.
 __device__ __noinline__ void draw_huge(uint32_t* plane, int res, const int* xy) {
     tds::draw_triangle(res, res, xy[0], xy[1], xy[2], xy[3], xy[4], xy[5],
         [&](int x, int y) { or_bit(plane, res, x, y); },
@@ -281,11 +310,12 @@ struct RasterArgs {
 };
 
 constexpr int kRows = tds::kMaxRasterRows;
+constexpr int kQueues = 3;                          // short inside, tall inside, clipped
 constexpr int kGroupExtra = kRows * 8 + 16 + 48;    // row tables, counters, view-quad edge functions
 
 __host__ __device__ inline int raster_group_bytes(int res, int n_planes, int G) {
     const int w32 = (res + 31) / 32;
-    return n_planes * res * w32 * 4 + 2 * G * 16 + kGroupExtra;
+    return n_planes * res * w32 * 4 + kQueues * 2 * G * 16 + kGroupExtra;
 }
 
 // G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras in flight per CTA, no block barriers)
@@ -305,6 +335,8 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int GROUPS = G == 32 ? 4 : 1;
     constexpr int QN = 2 * G;
+    constexpr bool SMALL = G <= 256;            // images up to 128 pixels: slopes through the reciprocal table
+    constexpr bool POW2 = RES == 64;
     const int res = RES ? RES : a.res;          // RES = 64 is compiled with constant strides
     const int W32 = RES ? RES / 32 : (res + 31) >> 5;
     const int group = G == 32 ? (threadIdx.x >> 5) : 0;
@@ -329,15 +361,15 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     for (int i = threadIdx.x; i <= res; i += blockDim.x) s_rcp[i] = tds::row_rcp(i);
     __syncthreads();
 
-    // per-group shared memory: planes | queue | row tables
+    // per-group shared memory: planes | queues | row tables
     const int plane_words = res * W32;
     const int group_bytes = raster_group_bytes(res, K, G);
     uint8_t* base = smem_raw + rcp_bytes + (size_t)group * group_bytes;
     uint32_t* planes = reinterpret_cast<uint32_t*>(base);
-    uint4* queue = reinterpret_cast<uint4*>(base + (size_t)K * plane_words * 4);          // [QN]
-    int* s_start = reinterpret_cast<int*>(queue + QN);
-    int* s_pref = s_start + kRows;                                         // exclusive prefix of the row counts
-    int* s_cnt = s_pref + kRows;                   // [0] queue fill, [1] total static candidates
+    uint4* queue = reinterpret_cast<uint4*>(base + (size_t)K * plane_words * 4);          // [kQueues][QN]
+    int* s_start = reinterpret_cast<int*>(queue + kQueues * QN);
+    int* s_count = s_start + kRows;
+    int* s_cnt = s_count + kRows;                  // queue fill levels (G > 32)
     float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
 
     // cameras are dealt round-robin to the groups of a persistent grid
@@ -350,8 +382,11 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
         const float2 csc = reinterpret_cast<const float2*>(a.cam_sc)[camid];
         group_sync<G>();                            // previous camera of this group is completely done
         make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy, s_edges, tid == 0);
-        for (int i = tid; i < K * plane_words; i += G) planes[i] = 0u;
-        if (tid == 0) s_cnt[0] = 0;
+        {
+            uint4* pz = reinterpret_cast<uint4*>(planes);
+            for (int i = tid; i < K * plane_words / 4; i += G) pz[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (tid < 4) s_cnt[tid] = 0;
+        }
 
         // ---- grid rows touched by the view quad (world coordinates), with a 5 cm safety margin
         const float margin = 0.05f;
@@ -396,116 +431,142 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 }
             }
             s_start[tid] = st;
-            s_pref[tid] = cnt;
+            s_count[tid] = cnt;
         }
         group_sync<G>();
-        if (tid == 0) {
-            int acc = 0;
-            for (int r = 0; r < nrows; r++) { const int n = s_pref[r]; s_pref[r] = acc; acc += n; }
-            s_cnt[1] = acc;
-        }
-        group_sync<G>();
-        const int total_static = s_cnt[1];
 
         const int T = a.T;
         const float* dtri = reinterpret_cast<const float*>(a.ws + (int64_t)b * ws_env_bytes(T));
         const uint8_t* dcls = reinterpret_cast<const uint8_t*>(dtri + (int64_t)T * 6);
         const uint8_t* pres = a.present ? (a.present_per_camera ? a.present + (int64_t)camid * a.N : a.present + (int64_t)b * a.N)
                                         : nullptr;
-        const int total = total_static + T;
 
-        // ---- ONE pass over the candidates.  Stage 1 (cull + project + truncate) plots the faces that are just
-        // their vertices and queues the others; whenever G faces are queued, stage 2 converts them to row runs,
-        // one face per thread, so that stage 2 always runs with full warps.
-        int row = 0;                                   // candidates are visited in increasing order
-        int nq = 0;                                    // queue fill (uniform over the group)
-        for (int c0 = 0; c0 < total; c0 += G) {
-            const int i = c0 + tid;
-            int kind = kCulled, plane = -1;
-            int xy[6];
-            if (i < total) {
-                float x0, y0, x1, y1, x2, y2;
-                int own = 7, cls;
-                if (i < total_static) {
-                    while (row + 1 < nrows && i >= s_pref[row + 1]) row++;
-                    const int idx = s_start[row] + (i - s_pref[row]);
-                    const float4 v01 = __ldg(map.rec + 2 * (int64_t)idx);
-                    const float4 v2o = __ldg(map.rec + 2 * (int64_t)idx + 1);
-                    x0 = v01.x; y0 = v01.y; x1 = v01.z; y1 = v01.w; x2 = v2o.x; y2 = v2o.y;
-                    const int meta = __float_as_int(v2o.z);
-                    own = meta & 7;
-                    cls = (meta >> 8) & 255;
-                } else {
-                    // dynamic primitives (agents, direction triangles, traffic lights, signs)
-                    int t = i - total_static;
-                    bool degenerate = false;
-                    if (t < 3 * a.N && pres && !pres[t / 3]) {
-                        // absent agent: faces * 0 -> degenerate triangle at actor vertex 0 with agent 0's class
-                        // (mesh.py:1083-1089)
-                        t = 0;
-                        degenerate = true;
+        // ---- ONE pass over the candidates: segment r < nrows = the record range of grid row r, segment nrows =
+        // the dynamic primitives of the environment.  Stage 1 (cull + project + truncate) plots the faces that are
+        // just their vertices and queues the others by kind; whenever G faces of a kind are queued, stage 2 turns
+        // them into row intervals, one face per thread, so stage 2 always runs with full warps.  The last
+        // iteration (seg > nrows) only drains the queues.
+        int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? s_count[0] : T;
+        if (nrows > 0) seg_start = s_start[0];
+        int nq0 = 0, nq1 = 0, nq2 = 0;                 // queue fill levels (uniform over the group)
+        while (true) {
+            while (j0 >= seg_count && seg <= nrows) {
+                seg++;
+                j0 = 0;
+                seg_count = seg < nrows ? s_count[seg] : (seg == nrows ? T : 0);
+                seg_start = seg < nrows ? s_start[seg] : 0;
+            }
+            const bool drain = seg > nrows;
+            if (!drain) {
+                const int j = j0 + tid;
+                j0 += G;
+                int kind = kCulled, plane = -1;
+                int xy[6];
+                if (j < seg_count) {
+                    float x0, y0, x1, y1, x2, y2;
+                    int own = 7, cls;
+                    if (seg < nrows) {
+                        const float4* rp = map.rec + 2 * (int64_t)(seg_start + j);
+                        const float4 v01 = __ldg(rp);
+                        const float4 v2o = __ldg(rp + 1);
+                        x0 = v01.x; y0 = v01.y; x1 = v01.z; y1 = v01.w; x2 = v2o.x; y2 = v2o.y;
+                        const int meta = __float_as_int(v2o.z);
+                        own = meta & 7;
+                        cls = (meta >> 8) & 255;
+                    } else {
+                        // dynamic primitives (agents, direction triangles, traffic lights, signs)
+                        int t = j;
+                        bool degenerate = false;
+                        if (t < 3 * a.N && pres && !pres[t / 3]) {
+                            // absent agent: faces * 0 -> degenerate triangle at actor vertex 0 with agent 0's class
+                            // (mesh.py:1083-1089)
+                            t = 0;
+                            degenerate = true;
+                        }
+                        cls = dcls[t];
+                        const float* p = dtri + (int64_t)t * 6;
+                        x0 = p[0]; y0 = p[1];
+                        x1 = degenerate ? x0 : p[2]; y1 = degenerate ? y0 : p[3];
+                        x2 = degenerate ? x0 : p[4]; y2 = degenerate ? y0 : p[5];
                     }
-                    cls = dcls[t];
-                    const float* p = dtri + (int64_t)t * 6;
-                    x0 = p[0]; y0 = p[1];
-                    x1 = degenerate ? x0 : p[2]; y1 = degenerate ? y0 : p[3];
-                    x2 = degenerate ? x0 : p[4]; y2 = degenerate ? y0 : p[5];
+                    plane = cls < TDS_MAX_CLASSES ? s_plane_of_class[cls] : -1;
+                    if (plane >= 0) kind = setup_triangle<POW2>(cam, x0, y0, x1, y1, x2, y2, own, xy);
                 }
-                plane = cls < TDS_MAX_CLASSES ? s_plane_of_class[cls] : -1;
-                if (plane >= 0) kind = setup_triangle(cam, x0, y0, x1, y1, x2, y2, own, xy);
+                if (kind == kVerts) {
+                    uint32_t* pl = planes + plane * plane_words;
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        if ((unsigned)xy[2 * k] < (unsigned)res && (unsigned)xy[2 * k + 1] < (unsigned)res)
+                            or_bit(pl, res, xy[2 * k], xy[2 * k + 1]);
+                } else if (kind == kHuge) {
+                    draw_huge(planes + plane * plane_words, res, xy);
+                }
+                // queue the other faces by kind (warp-aggregated append)
+                const unsigned m0 = __ballot_sync(0xffffffffu, kind == kShort), m1 = __ballot_sync(0xffffffffu, kind == kTall),
+                               m2 = __ballot_sync(0xffffffffu, kind == kClipped);
+                if (m0 | m1 | m2) {
+                    int b0 = nq0, b1 = nq1, b2 = nq2;
+                    if (G != 32) {
+                        if (lane == 0) {
+                            if (m0) b0 = atomicAdd(&s_cnt[0], __popc(m0));
+                            if (m1) b1 = atomicAdd(&s_cnt[1], __popc(m1));
+                            if (m2) b2 = atomicAdd(&s_cnt[2], __popc(m2));
+                        }
+                        b0 = __shfl_sync(0xffffffffu, b0, 0);
+                        b1 = __shfl_sync(0xffffffffu, b1, 0);
+                        b2 = __shfl_sync(0xffffffffu, b2, 0);
+                    } else {
+                        nq0 += __popc(m0); nq1 += __popc(m1); nq2 += __popc(m2);
+                    }
+                    if (kind >= kShort) {
+                        const unsigned below = (1u << lane) - 1;
+                        const int pos = kind == kShort ? b0 + __popc(m0 & below)
+                                      : (kind == kTall ? QN + b1 + __popc(m1 & below) : 2 * QN + b2 + __popc(m2 & below));
+                        queue[pos] = make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
+                                                (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
+                                                (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
+                    }
+                }
+                group_sync<G>();
+                if (G != 32) { nq0 = s_cnt[0]; nq1 = s_cnt[1]; nq2 = s_cnt[2]; }
             }
-            uint32_t* pl = planes + plane * plane_words;
-            if (kind == kVerts) {
-                if ((unsigned)xy[0] < (unsigned)res && (unsigned)xy[1] < (unsigned)res) or_bit(pl, res, xy[0], xy[1]);
-                if ((xy[2] != xy[0] || xy[3] != xy[1]) && (unsigned)xy[2] < (unsigned)res && (unsigned)xy[3] < (unsigned)res)
-                    or_bit(pl, res, xy[2], xy[3]);
-                if ((xy[4] != xy[0] || xy[5] != xy[1]) && (xy[4] != xy[2] || xy[5] != xy[3]) &&
-                    (unsigned)xy[4] < (unsigned)res && (unsigned)xy[5] < (unsigned)res)
-                    or_bit(pl, res, xy[4], xy[5]);
-            } else if (kind == kHuge) {
-                draw_huge(pl, res, xy);
+            // stage 2: a queue is drawn when it holds a full group (or, at the end, whatever is left)
+#pragma unroll 1
+            for (int which = 0; which < 2; which++) {
+                const int nq = which ? nq1 : nq0;
+                if (nq >= G || (drain && nq > 0)) {
+                    const int take = min(nq, G);
+                    if (tid < take) {
+                        const uint4 q = queue[which * QN + nq - take + tid];
+                        draw_inside<RES, SMALL>(planes + (int)q.w * plane_words, res, s_rcp,
+                                                (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
+                                                (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
+                    }
+                    if (which) nq1 -= take; else nq0 -= take;
+                    group_sync<G>();
+                    if (G != 32) {
+                        if (tid == 0) s_cnt[which] = nq - take;
+                        group_sync<G>();
+                    }
+                }
             }
-            // queue the general faces (warp-aggregated append)
-            const unsigned mg = __ballot_sync(0xffffffffu, kind == kGeneral);
-            int qbase = nq;
-            if (G != 32) {
-                if (lane == 0 && mg) qbase = atomicAdd(&s_cnt[0], __popc(mg));
-                qbase = __shfl_sync(0xffffffffu, qbase, 0);
-            }
-            if (kind == kGeneral) {
-                const int pos = qbase + __popc(mg & ((1u << lane) - 1));
-                queue[pos] = make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
-                                        (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
-                                        (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
-            }
-            group_sync<G>();
-            if (G == 32) nq += __popc(mg);
-            else nq = s_cnt[0];
-            const bool last = c0 + G >= total;
-            if (nq >= G || (last && nq > 0)) {
-                // stage 2 on the newest min(nq, G) entries... (a full group unless this is the tail)
-                const int take = min(nq, G);
+            if (nq2 >= G || (drain && nq2 > 0)) {
+                const int take = min(nq2, G);
                 if (tid < take) {
-                    const uint4 q = queue[nq - take + tid];
-                    draw_rows<RES>(planes + (int)q.w * plane_words, res, s_rcp,
-                                   (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff), (int32_t)q.y >> 16,
-                                   (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
+                    const uint4 q = queue[2 * QN + nq2 - take + tid];
+                    draw_clipped<RES>(planes + (int)q.w * plane_words, res, s_rcp,
+                                      (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
+                                      (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
                 }
-                nq -= take;
+                nq2 -= take;
                 group_sync<G>();
                 if (G != 32) {
-                    if (tid == 0) s_cnt[0] = nq;
+                    if (tid == 0) s_cnt[2] = nq2;
                     group_sync<G>();
                 }
-                if (last && nq > 0) {               // only when the tail left more than G entries (G != 32 cannot; G == 32: nq < G)
-                    if (tid < nq) {
-                        const uint4 q = queue[tid];
-                        draw_rows<RES>(planes + (int)q.w * plane_words, res, s_rcp,
-                                       (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff), (int32_t)q.y >> 16,
-                                       (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
-                    }
-                    nq = 0;
-                }
+            }
+            if (drain) {
+                if ((nq0 | nq1 | nq2) == 0) break;     // a queue held more than one group: drain again
             }
         }
         group_sync<G>();

@@ -171,4 +171,117 @@ TDS_HD void row_tri_step(RowTri& t, int W, int y, Emit&& emit) {
     if (y >= t.f.fylo && y <= t.f.fyhi && row_fill_step(t.f, W, y, lo, hi)) emit(lo, hi);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: all three vertices INSIDE the image (no clipLine, no clamps).  Then every row of the triangle
+// is ONE interval [L, R]: the fill span ends within one pixel of the LineIterator pixels of the two boundary
+// edges (both approximate the same line, the span by round-half-up of a 16.16 value, the iterator by
+// round-half-down), runs of x-major edges are contiguous with them, and at the rows of the vertices the
+// edges meet in the vertex pixel.  So L = min and R = max over the fill span and the runs of the edges
+// that are active in the row: the long edge T-B, and T-M above the middle vertex / M-B from it on.
+// (Clipped edges do NOT have this property: they are redrawn between moved endpoints.)
+struct FastEdge {
+    int cur, gend;   // x-major boundaries, as absolute columns
+    int n, b1;
+    int lx;
+    uint32_t rcp;
+    int xm;          // ~0 for x-major, 0 for y-major
+    int yend;        // last row of the edge
+};
+
+// top endpoint (px,py) -> bottom endpoint (qx,qy), py <= qy
+template <class RcpFn>
+TDS_HD void fast_edge_setup(int px, int py, int qx, int qy, FastEdge& e, RcpFn&& rcp_of) {
+    const int dy = qy - py, dxs = qx - px;
+    const bool down = dxs >= 0;                 // the left endpoint is the top one
+    const int dx = down ? dxs : -dxs;
+    const int lx = down ? px : qx;
+    const bool xmajor = dx >= dy;
+    const int a1 = 2 * dx;
+    const int a0 = xmajor ? 2 * dy - dx : dy - 1;
+    e.lx = lx;
+    e.rcp = rcp_of(dy);
+    e.xm = xmajor ? -1 : 0;
+    e.yend = qy;
+    e.cur = lx + (down ? 0 : dx + 1);
+    e.gend = lx + (down ? dx + 1 : 0);
+    e.b1 = down ? a1 : -a1;
+    e.n = down ? a0 + (xmajor ? a1 : 0) : a1 * dy + a0;
+}
+
+TDS_HD void fast_edge_step(FastEdge& e, int y, int& lo, int& hi) {
+    const int q = e.lx + (int)mulhi_u32((uint32_t)e.n, e.rcp);
+    e.n += e.b1;
+    const int nxt = y == e.yend ? e.gend : q;
+    const int a = e.cur < nxt ? e.cur : nxt, b = (e.cur < nxt ? nxt : e.cur) - 1;
+    e.cur = nxt;
+    lo = (a & e.xm) | (q & ~e.xm);
+    hi = (b & e.xm) | (q & ~e.xm);
+}
+
+// 16.16 slope of FillConvexPoly through the reciprocal table: exact while |num| * 2 dy < 2^32 (images <= 128)
+TDS_HD int edge_dx_rcp(int dxs, int dy, uint32_t rcp) {
+    const int num = dxs * 131072 + dy;
+    const int q = (int)mulhi_u32((uint32_t)(num < 0 ? -num : num), rcp);
+    return num < 0 ? -q : q;
+}
+
+struct FastTri {
+    FastEdge tb, s, mb;      // long edge, current short edge (T-M until the middle row), M-B
+    int ty, my, by;
+    int xa, dTB, xb, dS, xM, dMB;   // fill: both ends carry the +0.5 rounding bias
+};
+
+template <bool SMALL, class RcpFn>
+TDS_HD void fast_tri_setup(int x0, int y0, int x1, int y1, int x2, int y2, FastTri& t, RcpFn&& rcp_of) {
+    int tx = x0, ty = y0, mx = x1, my = y1, bx = x2, by = y2, w;
+    if (my < ty) { w = tx; tx = mx; mx = w; w = ty; ty = my; my = w; }
+    if (by < my) { w = mx; mx = bx; bx = w; w = my; my = by; by = w; }
+    if (my < ty) { w = tx; tx = mx; mx = w; w = ty; ty = my; my = w; }
+    fast_edge_setup(tx, ty, bx, by, t.tb, rcp_of);
+    fast_edge_setup(tx, ty, mx, my, t.s, rcp_of);
+    fast_edge_setup(mx, my, bx, by, t.mb, rcp_of);
+    t.ty = ty; t.my = my; t.by = by;
+    if (SMALL) {
+        t.dTB = by > ty ? edge_dx_rcp(bx - tx, by - ty, t.tb.rcp) : 0;
+        t.dS = my > ty ? edge_dx_rcp(mx - tx, my - ty, t.s.rcp) : 0;
+        t.dMB = by > my ? edge_dx_rcp(bx - mx, by - my, t.mb.rcp) : 0;
+    } else {
+        t.dTB = by > ty ? edge_dx<int>(tx, ty, bx, by) : 0;
+        t.dS = my > ty ? edge_dx<int>(tx, ty, mx, my) : 0;
+        t.dMB = by > my ? edge_dx<int>(mx, my, bx, by) : 0;
+    }
+    t.xa = (tx << 16) + 32768;
+    t.xb = t.xa;
+    t.xM = (mx << 16) + 32768;
+}
+
+// emit(y, L, R) once per row ty..by, in order
+template <class Emit>
+TDS_HD void fast_tri_rows(FastTri& t, Emit&& emit) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int y = t.ty; y <= t.by; y++) {
+        int eL = 0x7fffffff, eH = -1;
+        if (y == t.my) {
+            // last row of T-M, then M-B takes over (its first row is this one)
+            fast_edge_step(t.s, y, eL, eH);
+            t.s = t.mb;
+            t.xb = t.xM;
+            t.dS = t.dMB;
+        }
+        int l1, h1, l2, h2;
+        fast_edge_step(t.tb, y, l1, h1);
+        fast_edge_step(t.s, y, l2, h2);
+        const int xl = t.xa < t.xb ? t.xa : t.xb, xr = t.xa < t.xb ? t.xb : t.xa;
+        t.xa += t.dTB;
+        t.xb += t.dS;
+        int L = xl >> 16, R = xr >> 16;
+        L = L < l1 ? L : l1; L = L < l2 ? L : l2; L = L < eL ? L : eL;
+        R = R > h1 ? R : h1; R = R > h2 ? R : h2; R = R > eH ? R : eH;
+        emit(y, L, R);
+    }
+}
+
 }  // namespace tds
