@@ -160,7 +160,8 @@ typedef struct {
     int32_t tl_state_class[TDS_MAX_TL_STATES];      /* class of traffic-light state index s */
 } tds_palette_t;
 
-/* bytes of the per-step scratch buffer (world-space dynamic triangles of every environment) */
+/* bytes of the per-step scratch buffer (world-space dynamic triangles of every environment + the work
+ * counter of the persistent raster grid); always > 0 */
 int64_t tds_raster_workspace_bytes(int32_t B, int32_t N, int32_t L, int32_t R);
 
 /* Renders Nc cameras per environment.
@@ -171,7 +172,7 @@ int64_t tds_raster_workspace_bytes(int32_t B, int32_t N, int32_t L, int32_t R);
  *   d_rect_corners [B,R,4,2], d_rect_class [B,R] int32: extra rectangles (stop / yield signs)
  *   scale = 2 / fov, res = H = W (square only, as the reference)
  *   d_out [B,Nc,3,res,res] float32 in [0,255]
- *   d_workspace: tds_raster_workspace_bytes(B,N,L,R) bytes */
+ *   d_workspace: tds_raster_workspace_bytes(B,N,L,R) bytes, required even when N = L = R = 0 */
 int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps, const int32_t* d_env_map,
                         int32_t B, int32_t Nc, int32_t N,
                         const float* d_cam_xy, const float* d_cam_sc,

@@ -254,10 +254,18 @@ __device__ __forceinline__ void or_span(uint32_t* plane, int res, int y, int lo,
     }
 }
 
+// 64-pixel rows: the two 32-bit halves of a row mask, each OR-ed only when non-zero (predicated red.shared, no branch)
 __device__ __forceinline__ void or_mask64(uint32_t* plane, int y, unsigned long long m) {
     const uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
-    if (m0) atomicOr(plane + y, m0);
-    if (m1) atomicOr(plane + 64 + y, m1);
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(plane + y);
+    asm volatile(
+        "{\n\t.reg .pred p0, p1;\n\t"
+        "setp.ne.u32 p0, %1, 0;\n\t"
+        "setp.ne.u32 p1, %2, 0;\n\t"
+        "@p0 red.shared.or.b32 [%0], %1;\n\t"
+        "@p1 red.shared.or.b32 [%0+256], %2;\n\t}"
+        ::"r"(addr), "r"(m0), "r"(m1)
+        : "memory");
 }
 
 // stage 2a: a triangle with all vertices inside the image: one interval and one atomic OR per row and word
@@ -307,6 +315,7 @@ struct RasterArgs {
     int32_t B, Nc, N, T, present_per_camera, res;
     int32_t ncam;
     float scale;
+    int32_t* next_cam;         // work counter of the persistent grid (zeroed before the launch)
 };
 
 constexpr int kRows = tds::kMaxRasterRows;
@@ -327,7 +336,7 @@ __device__ __forceinline__ void group_sync() {
 }
 
 #ifndef TDS_RASTER_MINB
-#define TDS_RASTER_MINB 6
+#define TDS_RASTER_MINB 7
 #endif
 // NS = bits of the per-pixel draw rank (0 = background): 3 for up to 7 active classes, 5 for up to 31
 template <int G, int RES, int NS>
@@ -360,6 +369,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     }
     for (int i = threadIdx.x; i <= res; i += blockDim.x) s_rcp[i] = tds::row_rcp(i);
     __syncthreads();
+    const int plane_tbl = s_plane_of_class[lane];       // lane c holds the plane of class c (TDS_MAX_CLASSES == 32)
 
     // per-group shared memory: planes | queues | row tables
     const int plane_words = res * W32;
@@ -372,8 +382,20 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     int* s_cnt = s_count + kRows;                  // queue fill levels (G > 32)
     float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
 
-    // cameras are dealt round-robin to the groups of a persistent grid
-    for (int camid = blockIdx.x * GROUPS + group; camid < a.ncam; camid += gridDim.x * GROUPS) {
+    // persistent grid: every group (warp or CTA) pulls the next camera from a global counter, so uneven cameras
+    // (a junction full of lane markings next to an empty field) do not leave SMs idle at the end
+    while (true) {
+        int camid = 0;
+        if (G == 32) {
+            if (lane == 0) camid = atomicAdd(a.next_cam, 1);
+            camid = __shfl_sync(0xffffffffu, camid, 0);
+        } else {
+            __syncthreads();                        // previous camera completely done (s_cnt is reused below)
+            if (tid == 0) s_cnt[3] = atomicAdd(a.next_cam, 1);
+            __syncthreads();
+            camid = s_cnt[3];
+        }
+        if (camid >= a.ncam) break;
         const int b = camid / a.Nc;
         const MapDev& map = maps.m[a.env_map ? a.env_map[b] : 0];
         Camera cam;
@@ -458,40 +480,43 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
             }
             const bool drain = seg > nrows;
             if (!drain) {
+                // uniform control flow: every lane fetches a valid record (the last one of the segment past its end)
                 const int j = j0 + tid;
                 j0 += G;
-                int kind = kCulled, plane = -1;
-                int xy[6];
-                if (j < seg_count) {
-                    float x0, y0, x1, y1, x2, y2;
-                    int own = 7, cls;
-                    if (seg < nrows) {
-                        const float4* rp = map.rec + 2 * (int64_t)(seg_start + j);
-                        const float4 v01 = __ldg(rp);
-                        const float4 v2o = __ldg(rp + 1);
-                        x0 = v01.x; y0 = v01.y; x1 = v01.z; y1 = v01.w; x2 = v2o.x; y2 = v2o.y;
-                        const int meta = __float_as_int(v2o.z);
-                        own = meta & 7;
-                        cls = (meta >> 8) & 255;
-                    } else {
-                        // dynamic primitives (agents, direction triangles, traffic lights, signs)
-                        int t = j;
-                        bool degenerate = false;
-                        if (t < 3 * a.N && pres && !pres[t / 3]) {
-                            // absent agent: faces * 0 -> degenerate triangle at actor vertex 0 with agent 0's class
-                            // (mesh.py:1083-1089)
-                            t = 0;
-                            degenerate = true;
-                        }
-                        cls = dcls[t];
-                        const float* p = dtri + (int64_t)t * 6;
-                        x0 = p[0]; y0 = p[1];
-                        x1 = degenerate ? x0 : p[2]; y1 = degenerate ? y0 : p[3];
-                        x2 = degenerate ? x0 : p[4]; y2 = degenerate ? y0 : p[5];
+                const bool valid = j < seg_count;
+                const int jj = valid ? j : seg_count - 1;
+                float x0, y0, x1, y1, x2, y2;
+                int own = 7, cls;
+                if (seg < nrows) {
+                    const float4* rp = map.rec + 2 * (int64_t)(seg_start + jj);
+                    const float4 v01 = __ldg(rp);
+                    const float4 v2o = __ldg(rp + 1);
+                    x0 = v01.x; y0 = v01.y; x1 = v01.z; y1 = v01.w; x2 = v2o.x; y2 = v2o.y;
+                    const int meta = __float_as_int(v2o.z);
+                    own = meta & 7;
+                    cls = meta >> 8;
+                } else {
+                    // dynamic primitives (agents, direction triangles, traffic lights, signs)
+                    int t = jj;
+                    bool degenerate = false;
+                    if (t < 3 * a.N && pres && !pres[t / 3]) {
+                        // absent agent: faces * 0 -> degenerate triangle at actor vertex 0 with agent 0's class
+                        // (mesh.py:1083-1089)
+                        t = 0;
+                        degenerate = true;
                     }
-                    plane = cls < TDS_MAX_CLASSES ? s_plane_of_class[cls] : -1;
-                    if (plane >= 0) kind = setup_triangle<POW2>(cam, x0, y0, x1, y1, x2, y2, own, xy);
+                    cls = dcls[t];
+                    const float* p = dtri + (int64_t)t * 6;
+                    x0 = p[0]; y0 = p[1];
+                    x1 = degenerate ? x0 : p[2]; y1 = degenerate ? y0 : p[3];
+                    x2 = degenerate ? x0 : p[4]; y2 = degenerate ? y0 : p[5];
                 }
+                // class -> plane through the lane-resident table (lane c holds the plane of class c)
+                int plane = __shfl_sync(0xffffffffu, plane_tbl, cls & 31);
+                plane = (valid && (unsigned)cls < (unsigned)TDS_MAX_CLASSES) ? plane : -1;
+                int kind = kCulled;
+                int xy[6];
+                if (plane >= 0) kind = setup_triangle<POW2>(cam, x0, y0, x1, y1, x2, y2, own, xy);
                 if (kind == kVerts) {
                     uint32_t* pl = planes + plane * plane_words;
 #pragma unroll
@@ -519,9 +544,9 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                         nq0 += __popc(m0); nq1 += __popc(m1); nq2 += __popc(m2);
                     }
                     if (kind >= kShort) {
-                        const unsigned below = (1u << lane) - 1;
-                        const int pos = kind == kShort ? b0 + __popc(m0 & below)
-                                      : (kind == kTall ? QN + b1 + __popc(m1 & below) : 2 * QN + b2 + __popc(m2 & below));
+                        const unsigned mine = kind == kShort ? m0 : (kind == kTall ? m1 : m2);
+                        const int qb = kind == kShort ? b0 : (kind == kTall ? QN + b1 : 2 * QN + b2);
+                        const int pos = qb + __popc(mine & ((1u << lane) - 1));
                         queue[pos] = make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
                                                 (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
                                                 (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
@@ -530,6 +555,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 group_sync<G>();
                 if (G != 32) { nq0 = s_cnt[0]; nq1 = s_cnt[1]; nq2 = s_cnt[2]; }
             }
+            if (!(drain | (nq0 >= G) | (nq1 >= G) | (nq2 >= G))) continue;
             // stage 2: a queue is drawn when it holds a full group (or, at the end, whatever is left)
 #pragma unroll 1
             for (int which = 0; which < 2; which++) {
@@ -654,7 +680,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     TDS_REQUIRE(scale > 0.0f, "raster: scale must be positive");
     TDS_REQUIRE(palette->n_classes >= 0 && palette->n_classes <= TDS_MAX_CLASSES, "raster: bad palette");
     const int T = 3 * N + 2 * L + 2 * R;
-    TDS_REQUIRE(T == 0 || d_workspace, "raster: null workspace");
+    TDS_REQUIRE(d_workspace, "raster: null workspace (tds_raster_workspace_bytes)");
     MapSetDev set;
     if (int e = tds::gather_maps(maps, n_maps, set)) return e;
     // the view quad's bounding box must fit kMaxRasterRows grid rows of every map
@@ -705,6 +731,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     const int64_t ncam = (int64_t)B * Nc;
     TDS_REQUIRE(ncam <= 2147483647LL, "raster: too many cameras");
     a.ncam = (int32_t)ncam;
+    a.next_cam = reinterpret_cast<int32_t*>((uint8_t*)d_workspace + (int64_t)B * ws_env_bytes(T));
     const int K = pal.n_classes;
     TDS_REQUIRE(K <= 31, "raster: at most 31 active classes (got %d)", K);
     const int sms = tds::sm_count();
@@ -719,6 +746,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
         // persistent grid: every resident CTA slot of the GPU, cameras dealt round-robin
         const int64_t want = (ncam + groups - 1) / groups;
         const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per_sm);
+        TDS_CUDA_OK(cudaMemsetAsync(a.next_cam, 0, sizeof(int32_t), st));
         if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
         kernel<<<grid, threads, smem, st>>>(set, a, pal);
         if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);

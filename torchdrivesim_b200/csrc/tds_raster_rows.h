@@ -181,39 +181,45 @@ TDS_HD void row_tri_step(RowTri& t, int W, int y, Emit&& emit) {
 // that are active in the row: the long edge T-B, and T-M above the middle vertex / M-B from it on.
 // (Clipped edges do NOT have this property: they are redrawn between moved endpoints.)
 struct FastEdge {
-    int cur, gend;   // x-major boundaries, as absolute columns
+    int cur;         // x-major: boundary shared with the previous row, as an absolute column
+    int gmax;        // x-major: lx + dx + 1, the boundary after the last pixel
     int n, b1;
     int lx;
     uint32_t rcp;
     int xm;          // ~0 for x-major, 0 for y-major
-    int yend;        // last row of the edge
 };
 
-// top endpoint (px,py) -> bottom endpoint (qx,qy), py <= qy
+TDS_HD int imax_(int a, int b) { return a > b ? a : b; }
+TDS_HD int imin_(int a, int b) { return a < b ? a : b; }
+
+// top endpoint (px,py) -> bottom endpoint (qx,qy), py <= qy.
+// The boundary of an x-major edge towards the next row is mulhi(max(n, 0), rcp) clamped to dx + 1: the clamp
+// yields G(dy + 1) = dx + 1 after the last row of an edge walked away from its left endpoint (the formula
+// gives dx + 1 + floor(dx / 2dy) there), the max yields G(0) = 0 after the last row of an edge walked towards
+// its left endpoint (n = 2 dy - dx may be negative there).  A horizontal edge is walked "towards" its left end.
 template <class RcpFn>
 TDS_HD void fast_edge_setup(int px, int py, int qx, int qy, FastEdge& e, RcpFn&& rcp_of) {
     const int dy = qy - py, dxs = qx - px;
-    const bool down = dxs >= 0;                 // the left endpoint is the top one
-    const int dx = down ? dxs : -dxs;
-    const int lx = down ? px : qx;
+    const bool down = dxs >= 0 && dy > 0;       // the left endpoint is the top one
+    const int dx = dxs >= 0 ? dxs : -dxs;
+    const int lx = dxs >= 0 ? px : qx;
     const bool xmajor = dx >= dy;
     const int a1 = 2 * dx;
     const int a0 = xmajor ? 2 * dy - dx : dy - 1;
     e.lx = lx;
     e.rcp = rcp_of(dy);
     e.xm = xmajor ? -1 : 0;
-    e.yend = qy;
-    e.cur = lx + (down ? 0 : dx + 1);
-    e.gend = lx + (down ? dx + 1 : 0);
+    e.gmax = lx + dx + 1;
+    e.cur = down ? lx : lx + dx + 1;
     e.b1 = down ? a1 : -a1;
     e.n = down ? a0 + (xmajor ? a1 : 0) : a1 * dy + a0;
 }
 
-TDS_HD void fast_edge_step(FastEdge& e, int y, int& lo, int& hi) {
-    const int q = e.lx + (int)mulhi_u32((uint32_t)e.n, e.rcp);
+TDS_HD void fast_edge_step(FastEdge& e, int& lo, int& hi) {
+    const int q = e.lx + (int)mulhi_u32((uint32_t)imax_(e.n, 0), e.rcp);
     e.n += e.b1;
-    const int nxt = y == e.yend ? e.gend : q;
-    const int a = e.cur < nxt ? e.cur : nxt, b = (e.cur < nxt ? nxt : e.cur) - 1;
+    const int nxt = imin_(q, e.gmax);
+    const int a = imin_(e.cur, nxt), b = imax_(e.cur, nxt) - 1;
     e.cur = nxt;
     lo = (a & e.xm) | (q & ~e.xm);
     hi = (b & e.xm) | (q & ~e.xm);
@@ -266,14 +272,14 @@ TDS_HD void fast_tri_rows(FastTri& t, Emit&& emit) {
         int eL = 0x7fffffff, eH = -1;
         if (y == t.my) {
             // last row of T-M, then M-B takes over (its first row is this one)
-            fast_edge_step(t.s, y, eL, eH);
+            fast_edge_step(t.s, eL, eH);
             t.s = t.mb;
             t.xb = t.xM;
             t.dS = t.dMB;
         }
         int l1, h1, l2, h2;
-        fast_edge_step(t.tb, y, l1, h1);
-        fast_edge_step(t.s, y, l2, h2);
+        fast_edge_step(t.tb, l1, h1);
+        fast_edge_step(t.s, l2, h2);
         const int xl = t.xa < t.xb ? t.xa : t.xb, xr = t.xa < t.xb ? t.xb : t.xa;
         t.xa += t.dTB;
         t.xb += t.dS;
