@@ -347,6 +347,14 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         achieved = B * A * 12 * RES * RES / (raster_ms * 1e-3) / 1e9
+        # DRAM bytes of one raster launch of this size, from the committed `ncu --set full` capture (never measured
+        # under the timer): profiles/r1_raster_ncu_summary.json
+        traffic, traffic_src = None, None
+        ncu_path = os.path.join(ROOT, "profiles", "r1_raster_ncu_summary.json")
+        if os.path.exists(ncu_path):
+            nj = json.load(open(ncu_path))
+            if nj.get("algorithmic_bytes_per_launch") == B * A * 12 * RES * RES:
+                traffic, traffic_src = nj["traffic_bytes_per_launch"], "profiles/r1_raster_ncu_summary.json (dram__bytes_read+write.sum)"
         cpu_val, cpu_procs = float("nan"), 0
         if not args.kernels_only:
             cpu_val, cpu_procs, _ = cpu_port_throughput(max(8, min(os.cpu_count() or 1, 128)))
@@ -362,7 +370,7 @@ def run_ours(args):
                                   "note": "same, images stay in HBM for a GPU consumer (the reference API returns device tensors)"},
             "gpu_launches": 5 * K, "eager_ms_per_step": eager_ms,
             "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "raster_ms_per_launch": raster_ms, "algorithmic_bytes_per_launch": B * A * 12 * RES * RES,
                          "step_frac_of_hbm_roofline": value / world * BYTES_PER_AGENT_STEP / 1e9 / peak},
             "cpu_baseline": {"value": cpu_val, "unit": "agent-env-steps/s", "cores": cpu_procs, "kind": "port",
