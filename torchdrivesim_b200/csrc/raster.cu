@@ -242,22 +242,53 @@ __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float
     return !inside ? kClipped : (ymax - ymin <= kShortRows ? kShort : kTall);
 }
 
-// ---- bitplanes: one bit per pixel and draw rank; plane p, word column w, row y at  p * res * W32 + w * res + y
-__device__ __forceinline__ void or_bit(uint32_t* plane, int res, int x, int y) {
-    atomicOr(plane + (x >> 5) * res + y, 1u << (x & 31));
+// ---- shared memory is addressed through 32-bit shared-window addresses and explicit ld/st/red.shared: with
+// generic pointers the compiler re-derives the window base (S2R SR_CgaCtaId, LEA, IMAD ...) at every access site.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    // the volatile move makes the address a plain register value: it is computed once instead of being
+    // rematerialised from the special registers wherever it is used
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sred_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t slds(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t slds_const(uint32_t a) {      // tables that never change after the prologue
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ssts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 slds4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ssts4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ __forceinline__ void or_span(uint32_t* plane, int res, int y, int lo, int hi) {
+// ---- bitplanes: one bit per pixel and draw rank; plane p, word column w, row y at word  p * res * W32 + w * res + y.
+// `plane` below is the shared-window BYTE address of a plane.
+__device__ __forceinline__ void or_bit(uint32_t plane, int res, int x, int y) {
+    sred_or(plane + 4u * (uint32_t)((x >> 5) * res + y), 1u << (x & 31));
+}
+
+__device__ __forceinline__ void or_span(uint32_t plane, int res, int y, int lo, int hi) {
     for (int w = lo >> 5; w <= (hi >> 5); w++) {
         const int l = max(lo - 32 * w, 0), h = min(hi - 32 * w, 31);
-        atomicOr(plane + w * res + y, (0xffffffffu >> (31 - (h - l))) << l);
+        sred_or(plane + 4u * (uint32_t)(w * res + y), (0xffffffffu >> (31 - (h - l))) << l);
     }
 }
 
 // 64-pixel rows: the two 32-bit halves of a row mask, each OR-ed only when non-zero (predicated red.shared, no branch)
-__device__ __forceinline__ void or_mask64(uint32_t* plane, int y, unsigned long long m) {
+__device__ __forceinline__ void or_mask64(uint32_t plane, int y, unsigned long long m) {
     const uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
-    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(plane + y);
+    const uint32_t addr = plane + 4u * (uint32_t)y;
     asm volatile(
         "{\n\t.reg .pred p0, p1;\n\t"
         "setp.ne.u32 p0, %1, 0;\n\t"
@@ -270,10 +301,10 @@ __device__ __forceinline__ void or_mask64(uint32_t* plane, int y, unsigned long 
 
 // stage 2a: a triangle with all vertices inside the image: one interval and one atomic OR per row and word
 template <int RES, bool SMALL>
-__device__ __forceinline__ void draw_inside(uint32_t* plane, int res, const uint32_t* s_rcp, int x0, int y0, int x1, int y1,
+__device__ __forceinline__ void draw_inside(uint32_t plane, int res, uint32_t rcp_sa, int x0, int y0, int x1, int y1,
                                             int x2, int y2) {
     tds::FastTri t;
-    tds::fast_tri_setup<SMALL>(x0, y0, x1, y1, x2, y2, t, [&](int dy) { return s_rcp[dy]; });
+    tds::fast_tri_setup<SMALL>(x0, y0, x1, y1, x2, y2, t, [&](int dy) { return slds_const(rcp_sa + 4u * (uint32_t)dy); });
     tds::fast_tri_rows(t, [&](int y, int lo, int hi) {
         if (RES == 64) or_mask64(plane, y, (~0ull >> (63 - (hi - lo))) << lo);
         else or_span(plane, res, y, lo, hi);
@@ -282,10 +313,10 @@ __device__ __forceinline__ void draw_inside(uint32_t* plane, int res, const uint
 
 // stage 2b: a triangle that crosses the image border (|coordinates| < 8192): clipped outline runs + clamped spans
 template <int RES>
-__device__ __forceinline__ void draw_clipped(uint32_t* plane, int res, const uint32_t* s_rcp, int x0, int y0, int x1, int y1,
+__device__ __forceinline__ void draw_clipped(uint32_t plane, int res, uint32_t rcp_sa, int x0, int y0, int x1, int y1,
                                              int x2, int y2) {
     tds::RowTri t;
-    tds::row_tri_setup(res, res, x0, y0, x1, y1, x2, y2, t, [&](int dy) { return s_rcp[dy]; });
+    tds::row_tri_setup(res, res, x0, y0, x1, y1, x2, y2, t, [&](int dy) { return slds_const(rcp_sa + 4u * (uint32_t)dy); });
 #pragma unroll 1
     for (int y = t.ylo; y <= t.yhi; y++) {
         if (RES == 64) {
@@ -299,8 +330,8 @@ __device__ __forceinline__ void draw_clipped(uint32_t* plane, int res, const uin
 }
 
 // coordinates beyond +-8000 pixels (extreme zoom / giant rectangles): 64-bit rule, pixel by pixel.  Rare.
-__device__ __noinline__ void draw_huge(uint32_t* plane, int res, const int* xy) {
-    tds::draw_triangle(res, res, xy[0], xy[1], xy[2], xy[3], xy[4], xy[5],
+__device__ __noinline__ void draw_huge(uint32_t plane, int res, int x0, int y0, int x1, int y1, int x2, int y2) {
+    tds::draw_triangle(res, res, x0, y0, x1, y1, x2, y2,
         [&](int x, int y) { or_bit(plane, res, x, y); },
         [&](int y, int xa, int xb) { or_span(plane, res, y, xa, xb); });
 }
@@ -322,10 +353,13 @@ constexpr int kRows = tds::kMaxRasterRows;
 constexpr int kQueues = 3;                          // short inside, tall inside, clipped
 constexpr int kGroupExtra = kRows * 8 + 16 + 48;    // row tables, counters, view-quad edge functions
 
-__host__ __device__ inline int raster_group_bytes(int res, int n_planes, int G) {
-    const int w32 = (res + 31) / 32;
-    return n_planes * res * w32 * 4 + kQueues * 2 * G * 16 + kGroupExtra;
+__host__ __device__ constexpr int raster_group_bytes(int res, int n_planes, int G) {
+    return n_planes * res * ((res + 31) / 32) * 4 + kQueues * 2 * G * 16 + kGroupExtra;
 }
+// The 64x64 / <= 7 classes variant (the benchmark configuration) reserves 7 planes per camera in STATIC shared
+// memory: every address is then a compile-time offset and nothing has to be re-derived from the dynamic base.
+constexpr int kStaticPlanes = 7;
+__host__ __device__ constexpr bool raster_static_smem(int G, int RES, int NS) { return G == 32 && RES == 64 && NS == 3; }
 
 // G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras in flight per CTA, no block barriers)
 // for tiles up to 64x64, or the whole CTA for larger tiles.
@@ -356,7 +390,13 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     // CTA-wide tables: colour per draw rank (0 = background), reciprocals of the row runs, class -> plane
     __shared__ float4 s_lut[TDS_MAX_CLASSES + 1];
     __shared__ int8_t s_plane_of_class[TDS_MAX_CLASSES];
-    uint32_t* s_rcp = reinterpret_cast<uint32_t*>(smem_raw);                 // [res + 1]
+    constexpr bool STATIC = raster_static_smem(G, RES, NS);
+    constexpr int STATIC_RCP = ((64 + 1) * 4 + 15) & ~15;
+    constexpr int STATIC_BYTES = STATIC ? STATIC_RCP + 4 * raster_group_bytes(64, kStaticPlanes, 32) : 16;
+    __shared__ __align__(16) uint8_t smem_static[STATIC_BYTES];
+    uint8_t* const smem = STATIC ? smem_static : smem_raw;
+    const int KS = STATIC ? kStaticPlanes : K;                               // planes reserved per camera
+    uint32_t* s_rcp = reinterpret_cast<uint32_t*>(smem);                     // [res + 1]
     const int rcp_bytes = ((res + 1) * 4 + 15) & ~15;
     for (int i = threadIdx.x; i <= K; i += blockDim.x) {
         const float* c = pal.rgb[i == 0 ? 0 : pal.order[i - 1] + 1];
@@ -373,13 +413,15 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
 
     // per-group shared memory: planes | queues | row tables
     const int plane_words = res * W32;
-    const int group_bytes = raster_group_bytes(res, K, G);
-    uint8_t* base = smem_raw + rcp_bytes + (size_t)group * group_bytes;
-    uint32_t* planes = reinterpret_cast<uint32_t*>(base);
-    uint4* queue = reinterpret_cast<uint4*>(base + (size_t)K * plane_words * 4);          // [kQueues][QN]
-    int* s_start = reinterpret_cast<int*>(queue + kQueues * QN);
-    int* s_count = s_start + kRows;
-    int* s_cnt = s_count + kRows;                  // queue fill levels (G > 32)
+    const int group_bytes = raster_group_bytes(res, KS, G);
+    uint8_t* base = smem + rcp_bytes + group * group_bytes;
+    const uint32_t planes_sa = smem_addr(base);                            // [KS][W32][res] words
+    const uint32_t rcp_sa = planes_sa - (uint32_t)(rcp_bytes + group * group_bytes);
+    const uint32_t plane_bytes = 4u * (uint32_t)plane_words;
+    const uint32_t queue_sa = planes_sa + (uint32_t)KS * plane_bytes;      // [kQueues][QN] x 16 B
+    const uint32_t start_sa = queue_sa + kQueues * QN * 16;                // [kRows] first record of a grid row
+    const uint32_t count_sa = start_sa + kRows * 4;                        // [kRows] records of a grid row
+    int* s_cnt = reinterpret_cast<int*>(base + KS * plane_words * 4 + kQueues * QN * 16 + kRows * 8);   // queue fill levels (G > 32)
     float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
 
     // persistent grid: every group (warp or CTA) pulls the next camera from a global counter, so uneven cameras
@@ -405,8 +447,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
         group_sync<G>();                            // previous camera of this group is completely done
         make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy, s_edges, tid == 0);
         {
-            uint4* pz = reinterpret_cast<uint4*>(planes);
-            for (int i = tid; i < K * plane_words / 4; i += G) pz[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < K * plane_words / 4; i += G) ssts4(planes_sa + 16u * (uint32_t)i, make_uint4(0u, 0u, 0u, 0u));
             if (tid < 4) s_cnt[tid] = 0;
         }
 
@@ -452,8 +493,8 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                     cnt = map.rcell[r * map.rgx + c1 + 1] - st;
                 }
             }
-            s_start[tid] = st;
-            s_count[tid] = cnt;
+            ssts(start_sa + 4u * tid, (uint32_t)st);
+            ssts(count_sa + 4u * tid, (uint32_t)cnt);
         }
         group_sync<G>();
 
@@ -468,15 +509,15 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
         // just their vertices and queues the others by kind; whenever G faces of a kind are queued, stage 2 turns
         // them into row intervals, one face per thread, so stage 2 always runs with full warps.  The last
         // iteration (seg > nrows) only drains the queues.
-        int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? s_count[0] : T;
-        if (nrows > 0) seg_start = s_start[0];
+        int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? (int)slds(count_sa) : T;
+        if (nrows > 0) seg_start = (int)slds(start_sa);
         int nq0 = 0, nq1 = 0, nq2 = 0;                 // queue fill levels (uniform over the group)
         while (true) {
             while (j0 >= seg_count && seg <= nrows) {
                 seg++;
                 j0 = 0;
-                seg_count = seg < nrows ? s_count[seg] : (seg == nrows ? T : 0);
-                seg_start = seg < nrows ? s_start[seg] : 0;
+                seg_count = seg < nrows ? (int)slds(count_sa + 4u * seg) : (seg == nrows ? T : 0);
+                seg_start = seg < nrows ? (int)slds(start_sa + 4u * seg) : 0;
             }
             const bool drain = seg > nrows;
             if (!drain) {
@@ -518,13 +559,13 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 int xy[6];
                 if (plane >= 0) kind = setup_triangle<POW2>(cam, x0, y0, x1, y1, x2, y2, own, xy);
                 if (kind == kVerts) {
-                    uint32_t* pl = planes + plane * plane_words;
+                    const uint32_t pl = planes_sa + (uint32_t)plane * plane_bytes;
 #pragma unroll
                     for (int k = 0; k < 3; k++)
                         if ((unsigned)xy[2 * k] < (unsigned)res && (unsigned)xy[2 * k + 1] < (unsigned)res)
                             or_bit(pl, res, xy[2 * k], xy[2 * k + 1]);
                 } else if (kind == kHuge) {
-                    draw_huge(planes + plane * plane_words, res, xy);
+                    draw_huge(planes_sa + (uint32_t)plane * plane_bytes, res, xy[0], xy[1], xy[2], xy[3], xy[4], xy[5]);
                 }
                 // queue the other faces by kind (warp-aggregated append)
                 const unsigned m0 = __ballot_sync(0xffffffffu, kind == kShort), m1 = __ballot_sync(0xffffffffu, kind == kTall),
@@ -547,9 +588,10 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                         const unsigned mine = kind == kShort ? m0 : (kind == kTall ? m1 : m2);
                         const int qb = kind == kShort ? b0 : (kind == kTall ? QN + b1 : 2 * QN + b2);
                         const int pos = qb + __popc(mine & ((1u << lane) - 1));
-                        queue[pos] = make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
-                                                (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
-                                                (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
+                        ssts4(queue_sa + 16u * (uint32_t)pos,
+                              make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
+                                         (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
+                                         (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane));
                     }
                 }
                 group_sync<G>();
@@ -563,8 +605,8 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 if (nq >= G || (drain && nq > 0)) {
                     const int take = min(nq, G);
                     if (tid < take) {
-                        const uint4 q = queue[which * QN + nq - take + tid];
-                        draw_inside<RES, SMALL>(planes + (int)q.w * plane_words, res, s_rcp,
+                        const uint4 q = slds4(queue_sa + 16u * (uint32_t)(which * QN + nq - take + tid));
+                        draw_inside<RES, SMALL>(planes_sa + q.w * plane_bytes, res, rcp_sa,
                                                 (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
                                                 (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
                     }
@@ -579,8 +621,8 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
             if (nq2 >= G || (drain && nq2 > 0)) {
                 const int take = min(nq2, G);
                 if (tid < take) {
-                    const uint4 q = queue[2 * QN + nq2 - take + tid];
-                    draw_clipped<RES>(planes + (int)q.w * plane_words, res, s_rcp,
+                    const uint4 q = slds4(queue_sa + 16u * (uint32_t)(2 * QN + nq2 - take + tid));
+                    draw_clipped<RES>(planes_sa + q.w * plane_bytes, res, rcp_sa,
                                       (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
                                       (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
                 }
@@ -612,7 +654,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
             uint32_t rem[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 #pragma unroll 1
             for (int p = K - 1; p >= 0; p--) {          // last drawn = on top
-                const uint4 v = *reinterpret_cast<const uint4*>(planes + p * plane_words + w * res + 4 * yq);
+                const uint4 v = slds4(planes_sa + (uint32_t)p * plane_bytes + 4u * (uint32_t)(w * res + 4 * yq));
                 const uint32_t pw[4] = {v.x, v.y, v.z, v.w};
                 const int id = p + 1;
 #pragma unroll
@@ -735,9 +777,9 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     const int K = pal.n_classes;
     TDS_REQUIRE(K <= 31, "raster: at most 31 active classes (got %d)", K);
     const int sms = tds::sm_count();
-    auto launch = [&](auto kernel, int groups, int threads) -> int {
+    auto launch = [&](auto kernel, int groups, int threads, bool static_smem) -> int {
         const size_t rcp_bytes = (((size_t)res + 1) * 4 + 15) & ~(size_t)15;
-        const size_t smem = rcp_bytes + (size_t)raster_group_bytes(res, K, threads / groups) * groups;
+        const size_t smem = static_smem ? 0 : rcp_bytes + (size_t)raster_group_bytes(res, K, threads / groups) * groups;
         TDS_REQUIRE(smem <= 227 * 1024, "raster: res=%d with %d active classes needs %zu bytes of shared memory", res, K, smem);
         if (smem > 40 * 1024) TDS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -754,13 +796,13 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
         return TDS_OK;
     };
     if (K <= 7) {
-        if (res == 64) return launch(raster_kernel<32, 64, 3>, 4, 128);
-        if (res < 64) return launch(raster_kernel<32, 0, 3>, 4, 128);
-        if (res <= 128) return launch(raster_kernel<256, 0, 3>, 1, 256);
-        return launch(raster_kernel<512, 0, 3>, 1, 512);
+        if (res == 64) return launch(raster_kernel<32, 64, 3>, 4, 128, raster_static_smem(32, 64, 3));
+        if (res < 64) return launch(raster_kernel<32, 0, 3>, 4, 128, raster_static_smem(32, 0, 3));
+        if (res <= 128) return launch(raster_kernel<256, 0, 3>, 1, 256, raster_static_smem(256, 0, 3));
+        return launch(raster_kernel<512, 0, 3>, 1, 512, raster_static_smem(512, 0, 3));
     }
-    if (res == 64) return launch(raster_kernel<32, 64, 5>, 4, 128);
-    if (res < 64) return launch(raster_kernel<32, 0, 5>, 4, 128);
-    if (res <= 128) return launch(raster_kernel<256, 0, 5>, 1, 256);
-    return launch(raster_kernel<512, 0, 5>, 1, 512);
+    if (res == 64) return launch(raster_kernel<32, 64, 5>, 4, 128, raster_static_smem(32, 64, 5));
+    if (res < 64) return launch(raster_kernel<32, 0, 5>, 4, 128, raster_static_smem(32, 0, 5));
+    if (res <= 128) return launch(raster_kernel<256, 0, 5>, 1, 256, raster_static_smem(256, 0, 5));
+    return launch(raster_kernel<512, 0, 5>, 1, 512, raster_static_smem(512, 0, 5));
 }
