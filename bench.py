@@ -211,8 +211,8 @@ def run_ours(args):
 
     # ---- this rank's shard of independent environments (weak scaling: ENVS_PER_GPU each)
     state, size, lr, actions = synth_inputs(B, A, 1000 + rank, W + K)
-    town = tds.StaticMap.from_npz(map_npz(), raster_cell=float(os.environ.get("TDS_RASTER_CELL", "8")),
-                                  offroad_cell=float(os.environ.get("TDS_OFFROAD_CELL", "4")))
+    town = tds.StaticMap.from_npz(map_npz(), raster_cell=float(os.environ.get("TDS_RASTER_CELL", "16")),
+                                  offroad_cell=float(os.environ.get("TDS_OFFROAD_CELL", "2")))
     km = tds.KinematicBicycle(left_handed=True)
     km.set_params(lr=torch.tensor(lr, device=dev))
     km.set_state(torch.tensor(state, device=dev))

@@ -1,4 +1,5 @@
-"""Raster-only timing (CUDA events, 65536 cameras at 64x64, bench inputs).  Usage: TDS_B200_LIB=... python profiles/time_raster.py [B]"""
+"""Raster timing at other tile sizes / agent counts (configs 3 and 4 of BASELINE.json).
+Usage: python profiles/time_raster_res.py RES B A [FOV]"""
 import os
 import sys
 
@@ -8,26 +9,29 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 import torchdrivesim_b200 as tds  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-A = bench.AGENTS
+RES, B, A = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+FOV = float(sys.argv[4]) if len(sys.argv) > 4 else 35.0
 dev = torch.device("cuda:0")
 state, size, lr, actions = bench.synth_inputs(B, A, 1000, 1)
-town = tds.StaticMap.from_npz(bench.map_npz(), raster_cell=float(os.environ.get("TDS_RASTER_CELL", "16")))
+town = tds.StaticMap.from_npz(bench.map_npz())
 km = tds.KinematicBicycle(left_handed=True)
 km.set_params(lr=torch.tensor(lr, device=dev))
 km.set_state(torch.tensor(state, device=dev))
 sim = tds.Simulator(town, km, torch.tensor(size, device=dev), torch.ones(B, A, dtype=torch.bool, device=dev),
                     tds.TorchDriveConfig(left_handed_coordinates=True))
-out = torch.empty(B, A, 3, bench.RES, bench.RES, device=dev)
+res = tds.Resolution(RES, RES)
+out = torch.empty(B, A, 3, RES, RES, device=dev)
 for _ in range(3):
-    sim.render_egocentric(out=out)
+    sim.render_egocentric(out=out, res=res, fov=FOV)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 10
+n = 5
 e0.record()
 for _ in range(n):
-    sim.render_egocentric(out=out)
+    sim.render_egocentric(out=out, res=res, fov=FOV)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(f"{os.environ.get('TDS_B200_LIB', 'default'):60s} render {ms:.3f} ms  ({B * A * 12 * bench.RES ** 2 / ms / 1e6:.0f} GB/s)  checksum {float(out.sum()):.1f}")
+gb = B * A * 12 * RES * RES / 1e9
+print(f"res {RES} B {B} A {A} fov {FOV}: render {ms:.3f} ms, {gb:.2f} GB out, {gb / ms * 1e3:.0f} GB/s "
+      f"({100 * gb / ms * 1e3 / 6545.3:.1f} % of measured HBM), {B * A / ms * 1e3 / 1e6:.2f} M cameras/s")

@@ -44,8 +44,8 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
         fail(TDS_ERR_INVALID_ARGUMENT, "map_create: null pointer or negative size");
         return nullptr;
     }
-    if (raster_cell <= 0.f) raster_cell = 8.0f;
-    if (offroad_cell <= 0.f) offroad_cell = 4.0f;
+    if (raster_cell <= 0.f) raster_cell = 16.0f;
+    if (offroad_cell <= 0.f) offroad_cell = 2.0f;
     for (int f = 0; f < nf; f++) {
         for (int k = 0; k < 3; k++) {
             const int v = h_faces[3 * f + k];

@@ -374,7 +374,10 @@ __device__ __forceinline__ void group_sync() {
 #endif
 // NS = bits of the per-pixel draw rank (0 = background): 3 for up to 7 active classes, 5 for up to 31
 template <int G, int RES, int NS>
-__global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB : 1) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
+#ifndef TDS_RASTER_MINB_BIG
+#define TDS_RASTER_MINB_BIG 2
+#endif
+__global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB : (G == 256 ? 2 * TDS_RASTER_MINB_BIG : TDS_RASTER_MINB_BIG)) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int GROUPS = G == 32 ? 4 : 1;
     constexpr int QN = 2 * G;

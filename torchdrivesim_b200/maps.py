@@ -23,7 +23,7 @@ class StaticMap:
 
     def __init__(self, verts: np.ndarray, faces: np.ndarray, categories: Sequence[str], vert_category: np.ndarray,
                  name: str = "map", left_handed: bool = False, stoplines: Optional[np.ndarray] = None,
-                 stopline_types: Optional[Sequence[str]] = None, raster_cell: float = 8.0, offroad_cell: float = 4.0):
+                 stopline_types: Optional[Sequence[str]] = None, raster_cell: float = 16.0, offroad_cell: float = 2.0):
         self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 2)
         self.faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
         self.categories = [str(c) for c in categories]
