@@ -66,6 +66,8 @@ def test_golden_reference_images():
     ("carla_Town01", 128, 50.0, 4, 0.2, True),
     ("carla_Town01", 256, 35.0, 0, 0.0, False),
     ("carla_Town02", 64, 100.0, 2, 0.1, True),
+    ("carla_Town02", 64, 600.0, 0, 0.0, False),      # whole town in view: > 32 grid rows per camera, sub-pixel faces
+    ("carla_Town01", 32, 20.0, 0, 0.0, True),
 ])
 def test_vs_oracle_random_scenes(mapname, res, fov, ped_every, absent_p, lights):
     rng = np.random.default_rng(res * 7 + int(fov))

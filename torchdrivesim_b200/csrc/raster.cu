@@ -465,28 +465,12 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
         r0 = max(r0, 0);
         r1 = min(r1, map.rgy - 1);
         const int nrows = min(max(r1 - r0 + 1, 0), kRows);
-        // column interval of grid row (r0 + tid) -> one contiguous record range (all classes)
-        if (tid < nrows) {
-            const int r = r0 + tid;
-            const float ylo = map.ry0 + (float)r * map.rcs - margin, yhi = map.ry0 + (float)(r + 1) * map.rcs + margin;
-            float xmin = 3.0e38f, xmax = -3.0e38f;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int j = (i + 1) & 3;
-                const float y0 = wqy[i], y1 = wqy[j], x0 = wqx[i], x1 = wqx[j];
-                if (fmaxf(y0, y1) < ylo || fminf(y0, y1) > yhi) continue;
-                float t0 = 0.f, t1 = 1.f;
-                const float dy = y1 - y0;
-                if (dy != 0.f) {
-                    float ta = (ylo - y0) / dy, tb = (yhi - y0) / dy;
-                    if (ta > tb) { const float t = ta; ta = tb; tb = t; }
-                    t0 = fmaxf(t0, ta);
-                    t1 = fminf(t1, tb);
-                }
-                const float xa = x0 + t0 * (x1 - x0), xb = x0 + t1 * (x1 - x0);
-                xmin = fminf(xmin, fminf(xa, xb));
-                xmax = fmaxf(xmax, fmaxf(xa, xb));
-            }
+        // record ranges of the touched grid rows: the columns of the quad's bounding box (with 16 m cells the quad
+        // touches 3-5 rows and columns; candidates of the few extra corner cells are rejected after ~40
+        // instructions, which is cheaper than intersecting the quad with every row - and much less code)
+        const float xmin = fminf(fminf(wqx[0], wqx[1]), fminf(wqx[2], wqx[3])), xmax = fmaxf(fmaxf(wqx[0], wqx[1]), fmaxf(wqx[2], wqx[3]));
+        for (int ri = tid; ri < nrows; ri += G) {
+            const int r = r0 + ri;
             int st = 0, cnt = 0;
             if (xmin <= xmax) {
                 const int c0 = max((int)floorf((xmin - margin - map.rx0) * map.rinv), 0);
@@ -496,8 +480,8 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                     cnt = map.rcell[r * map.rgx + c1 + 1] - st;
                 }
             }
-            ssts(start_sa + 4u * tid, (uint32_t)st);
-            ssts(count_sa + 4u * tid, (uint32_t)cnt);
+            ssts(start_sa + 4u * ri, (uint32_t)st);
+            ssts(count_sa + 4u * ri, (uint32_t)cnt);
         }
         group_sync<G>();
 
