@@ -107,6 +107,20 @@ int tds_collision_allpairs_bwd(const float* d_ego_box, const float* d_all_box, c
                                float* d_grad_all, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Traffic-light violations.  Replaces TrafficLightControl.compute_violation (traffic_controls.py:152-178)
+ * with box2corners_with_rear_factor (_iou_utils.py:302-341) and the mask of
+ * Simulator.compute_traffic_lights_violations (simulator.py:1046-1062):
+ *   out[b,a] = present[b,a] and any over lights l of ( state[b,l] == red_state and
+ *              area( rear `rear_factor` part of box[b,a]  intersected with  stop line l ) > 0 ).
+ *   d_agent_box [B,A,5] (x, y, length, width, psi); d_tl_corners [B,L,4,2] in the corner order of
+ *   box2corners_th (masked controls have all corners equal); d_tl_state [B,L] int32; d_present [B,A] uint8 or NULL;
+ *   d_out [B,A] uint8.
+ * ---------------------------------------------------------------------------------------- */
+int tds_traffic_light_violation(const float* d_agent_box, const float* d_tl_corners, const int32_t* d_tl_state,
+                                const uint8_t* d_present, int32_t B, int32_t A, int32_t L, int32_t red_state,
+                                float rear_factor, uint8_t* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Static map: triangle mesh + uniform grids, built once per map per GPU.  Replaces the
  * per-camera / per-corner expansion of the mesh (mesh.py:1147-1157, infractions.py:219-226).
  * ---------------------------------------------------------------------------------------- */

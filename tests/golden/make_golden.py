@@ -174,7 +174,33 @@ def golden_offroad():
     print("offroad: nonzero", int((off05 > 0).sum()), "of", A, "max", float(off05.max()))
 
 
+def golden_traffic():
+    """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
+    simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
+    gen = torch.Generator().manual_seed(505)
+    B, A = 4, 64
+    present = torch.rand(B, A, generator=gen) > 0.15
+    sim, cfgm = make_sim("carla_Town01", B, A, gen, with_lights=True, present=present)
+    tl = sim.get_traffic_controls()["traffic_light"]
+    L = tl.pos.shape[1]
+    tl.set_state(torch.where(torch.rand(B, L, generator=gen) < 0.5, torch.zeros(B, L, dtype=torch.long), tl.state))
+    st = sim.get_state().clone()
+    pick = torch.randint(0, L, (B, A), generator=gen)
+    centre = torch.gather(tl.pos[..., :2], 1, pick.unsqueeze(-1).expand(-1, -1, 2))
+    st[..., :2] = centre + 2.0 * torch.randn(B, A, 2, generator=gen)        # within a car length of a stop line
+    st[:, ::5, :2] = centre[:, ::5]                                         # some exactly on it
+    sim.set_state(st)
+    viol = sim.compute_traffic_lights_violations()
+    box = torch.cat([st[..., :2], sim.get_agent_size()[..., :2], st[..., 2:3]], -1)
+    raw = tl.compute_violation(box)
+    np.savez_compressed(os.path.join(HERE, "traffic.npz"), agent_box=box.numpy(), present=present.numpy(),
+                        tl_corners=tl.corners.numpy(), tl_state=tl.state.numpy(), red_index=tl.allowed_states.index("red"),
+                        rear_factor=tl.violation_rear_factor, violation_raw=raw.numpy(),
+                        violation=np.asarray(viol.numpy() != 0))
+    print("traffic: violations", int(raw.sum()), "of", B * A, "red lights", int((tl.state == 0).sum()), "of", B * L)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic"]
     for w in which:
         globals()["golden_" + w]()

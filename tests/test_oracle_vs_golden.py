@@ -78,3 +78,14 @@ def test_category_ranks_follow_levels():
     r = R.category_ranks()
     assert r["road"] < r["right_lane"] < r["left_lane"] < r["traffic_light_green"] < r["traffic_light_red"] \
         < r["pedestrian"] < r["vehicle"] < r["direction"]
+
+
+def test_traffic_light_violation_oracle_matches_reference():
+    """oracle/traffic.py against TrafficLightControl.compute_violation of the unmodified reference."""
+    from oracle import traffic
+    g = util.golden("traffic")
+    raw = traffic.tl_violation(g["agent_box"], g["tl_corners"], g["tl_state"], int(g["red_index"]), float(g["rear_factor"]))
+    assert raw.sum() > 20 and np.array_equal(raw, g["violation_raw"])
+    masked = traffic.tl_violation(g["agent_box"], g["tl_corners"], g["tl_state"], int(g["red_index"]),
+                                  float(g["rear_factor"]), g["present"])
+    assert np.array_equal(masked, g["violation"])

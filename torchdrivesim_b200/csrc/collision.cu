@@ -109,8 +109,8 @@ __device__ __forceinline__ int clip_axis(const float* px, const float* py, int n
     return m;
 }
 
-__device__ float iou_pair(const Box& p, const Box& q) {
-    const float a1 = p.l * p.w, a2 = q.l * q.w;
+// intersection area of two oriented boxes: q is clipped against p in p's frame (Sutherland-Hodgman)
+__device__ float inter_area(const Box& p, const Box& q) {
     // bounding-circle early out: exact 0 in the reference for disjoint boxes
     const float dx = q.x - p.x, dy = q.y - p.y;
     const float rp = 0.5f * sqrtf(p.l * p.l + p.w * p.w), rq = 0.5f * sqrtf(q.l * q.l + q.w * q.w);
@@ -142,9 +142,52 @@ __device__ float iou_pair(const Box& p, const Box& q) {
         const int j = (i + 1 == n) ? 0 : i + 1;
         tot += px[i] * py[j] - py[i] * px[j];
     }
-    const float inter = 0.5f * fabsf(tot);
+    return 0.5f * fabsf(tot);
+}
+
+__device__ float iou_pair(const Box& p, const Box& q) {
+    const float a1 = p.l * p.w, a2 = q.l * q.w;
+    const float inter = inter_area(p, q);
+    if (inter == 0.0f) return 0.0f;
     const float iou = inter / (a1 + a2 - inter);
     return iou == iou ? iou : 0.0f;               // nan_to_num, simulator.py:1103
+}
+
+// ---- traffic-light violations (TrafficLightControl.compute_violation, traffic_controls.py:152-178): an agent
+// violates iff some RED light's stop-line rectangle overlaps, with positive area, the rear `rear_factor` part of
+// the agent's box (box2corners_with_rear_factor, _iou_utils.py:302-341).  One thread per agent, L lights each.
+__global__ void __launch_bounds__(128) tl_violation_kernel(const float* __restrict__ agent_box, const float* __restrict__ tl_corners,
+                                                           const int32_t* __restrict__ tl_state, const uint8_t* __restrict__ present,
+                                                           int B, int A, int L, int red, float rear, uint8_t* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (int64_t)B * A) return;
+    const int b = (int)(g / A);
+    const float* ab = agent_box + g * 5;
+    Box p = make_box(ab[0], ab[1], ab[2], ab[3], ab[4]);
+    const float shift = (p.l * (1.0f - rear)) / 2.0f;          // centre of the rear part, along the heading
+    p.x = p.x - shift * p.c;
+    p.y = p.y - shift * p.s;
+    p.l = p.l * rear;
+    bool hit = false;
+    if (!present || present[g]) {
+        for (int l = 0; l < L && !hit; l++) {
+            if (tl_state[(int64_t)b * L + l] != red) continue;
+            // stop-line rectangle from its corners (+,+), (-,+), (-,-), (+,-)  (box2corners_th)
+            const float* c = tl_corners + ((int64_t)b * L + l) * 8;
+            const float ex = c[0] - c[2], ey = c[1] - c[3];        // corner0 - corner1 = length * (cos, sin)
+            const float fx = c[0] - c[6], fy = c[1] - c[7];        // corner0 - corner3 = width * (-sin, cos)
+            Box q;
+            q.l = sqrtf(ex * ex + ey * ey);
+            q.w = sqrtf(fx * fx + fy * fy);
+            if (!(q.l > 0.0f) || !(q.w > 0.0f)) continue;          // masked / degenerate control: no area
+            q.x = 0.5f * (c[0] + c[4]);
+            q.y = 0.5f * (c[1] + c[5]);
+            q.c = ex / q.l;
+            q.s = ey / q.l;
+            hit = inter_area(p, q) > 0.0f;
+        }
+    }
+    out[g] = hit ? 1 : 0;
 }
 
 // ---- IoU backward.  d(intersection area) is the boundary integral of the normal velocity: every edge of
@@ -452,6 +495,22 @@ __global__ void __launch_bounds__(kWarps * 32) allpairs_bwd_kernel(const float* 
 }
 
 }  // namespace
+
+extern "C" int tds_traffic_light_violation(const float* d_agent_box, const float* d_tl_corners, const int32_t* d_tl_state,
+                                           const uint8_t* d_present, int32_t B, int32_t A, int32_t L, int32_t red_state,
+                                           float rear_factor, uint8_t* d_out, void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0 && L >= 0, "traffic_light_violation: negative size");
+    if (B == 0 || A == 0) return TDS_OK;
+    TDS_REQUIRE(d_agent_box && d_out, "traffic_light_violation: null pointer");
+    TDS_REQUIRE(L == 0 || (d_tl_corners && d_tl_state), "traffic_light_violation: null traffic light tensors");
+    TDS_REQUIRE(rear_factor > 0.0f && rear_factor <= 1.0f, "traffic_light_violation: rear_factor must be in (0, 1]");
+    const int64_t n = (int64_t)B * A;
+    tl_violation_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_agent_box, d_tl_corners, d_tl_state,
+                                                                                   d_present, B, A, L, red_state,
+                                                                                   rear_factor, d_out);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
 
 extern "C" int tds_collision_pairwise_fwd(const float* d_box1, const float* d_box2, int64_t p, int32_t metric,
                                           float* d_out, void* stream) {

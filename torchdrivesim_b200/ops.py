@@ -143,6 +143,28 @@ def collision_allpairs(ego_box: torch.Tensor, all_box: torch.Tensor, mask: torch
     return _AllPairs.apply(ego_box, all_box, mask, metric, ego_is_prefix)
 
 
+# ------------------------------------------------------------------------------------ traffic lights
+def traffic_light_violation(agent_box: torch.Tensor, tl_corners: torch.Tensor, tl_state: torch.Tensor, red_state: int,
+                            rear_factor: float = 0.1, present: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """agent_box [B,A,5], tl_corners [B,L,4,2], tl_state [B,L] -> bool [B,A]
+    (TrafficLightControl.compute_violation, traffic_controls.py:152-178; not differentiable, as the reference)."""
+    lib = _lib.load()
+    box = _lib.as_f32(agent_box)
+    if box.dim() != 3 or box.shape[-1] != 5:
+        raise _lib.TdsError("traffic_light_violation: agent_box must be [B,A,5]")
+    B, A = box.shape[0], box.shape[1]
+    L = tl_corners.shape[1]
+    if tl_corners.shape[0] != B or tuple(tl_corners.shape[2:]) != (4, 2) or tuple(tl_state.shape) != (B, L):
+        raise _lib.TdsError("traffic_light_violation: tl_corners must be [B,L,4,2] and tl_state [B,L]")
+    out = torch.zeros(B, A, dtype=torch.uint8, device=box.device)
+    cor = _lib.as_f32(tl_corners) if L > 0 else None
+    st = _lib.as_i32(tl_state.to(box.device)) if L > 0 else None
+    p = None if present is None else _lib.as_u8(present)
+    _lib.check(lib.tds_traffic_light_violation(_lib.ptr(box), _lib.ptr(cor), _lib.ptr(st), _lib.ptr(p), B, A, L,
+                                               int(red_state), float(rear_factor), _lib.ptr(out), _lib.stream_ptr(box.device)))
+    return out.view(torch.bool)
+
+
 # ------------------------------------------------------------------------------------ offroad
 class _Offroad(torch.autograd.Function):
     @staticmethod

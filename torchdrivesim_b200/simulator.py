@@ -255,6 +255,17 @@ class Simulator:
         return ops.offroad(self.get_state(), self.get_agent_size(), self.road_mesh, self.cfg.offroad_threshold,
                            self.get_present_mask())
 
+    def compute_traffic_lights_violations(self) -> Tensor:
+        """simulator.py:1046-1062: which agents run a red light (TrafficLightControl.compute_violation) times the
+        present mask; boolean BxA."""
+        state = self.get_state()
+        tl = self.traffic_controls.get('traffic_light') if self.traffic_controls is not None else None
+        if tl is None:
+            return torch.zeros(state.shape[0], state.shape[1], dtype=torch.bool, device=state.device)
+        box = torch.cat([state[..., :2], self.get_agent_size()[..., :2], state[..., 2:3]], dim=-1)
+        return ops.traffic_light_violation(box, tl.corners, tl.state, tl.allowed_states.index('red'),
+                                           tl.violation_rear_factor, present=self.get_present_mask())
+
     def compute_collision(self) -> Tensor:
         """simulator.py:1161-1194 for the `discs` and `iou` metrics, all agents in one launch."""
         state, size = self.get_state(), self.get_agent_size()[..., :2]

@@ -2,8 +2,9 @@
 
 Data-only mirror of torchdrivesim/traffic_controls.py:12-178 (`BaseTrafficControl`,
 `TrafficLightControl`): `pos` [B,L,5], `corners` [B,L,4,2] (masked ones at -1000), `state` [B,L],
-`replay_states` [B,L,T], `step(time)`, `extend`, `select_batch_elements`, `to`, `copy`.  Violations
-(`compute_violation`) are a "next" row of the scope table and are not implemented here.
+`replay_states` [B,L,T], `step(time)`, `extend`, `select_batch_elements`, `to`, `copy`, and
+`TrafficLightControl.compute_violation` (traffic_controls.py:152-178) on the GPU through
+`tds_traffic_light_violation`.
 """
 from typing import List, Optional
 
@@ -75,6 +76,11 @@ class BaseTrafficControl:
     def compute_state(self, time: int) -> Tensor:
         return self.state
 
+    def compute_violation(self, agent_state: Tensor) -> Tensor:
+        """BxAx5 (x, y, length, width, psi) -> BxA bool; the base class reports no violations
+        (traffic_controls.py:137-149)."""
+        return torch.zeros(agent_state.shape[0], agent_state.shape[1], dtype=torch.bool, device=agent_state.device)
+
     def step(self, time: int) -> None:
         if time < self.total_replay_time:
             self.set_state(self.replay_states[..., time])
@@ -83,9 +89,18 @@ class BaseTrafficControl:
 
 
 class TrafficLightControl(BaseTrafficControl):
+    violation_rear_factor = 0.1
+
     @classmethod
     def _default_allowed_states(cls) -> List[str]:
         return ['red', 'yellow', 'green']
+
+    def compute_violation(self, agent_state: Tensor) -> Tensor:
+        """An agent violates a light iff the light is red and the rear 10 % of its box overlaps the stop line
+        (traffic_controls.py:162-178)."""
+        from . import ops
+        return ops.traffic_light_violation(agent_state, self.corners, self.state, self.allowed_states.index('red'),
+                                           self.violation_rear_factor)
 
 
 class StopSignControl(BaseTrafficControl):
