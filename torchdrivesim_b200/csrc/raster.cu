@@ -285,18 +285,13 @@ __device__ __forceinline__ void or_span(uint32_t plane, int res, int y, int lo, 
     }
 }
 
-// 64-pixel rows: the two 32-bit halves of a row mask, each OR-ed only when non-zero (predicated red.shared, no branch)
+// 64-pixel rows: the two 32-bit halves of a row mask.  Both are OR-ed unconditionally: ptxas turns a predicated
+// red.shared into a branch around it (ISETP, BSSY, BRA, BSYNC), which costs more issue slots than the idle OR of a
+// zero (the LSU pipe is 14 % busy, the issue slots 77 %).
 __device__ __forceinline__ void or_mask64(uint32_t plane, int y, unsigned long long m) {
-    const uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
     const uint32_t addr = plane + 4u * (uint32_t)y;
-    asm volatile(
-        "{\n\t.reg .pred p0, p1;\n\t"
-        "setp.ne.u32 p0, %1, 0;\n\t"
-        "setp.ne.u32 p1, %2, 0;\n\t"
-        "@p0 red.shared.or.b32 [%0], %1;\n\t"
-        "@p1 red.shared.or.b32 [%0+256], %2;\n\t}"
-        ::"r"(addr), "r"(m0), "r"(m1)
-        : "memory");
+    sred_or(addr, (uint32_t)m);
+    sred_or(addr + 256u, (uint32_t)(m >> 32));
 }
 
 // stage 2a: a triangle with all vertices inside the image: one interval and one atomic OR per row and word
