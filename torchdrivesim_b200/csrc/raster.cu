@@ -541,11 +541,14 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 int xy[6];
                 if (plane >= 0) kind = setup_triangle<POW2>(cam, x0, y0, x1, y1, x2, y2, own, xy);
                 if (kind == kVerts) {
+                    // a vertex outside the image ORs a zero into pixel (0, 0): no branch around the reduction
                     const uint32_t pl = planes_sa + (uint32_t)plane * plane_bytes;
 #pragma unroll
-                    for (int k = 0; k < 3; k++)
-                        if ((unsigned)xy[2 * k] < (unsigned)res && (unsigned)xy[2 * k + 1] < (unsigned)res)
-                            or_bit(pl, res, xy[2 * k], xy[2 * k + 1]);
+                    for (int k = 0; k < 3; k++) {
+                        const bool in = (unsigned)xy[2 * k] < (unsigned)res && (unsigned)xy[2 * k + 1] < (unsigned)res;
+                        const int x = in ? xy[2 * k] : 0, y = in ? xy[2 * k + 1] : 0;
+                        sred_or(pl + 4u * (uint32_t)((x >> 5) * res + y), in ? 1u << (x & 31) : 0u);
+                    }
                 } else if (kind == kHuge) {
                     draw_huge(planes_sa + (uint32_t)plane * plane_bytes, res, xy[0], xy[1], xy[2], xy[3], xy[4], xy[5]);
                 }
