@@ -236,7 +236,28 @@ struct FastTri {
     FastEdge tb, s, mb;      // long edge, current short edge (T-M until the middle row), M-B
     int ty, my, by;
     int xa, dTB, xb, dS, xM, dMB;   // fill: both ends carry the +0.5 rounding bias
+    int eL, eH;              // run of T-M in its LAST row (the middle row), precomputed: the row loop never steps
+                             // T-M there, it only switches to M-B
 };
+
+// run of the edge top (px,py) -> bottom (qx,qy) in its last row qy, in closed form
+template <class RcpFn>
+TDS_HD void fast_edge_last_run(int px, int py, int qx, int qy, int& lo, int& hi, RcpFn&& rcp_of) {
+    const int dy = qy - py, dxs = qx - px;
+    const int dx = dxs >= 0 ? dxs : -dxs;
+    const int lx = dxs >= 0 ? px : qx;
+    if (dy == 0) { lo = lx; hi = lx + dx; return; }            // horizontal: the whole edge
+    if (dx < dy) { lo = hi = qx; return; }                      // y-major: one pixel per row, the endpoint
+    // x-major: row offset r from the LEFT endpoint holds [G(r), G(r+1) - 1], G(r) = mulhi(2 dx r - dx + 2 dy, rcp)
+    const uint32_t rcp = rcp_of(dy);
+    if (dxs >= 0) {         // the bottom endpoint is the right one: last row r = dy -> [G(dy), dx]
+        lo = lx + (int)mulhi_u32((uint32_t)(2 * dx * dy - dx + 2 * dy), rcp);
+        hi = lx + dx;
+    } else {                // the bottom endpoint is the left one: last row r = 0 -> [0, G(1) - 1]
+        lo = lx;
+        hi = lx + (int)mulhi_u32((uint32_t)(dx + 2 * dy), rcp) - 1;
+    }
+}
 
 template <bool SMALL, class RcpFn>
 TDS_HD void fast_tri_setup(int x0, int y0, int x1, int y1, int x2, int y2, FastTri& t, RcpFn&& rcp_of) {
@@ -247,6 +268,7 @@ TDS_HD void fast_tri_setup(int x0, int y0, int x1, int y1, int x2, int y2, FastT
     fast_edge_setup(tx, ty, bx, by, t.tb, rcp_of);
     fast_edge_setup(tx, ty, mx, my, t.s, rcp_of);
     fast_edge_setup(mx, my, bx, by, t.mb, rcp_of);
+    fast_edge_last_run(tx, ty, mx, my, t.eL, t.eH, rcp_of);
     t.ty = ty; t.my = my; t.by = by;
     if (SMALL) {
         t.dTB = by > ty ? edge_dx_rcp(bx - tx, by - ty, t.tb.rcp) : 0;
@@ -269,14 +291,14 @@ TDS_HD void fast_tri_rows(FastTri& t, Emit&& emit) {
 #pragma unroll 1
 #endif
     for (int y = t.ty; y <= t.by; y++) {
-        int eL = 0x7fffffff, eH = -1;
-        if (y == t.my) {
-            // last row of T-M, then M-B takes over (its first row is this one)
-            fast_edge_step(t.s, eL, eH);
+        const bool mid = y == t.my;
+        if (mid) {
+            // M-B takes over (its first row is this one); the last row of T-M was computed at set-up
             t.s = t.mb;
             t.xb = t.xM;
             t.dS = t.dMB;
         }
+        const int eL = mid ? t.eL : 0x7fffffff, eH = mid ? t.eH : -1;
         int l1, h1, l2, h2;
         fast_edge_step(t.tb, l1, h1);
         fast_edge_step(t.s, l2, h2);
