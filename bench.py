@@ -152,7 +152,7 @@ class ClockSampler:
     background thread; falls back to polling `nvidia-smi` when NVML cannot be imported."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         self.index, self.period, self.rows, self.stop_flag, self.thread, self.err = index, period, [], False, None, None
 
     def _loop(self):
@@ -289,7 +289,9 @@ def run_ours(args):
     barrier()
     t_wall1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    # clocks under load: the samples of the timed region plus the identical warm-up spin right before it (the
+    # timed region alone lasts ~30 ms, i.e. one or two NVML samples)
+    clocks = sampler.stop(t_spin, t_wall1) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
