@@ -184,6 +184,8 @@ int64_t tds_raster_workspace_bytes(int32_t B, int32_t N, int32_t L, int32_t R);
  *   d_present [B,N] uint8, or [B,Nc,N] when present_per_camera != 0 (rendering_mask)
  *   d_tl_corners [B,L,4,2], d_tl_state [B,L] int32 (L may be 0)
  *   d_rect_corners [B,R,4,2], d_rect_class [B,R] int32: extra rectangles (stop / yield signs)
+ *   d_cam_tris [B,Nc,Tc,3,2], d_cam_tri_class [B,Nc,Tc] int32 (< 0: skipped): world-space triangles seen by ONE
+ *       camera each - the goal-waypoint discs of generate(waypoints=...), mesh.py:1120-1145 (Tc may be 0)
  *   scale = 2 / fov, res = H = W (square only, as the reference)
  *   d_out [B,Nc,3,res,res] float32 in [0,255]
  *   d_workspace: tds_raster_workspace_bytes(B,N,L,R) bytes, required even when N = L = R = 0 */
@@ -194,6 +196,7 @@ int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps, const int3
                         const uint8_t* d_present, int32_t present_per_camera,
                         const float* d_tl_corners, const int32_t* d_tl_state, int32_t L,
                         const float* d_rect_corners, const int32_t* d_rect_class, int32_t R,
+                        const float* d_cam_tris, const int32_t* d_cam_tri_class, int32_t Tc,
                         const tds_palette_t* palette, float scale, int32_t res,
                         float* d_out, void* d_workspace, void* stream);
 

@@ -97,6 +97,21 @@ def box_corners(box: np.ndarray) -> np.ndarray:
     return np.stack([X + x, Y + y], -1).astype(f32)
 
 
+def disc_template(radius: float = 2.0, num_triangles: int = 10):
+    """The waypoint disc of generate_disc_mesh (mesh.py:1243-1271): centre + rim vertices produced by REPEATED
+    rotation of (radius, 0) with torch.matmul (utils.py:36-69), faces (0, k, k+1) and finally (0, n, 1).
+    Evaluated with the same ATen ops as the reference (the accumulated fp32 rounding is part of the result)."""
+    import torch
+    step = torch.deg2rad(torch.tensor([[360 / num_triangles]], dtype=torch.float32))
+    c, s = torch.cos(step), torch.sin(step)
+    rot = torch.stack([torch.cat([c, -s], -1), torch.cat([s, c], -1)], -2)
+    verts = [torch.zeros(1, 2), torch.tensor([[radius, 0.0]], dtype=torch.float32)]
+    for _ in range(num_triangles - 1):
+        verts.append(torch.matmul(rot, verts[-1].unsqueeze(-1)).squeeze(-1))
+    faces = [[0, k, k + 1] for k in range(1, num_triangles)] + [[0, num_triangles, 1]]
+    return torch.cat(verts, 0).numpy().astype(f32), np.array(faces, np.int32)
+
+
 def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_cat: Sequence[str],
                 agent_state: Optional[np.ndarray] = None, agent_size: Optional[np.ndarray] = None,
                 agent_type_names: Optional[List[str]] = None, agent_types: Optional[np.ndarray] = None,
@@ -104,13 +119,17 @@ def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_
                 tl_corners: Optional[np.ndarray] = None, tl_state: Optional[np.ndarray] = None,
                 tl_allowed_states: Sequence[str] = ("red", "yellow", "green"),
                 static_controls: Optional[Dict[str, np.ndarray]] = None,
-                levels: Dict[str, float] = None, colors: Dict[str, Tuple[int, int, int]] = None) -> Scene:
+                levels: Dict[str, float] = None, colors: Dict[str, Tuple[int, int, int]] = None,
+                waypoints: Optional[np.ndarray] = None, waypoints_mask: Optional[np.ndarray] = None) -> Scene:
     """Restates generate() for one environment and one rendering mask.
 
     static_face_cat: per static face category NAME (the category of its first vertex, cv2.py:58).
     present: [N] bool rendering mask; absent agents collapse to a degenerate triangle at actor
     vertex 0 with agent 0's colour / level (mesh.py:1083-1089).
-    Concatenation order (mesh.py:1147-1157): background, actors, static controls, traffic lights.
+    Concatenation order (mesh.py:1147-1157): background, actors, static controls, traffic lights, waypoints.
+    waypoints [M,2] (+ mask [M]) are those of ONE camera (mesh.py:1120-1145): a disc per waypoint, translated (the
+    pose has psi = 0, so the rotation is the identity); the faces of a masked waypoint collapse onto vertex 0 of the
+    camera's waypoint mesh, the centre of its first waypoint.
     """
     levels = DEFAULT_LEVELS if levels is None else levels
     colors = DEFAULT_COLORS if colors is None else colors
@@ -149,6 +168,16 @@ def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_
             faces.append(np.array([[nv, nv + 1, nv + 3], [nv + 1, nv + 3, nv + 2]], np.int32))
             cats += ["traffic_light_" + tl_allowed_states[int(tl_state[k])]] * 2
             nv += 4
+    if waypoints is not None and len(waypoints) > 0:
+        waypoints = np.asarray(waypoints, f32).reshape(-1, 2)
+        wmask = np.ones(len(waypoints), bool) if waypoints_mask is None else np.asarray(waypoints_mask, bool)
+        dv, df = disc_template()
+        first = nv
+        for k in range(waypoints.shape[0]):
+            verts.append((dv + waypoints[k][None]).astype(f32))
+            faces.append((df + nv) if wmask[k] else np.full_like(df, first))
+            cats += ["goal_waypoint"] * df.shape[0]
+            nv += dv.shape[0]
     verts = np.concatenate(verts, 0).astype(f32)
     faces = np.concatenate(faces, 0).astype(np.int32)
     lut = {c: quantize_color(colors[c]) for c in set(cats)}

@@ -174,6 +174,31 @@ def golden_offroad():
     print("offroad: nonzero", int((off05 > 0).sum()), "of", A, "max", float(off05.max()))
 
 
+def golden_waypoints():
+    """Goal-waypoint discs in the birdview (mesh.py:1120-1145, 1243-1271): M waypoints per camera with a mask."""
+    gen = torch.Generator().manual_seed(606)
+    B, A, M, res, fov = 2, 5, 3, 64, 35.0
+    sim, cfgm = make_sim("carla_Town01", B, A, gen)
+    st = sim.get_state().clone()
+    st[:, 1:, :2] = st[:, :1, :2] + 8.0 * torch.randn(B, A - 1, 2, generator=gen)
+    sim.set_state(st)
+    wp = st[:, :, None, :2] + 12.0 * torch.randn(B, A, M, 2, generator=gen)            # around every camera
+    wp[0, 0, 0] = st[0, 0, :2] + torch.tensor([16.5, 0.0])                             # one cut by the image border
+    mask = torch.rand(B, A, M, generator=gen) > 0.3
+    mask[0, 1] = False                                                                  # all masked for one camera
+    img = sim.render(st[..., :2], st[..., 2:3], res=Resolution(res, res), fov=fov, waypoints=wp,
+                     waypoints_rendering_mask=mask)
+    img = img.reshape(B, A, 3, res, res)
+    assert float((img - img.round()).abs().max()) == 0.0
+    tl = sim.traffic_controls["traffic_light"]
+    np.savez_compressed(os.path.join(HERE, "render_waypoints.npz"), map="carla_Town01", state=st.numpy(),
+                        size=sim.get_agent_size().numpy(), tl_state=tl.state.numpy(), tl_corners=tl.corners.numpy(),
+                        waypoints=wp.numpy(), waypoints_mask=mask.numpy(), res=res, fov=fov,
+                        image=img.numpy().astype(np.uint8))
+    goal = np.array([139, 64, 0]) * 0.999
+    print("waypoints: image", img.shape, "goal-coloured px", int((img[:, :, 0] == np.floor(goal[0] / 255 * 256)).sum()))
+
+
 def golden_traffic():
     """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
     simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
@@ -201,6 +226,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints"]
     for w in which:
         globals()["golden_" + w]()

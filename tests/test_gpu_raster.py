@@ -174,3 +174,49 @@ def test_full_size_sampled_cameras_and_determinism():
                                    bench.FOV, cams=cams)
     bad = sum(int((img[b, c].cpu().numpy() != o).any(0).sum()) for (b, c), o in ora.items())
     assert bad == 0, f"{bad} mismatching pixels over {len(ora)} sampled cameras"
+
+
+def test_goal_waypoints_golden_and_oracle():
+    """Goal-waypoint discs per camera with a rendering mask (BirdviewRGBMeshGenerator.generate(waypoints=...),
+    mesh.py:1120-1145): images of the unmodified reference, then a larger random case against the oracle at 128x128."""
+    import torchdrivesim_b200 as tds
+    dev = torch.device("cuda:0")
+
+    def render(mapname, st, size, tl_corners, tl_state, wp, mask, res, fov):
+        B, A = st.shape[:2]
+        town = tds.StaticMap.from_npz(util.map_path(mapname))
+        km = tds.KinematicBicycle(left_handed=True)
+        km.set_params(lr=torch.full((B, A), util.VEH[2], device=dev))
+        km.set_state(torch.as_tensor(st, device=dev))
+        tc = None
+        if tl_corners is not None:
+            tl = tds.TrafficLightControl(pos=torch.zeros(B, tl_corners.shape[1], 5, device=dev))
+            tl.corners = torch.as_tensor(tl_corners, device=dev)
+            tl.set_state(torch.as_tensor(tl_state, device=dev))
+            tc = {"traffic_light": tl}
+        sim = tds.Simulator(town, km, torch.as_tensor(size, device=dev), torch.ones(B, A, dtype=torch.bool, device=dev),
+                            tds.TorchDriveConfig(left_handed_coordinates=True), traffic_controls=tc)
+        s = sim.get_state()
+        img = sim.render(s[..., :2], s[..., 2:3], res=tds.Resolution(res, res), fov=fov,
+                         waypoints=torch.as_tensor(wp, device=dev), waypoints_rendering_mask=torch.as_tensor(mask, device=dev))
+        torch.cuda.synchronize()
+        return img.cpu().numpy()
+
+    g = util.golden("render_waypoints")
+    img = render(str(g["map"]), g["state"], g["size"], g["tl_corners"], g["tl_state"], g["waypoints"], g["waypoints_mask"],
+                 int(g["res"]), float(g["fov"]))
+    ref = g["image"].astype(np.float32)
+    assert int((img != ref).any(2).sum()) == 0
+    assert (ref[:, :, 0] == 139).sum() > 100            # the goal colour is really there
+
+    rng = np.random.default_rng(21)
+    m = util.load_map_np("carla_Town02")
+    B, A, M = 2, 6, 4
+    state, size, types, present = util.random_scene(m, B, A, rng)
+    wp = (state[:, :, None, :2] + rng.normal(0, 25, (B, A, M, 2))).astype(np.float32)
+    mask = rng.uniform(size=(B, A, M)) > 0.3
+    img = render("carla_Town02", state, size, None, None, wp, mask, 128, 60.0)
+    cam_sc = _sincos_torch(state[..., 2])
+    ora = util.oracle_render_batch(m, state, size, types, np.ones((B, A), bool), ["vehicle"], None, None,
+                                   state[..., :2].copy(), cam_sc, 128, 60.0, waypoints=wp, waypoints_mask=mask)
+    assert sum(int((img[b, c] != o).any(0).sum()) for (b, c), o in ora.items()) == 0

@@ -99,9 +99,31 @@ def test_generator_rejects_unsupported_inputs():
     with pytest.raises(tds._lib.TdsError):
         gen.generate(3, agent_state=per_cam, present_mask=None)
     with pytest.raises(NotImplementedError):
-        gen.generate(1, agent_state=st[:, None], waypoints=torch.zeros(4, 1, 2, 2))
+        gen.generate(1, agent_state=st[:, None], custom_agent_colors=torch.zeros(4, 1, 6, 3))
+    with pytest.raises(tds._lib.TdsError):
+        gen.generate(1, agent_state=st[:, None], waypoints=torch.zeros(4, 2, 2, 2))          # Nc mismatch
     big = gen.expand(2)
     assert big.agent_size.shape[0] == 8 and big.world_center.shape[0] == 8
+
+
+def test_waypoint_triangles_follow_the_reference_layout():
+    """generate(waypoints=...) (mesh.py:1120-1145): 10-face discs of radius 2 m, masked ones collapse onto the centre of
+    the camera's first waypoint; the disc template equals the oracle's restatement of generate_disc_mesh."""
+    from oracle import raster as R
+    sim = _sim(lights=False)
+    gen = sim.birdview_mesh_generator
+    B = sim.batch_size
+    wp = torch.arange(B * 2 * 3 * 2, dtype=torch.float32).reshape(B, 2, 3, 2)
+    mask = torch.ones(B, 2, 3, dtype=torch.bool)
+    mask[0, 1, 2] = False
+    tris, cls = gen._waypoint_triangles(2, wp, mask)
+    assert tris.shape == (B, 2, 30, 3, 2) and cls.shape == (B, 2, 30) and cls.dtype == torch.int32
+    dv, df = R.disc_template()
+    assert np.array_equal(tris[1, 0, :10].numpy(), (dv + wp[1, 0, 0].numpy())[df])
+    assert np.array_equal(tris[0, 1, 20:].numpy(), np.broadcast_to(wp[0, 1, 0].numpy(), (10, 3, 2)))
+    scene = gen.generate(2, agent_state=sim.get_state()[:, None].expand(-1, 2, -1, -1), waypoints=wp,
+                         waypoints_rendering_mask=mask)
+    assert scene.cam_tris.shape == (B, 2, 30, 3, 2) and scene.slice(1, 3).cam_tri_class.shape[0] == 2
 
 
 def test_fit_action_inverts_the_oracle_step():

@@ -74,6 +74,21 @@ def test_render_pixel_exact():
     assert total == 12 + 5 + 6 + 2
 
 
+def test_render_waypoints_pixel_exact():
+    """Goal-waypoint discs per camera with a rendering mask (mesh.py:1120-1145) against the unmodified reference."""
+    g = util.golden("render_waypoints")
+    m = util.load_map_np(str(g["map"]))
+    st = g["state"]
+    B, A = st.shape[:2]
+    cam_sc = torch.stack([torch.sin(torch.tensor(st[..., 2])), torch.cos(torch.tensor(st[..., 2]))], -1).numpy()
+    ora = util.oracle_render_batch(m, st, g["size"], np.zeros((B, A), np.int64), np.ones((B, A), bool), ["vehicle"],
+                                   g["tl_corners"], g["tl_state"], st[..., :2], cam_sc, int(g["res"]), float(g["fov"]),
+                                   waypoints=g["waypoints"], waypoints_mask=g["waypoints_mask"])
+    for (b, c), img in ora.items():
+        assert np.array_equal(img, g["image"][b, c].astype(np.float32)), f"camera {(b, c)}"
+    assert len(ora) == B * A
+
+
 def test_category_ranks_follow_levels():
     r = R.category_ranks()
     assert r["road"] < r["right_lane"] < r["left_lane"] < r["traffic_light_green"] < r["traffic_light_red"] \

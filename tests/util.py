@@ -56,7 +56,7 @@ def tl_tensors(m, B, rng):
 
 
 def oracle_render_batch(m, state, size, types, present, type_names, tl_corners, tl_state, cam_xy, cam_sc, res, fov,
-                        cams=None):
+                        cams=None, waypoints=None, waypoints_mask=None):
     """Oracle images for the cameras in `cams` (list of (b, c)); present [B,N] or [B,Nc,N]."""
     from oracle import raster as R
     out = {}
@@ -65,7 +65,9 @@ def oracle_render_batch(m, state, size, types, present, type_names, tl_corners, 
         pr = present[b, c] if present.ndim == 3 else present[b]
         sc = R.build_scene(m["verts"], m["faces"], m["face_cat"], state[b], size[b], type_names, types[b], pr,
                            tl_corners=None if tl_corners is None else tl_corners[b],
-                           tl_state=None if tl_state is None else tl_state[b])
+                           tl_state=None if tl_state is None else tl_state[b],
+                           waypoints=None if waypoints is None else waypoints[b, c],
+                           waypoints_mask=None if waypoints_mask is None else waypoints_mask[b, c])
         img, _ = R.render_camera(sc, cam_xy[b, c], cam_sc[b, c], res, fov)
         out[(b, c)] = img
     return out

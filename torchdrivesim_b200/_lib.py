@@ -77,6 +77,7 @@ SIGNATURES = {
     "tds_raster_birdview": (c_int32, [POINTER(c_void_p), c_int32, c_void_p, c_int32, c_int32, c_int32,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                       c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32,
+                                      c_void_p, c_void_p, c_int32,
                                       POINTER(Palette), c_float, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

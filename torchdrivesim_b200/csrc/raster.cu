@@ -342,6 +342,9 @@ struct RasterArgs {
     int32_t ncam;
     float scale;
     int32_t* next_cam;         // work counter of the persistent grid (zeroed before the launch)
+    const float* cam_tris;     // [B*Nc][Tc][6] world-space triangles of each camera (waypoint discs), or NULL
+    const int32_t* cam_cls;    // [B*Nc][Tc] their classes (< 0: skipped)
+    int32_t Tc;
 };
 
 constexpr int kRows = tds::kMaxRasterRows;
@@ -491,14 +494,14 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
         // just their vertices and queues the others by kind; whenever G faces of a kind are queued, stage 2 turns
         // them into row intervals, one face per thread, so stage 2 always runs with full warps.  The last
         // iteration (seg > nrows) only drains the queues.
-        int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? (int)slds(count_sa) : T;
+        int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? (int)slds(count_sa) : T + a.Tc;
         if (nrows > 0) seg_start = (int)slds(start_sa);
         int nq0 = 0, nq1 = 0, nq2 = 0;                 // queue fill levels (uniform over the group)
         while (true) {
             while (j0 >= seg_count && seg <= nrows) {
                 seg++;
                 j0 = 0;
-                seg_count = seg < nrows ? (int)slds(count_sa + 4u * seg) : (seg == nrows ? T : 0);
+                seg_count = seg < nrows ? (int)slds(count_sa + 4u * seg) : (seg == nrows ? T + a.Tc : 0);
                 seg_start = seg < nrows ? (int)slds(start_sa + 4u * seg) : 0;
             }
             const bool drain = seg > nrows;
@@ -518,6 +521,13 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                     const int meta = __float_as_int(v2o.z);
                     own = meta & 7;
                     cls = meta >> 8;
+                } else if (jj >= T) {
+                    // triangles of this camera only (goal-waypoint discs, mesh.py:1120-1145)
+                    const int64_t ct = (int64_t)camid * a.Tc + (jj - T);
+                    const int c = a.cam_cls[ct];
+                    cls = c < 0 ? 255 : c;
+                    const float* p = a.cam_tris + ct * 6;
+                    x0 = p[0]; y0 = p[1]; x1 = p[2]; y1 = p[3]; x2 = p[4]; y2 = p[5];
                 } else {
                     // dynamic primitives (agents, direction triangles, traffic lights, signs)
                     int t = jj;
@@ -695,6 +705,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
                                    const uint8_t* d_present, int32_t present_per_camera,
                                    const float* d_tl_corners, const int32_t* d_tl_state, int32_t L,
                                    const float* d_rect_corners, const int32_t* d_rect_class, int32_t R,
+                                   const float* d_cam_tris, const int32_t* d_cam_tri_class, int32_t Tc,
                                    const tds_palette_t* palette, float scale, int32_t res,
                                    float* d_out, void* d_workspace, void* stream) {
     TDS_REQUIRE(B >= 0 && Nc >= 0 && N >= 0 && L >= 0 && R >= 0, "raster: negative size");
@@ -703,6 +714,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     TDS_REQUIRE(N == 0 || (d_agent_state && d_agent_size), "raster: null agent tensors");
     TDS_REQUIRE(L == 0 || (d_tl_corners && d_tl_state), "raster: null traffic light tensors");
     TDS_REQUIRE(R == 0 || (d_rect_corners && d_rect_class), "raster: null rectangle tensors");
+    TDS_REQUIRE(Tc >= 0 && (Tc == 0 || (d_cam_tris && d_cam_tri_class)), "raster: null per-camera triangle tensors");
     TDS_REQUIRE(res >= 4 && res % 4 == 0 && res <= 448, "raster: res=%d must be a multiple of 4 in [4,448]", res);
     TDS_REQUIRE(scale > 0.0f, "raster: scale must be positive");
     TDS_REQUIRE(palette->n_classes >= 0 && palette->n_classes <= TDS_MAX_CLASSES, "raster: bad palette");
@@ -758,6 +770,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     const int64_t ncam = (int64_t)B * Nc;
     TDS_REQUIRE(ncam <= 2147483647LL, "raster: too many cameras");
     a.ncam = (int32_t)ncam;
+    a.cam_tris = d_cam_tris; a.cam_cls = d_cam_tri_class; a.Tc = Tc;
     a.next_cam = reinterpret_cast<int32_t*>((uint8_t*)d_workspace + (int64_t)B * ws_env_bytes(T));
     const int K = pal.n_classes;
     TDS_REQUIRE(K <= 31, "raster: at most 31 active classes (got %d)", K);

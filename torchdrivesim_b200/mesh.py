@@ -35,6 +35,8 @@ class BirdviewScene:
     rect_categories: List[str]
     batch_size: int
     workspace: Optional[Tensor] = None
+    cam_tris: Optional[Tensor] = None          # [B,Nc,Tc,3,2] triangles of one camera each (waypoint discs)
+    cam_tri_class: Optional[Tensor] = None     # [B,Nc,Tc] int32 class ids (< 0: skipped)
 
     def slice(self, b0: int, b1: int) -> "BirdviewScene":
         """Environments [b0, b1) of the scene (views, no copies) - used to render in chunks."""
@@ -43,7 +45,7 @@ class BirdviewScene:
         return BirdviewScene(ms, cut(self.agent_state), cut(self.agent_size), cut(self.agent_type), cut(self.present),
                              self.agent_type_names, self.render_agent_direction, cut(self.tl_corners), cut(self.tl_state),
                              self.tl_allowed_states, cut(self.rect_corners), cut(self.rect_class), self.rect_categories,
-                             b1 - b0, self.workspace)
+                             b1 - b0, self.workspace, cut(self.cam_tris), cut(self.cam_tri_class))
 
     def palette(self, color_map, rendering_levels) -> "_lib.Palette":
         active = list(self.mapset.static_categories())
@@ -54,6 +56,8 @@ class BirdviewScene:
         if self.tl_corners is not None:
             active += [f"traffic_light_{s}" for s in self.tl_allowed_states]
         active += self.rect_categories
+        if self.cam_tris is not None:
+            active.append("goal_waypoint")
         return build_palette(color_map, rendering_levels, active, self.agent_type_names,
                              self.render_agent_direction, self.tl_allowed_states)
 
@@ -144,8 +148,8 @@ class B200BirdviewMeshGenerator:
                  custom_agent_colors: Optional[Tensor] = None) -> BirdviewScene:
         """Same arguments as the reference's generate (mesh.py:1053-1075): agent_state [B,Nc,N,4] (one
         copy per camera; must be the broadcast of a [B,N,4] tensor), present_mask [B,Nc,N]."""
-        if waypoints is not None or custom_agent_colors is not None:
-            raise NotImplementedError("waypoint discs and custom agent colours are not part of the B200 hot path yet")
+        if custom_agent_colors is not None:
+            raise NotImplementedError("custom agent colours are not part of the B200 hot path yet")
         state = size = types = present = None
         if agent_state is not None and self.agent_size is not None:
             if agent_state.dim() == 4:
@@ -171,6 +175,8 @@ class B200BirdviewMeshGenerator:
                               tl_corners=tl_corners, tl_state=tl_state, tl_allowed_states=self.tl_allowed_states,
                               rect_corners=self.rect_corners, rect_class=self.rect_class,
                               rect_categories=self.rect_categories, batch_size=B, workspace=self._workspace)
+        if waypoints is not None and waypoints.shape[-2] > 0:
+            scene.cam_tris, scene.cam_tri_class = self._waypoint_triangles(num_cameras, waypoints, waypoints_rendering_mask)
         if state is not None:
             need = _lib.load().tds_raster_workspace_bytes(B, state.shape[1], 0 if tl_corners is None else tl_corners.shape[1],
                                                           0 if self.rect_corners is None else self.rect_corners.shape[1])
@@ -178,6 +184,47 @@ class B200BirdviewMeshGenerator:
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=state.device)
             scene.workspace = self._workspace
         return scene
+
+    # ---- goal waypoints (mesh.py:885-909, 1120-1145, 1243-1271) -------------------------------------------
+    waypoint_radius = 2.0
+    waypoint_num_triangles = 10
+
+    def _disc_template(self, device) -> Tuple[Tensor, Tensor]:
+        """Centre + rim vertices of the waypoint disc and its faces (0, k, k+1), ..., (0, n, 1).  The rim is made by
+        REPEATED rotation of (radius, 0) with torch.matmul on the CPU, like generate_disc_mesh: the accumulated fp32
+        rounding of those ATen ops is part of the reference's result."""
+        key = (self.waypoint_radius, self.waypoint_num_triangles)
+        if getattr(self, "_disc_cache", None) is None or self._disc_cache[0] != key:
+            n = self.waypoint_num_triangles
+            step = torch.deg2rad(torch.tensor([[360 / n]], dtype=torch.float32))
+            c, s = torch.cos(step), torch.sin(step)
+            rot = torch.stack([torch.cat([c, -s], -1), torch.cat([s, c], -1)], -2)
+            verts = [torch.zeros(1, 2), torch.tensor([[self.waypoint_radius, 0.0]], dtype=torch.float32)]
+            for _ in range(n - 1):
+                verts.append(torch.matmul(rot, verts[-1].unsqueeze(-1)).squeeze(-1))
+            faces = torch.tensor([[0, k, k + 1] for k in range(1, n)] + [[0, n, 1]], dtype=torch.long)
+            self._disc_cache = (key, torch.cat(verts, 0), faces)
+        return self._disc_cache[1].to(device), self._disc_cache[2].to(device)
+
+    def _waypoint_triangles(self, num_cameras: int, waypoints: Tensor, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+        """waypoints [B,Nc,M,2] (+ mask [B,Nc,M]) -> world-space triangles [B,Nc,M*n,3,2] and their class ids.  A disc
+        is the template translated to its waypoint (the pose has psi = 0: the rotation is the identity); the faces
+        of a masked waypoint collapse onto vertex 0 of the camera's waypoint mesh, the centre of its FIRST waypoint."""
+        if waypoints.dim() != 4 or waypoints.shape[1] != num_cameras or waypoints.shape[-1] != 2:
+            raise _lib.TdsError("waypoints must be [B,Nc,M,2]")
+        wp = waypoints.detach().to(torch.float32)
+        B, Nc, M = wp.shape[:3]
+        dv, df = self._disc_template(wp.device)
+        verts = dv[None, None, None] + wp[..., None, :]                       # [B,Nc,M,V,2]
+        tris = verts[:, :, :, df]                                               # [B,Nc,M,n,3,2]
+        if mask is not None:
+            if tuple(mask.shape) != (B, Nc, M):
+                raise _lib.TdsError("waypoints_rendering_mask must be [B,Nc,M]")
+            first = verts[:, :, 0, 0]                                           # [B,Nc,2]
+            tris = torch.where(mask.to(torch.bool)[..., None, None, None], tris, first[:, :, None, None, None, :])
+        n = df.shape[0]
+        cls = torch.full((B, Nc, M * n), class_id("goal_waypoint"), dtype=torch.int32, device=wp.device)
+        return tris.reshape(B, Nc, M * n, 3, 2).contiguous(), cls
 
     # ---- batch plumbing -----------------------------------------------------------------------
     def _tensors(self):

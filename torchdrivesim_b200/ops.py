@@ -220,9 +220,11 @@ def raster_birdview(mapset: MapSet, palette: "_lib.Palette", cam_xy: torch.Tenso
                     tl_corners: Optional[torch.Tensor], tl_state: Optional[torch.Tensor],
                     rect_corners: Optional[torch.Tensor], rect_class: Optional[torch.Tensor],
                     res: int, fov: float, out: Optional[torch.Tensor] = None,
-                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    workspace: Optional[torch.Tensor] = None, cam_tris: Optional[torch.Tensor] = None,
+                    cam_tri_class: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cam_xy, cam_sc [B,Nc,2] -> images [B,Nc,3,res,res] float32 in [0,255] (not differentiable, like
-    the cv2 backend).  present is [B,N] or [B,Nc,N]."""
+    the cv2 backend).  present is [B,N] or [B,Nc,N]; cam_tris [B,Nc,Tc,3,2] + cam_tri_class [B,Nc,Tc] are
+    triangles seen by one camera each (waypoint discs)."""
     lib = _lib.load()
     dev = cam_xy.device
     cxy, csc = _lib.as_f32(cam_xy), _lib.as_f32(cam_sc)
@@ -251,11 +253,17 @@ def raster_birdview(mapset: MapSet, palette: "_lib.Palette", cam_xy: torch.Tenso
     need = lib.tds_raster_workspace_bytes(B, N, L, R)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    Tc, ctr, ccl = 0, None, None
+    if cam_tris is not None and cam_tris.shape[2] > 0:
+        Tc = cam_tris.shape[2]
+        if tuple(cam_tris.shape) != (B, Nc, Tc, 3, 2) or cam_tri_class is None or tuple(cam_tri_class.shape) != (B, Nc, Tc):
+            raise _lib.TdsError("raster: cam_tris must be [B,Nc,Tc,3,2] and cam_tri_class [B,Nc,Tc]")
+        ctr, ccl = _lib.as_f32(cam_tris), _lib.as_i32(cam_tri_class)
     handles, n_maps = mapset.handles(dev)
     env_map = mapset.env_map_on(dev)
     _lib.check(lib.tds_raster_birdview(handles, n_maps, _lib.ptr(env_map), B, Nc, N, _lib.ptr(cxy), _lib.ptr(csc),
                                        _lib.ptr(ast), _lib.ptr(asz), _lib.ptr(aty), _lib.ptr(pr), per_cam,
                                        _lib.ptr(tlc), _lib.ptr(tls), L, _lib.ptr(rc), _lib.ptr(rcl), R,
-                                       ctypes.byref(palette), float(2.0 / fov), int(res), _lib.ptr(out),
+                                       _lib.ptr(ctr), _lib.ptr(ccl), Tc, ctypes.byref(palette), float(2.0 / fov), int(res), _lib.ptr(out),
                                        _lib.ptr(workspace), _lib.stream_ptr(dev)))
     return out

@@ -84,7 +84,7 @@ class B200Renderer(BirdviewRenderer):
         img = ops.raster_birdview(scene.mapset, palette, camera_xy, camera_sc, scene.agent_state, scene.agent_size,
                                   scene.agent_type, scene.present, scene.tl_corners, scene.tl_state,
                                   scene.rect_corners, scene.rect_class, res.height, fov_m, out=out,
-                                  workspace=scene.workspace)
+                                  workspace=scene.workspace, cam_tris=scene.cam_tris, cam_tri_class=scene.cam_tri_class)
         return img.reshape(B * Nc, 3, res.height, res.width)
 
 

@@ -178,8 +178,10 @@ class Simulator:
         return self.kinematic_model.fit_action(future_state=future_state, current_state=current_state)
 
     def render(self, camera_xy: Tensor, camera_psi: Tensor, res: Optional[Resolution] = None,
-               rendering_mask: Optional[Tensor] = None, fov: Optional[float] = None, out: Optional[Tensor] = None) -> Tensor:
-        """camera_xy BxNx2, camera_psi BxNx1 -> BxNx3xHxW (simulator.py:920-992)."""
+               rendering_mask: Optional[Tensor] = None, fov: Optional[float] = None, out: Optional[Tensor] = None,
+               waypoints: Optional[Tensor] = None, waypoints_rendering_mask: Optional[Tensor] = None) -> Tensor:
+        """camera_xy BxNx2, camera_psi BxNx1 -> BxNx3xHxW (simulator.py:920-992); waypoints BxNxMx2 and their
+        BxNxM mask draw goal-waypoint discs for the camera they belong to."""
         camera_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
         if camera_xy.dim() == 2:
             camera_xy, camera_sc = camera_xy.unsqueeze(1), camera_sc.unsqueeze(1)
@@ -192,7 +194,8 @@ class Simulator:
         tl = self.traffic_controls.get('traffic_light') if self.traffic_controls is not None else None
         scene = self.birdview_mesh_generator.generate(
             n_cameras, agent_state=self.get_all_agent_state().detach()[:, None].expand(-1, n_cameras, -1, -1),
-            present_mask=present, traffic_lights=tl)
+            present_mask=present, traffic_lights=tl, waypoints=waypoints,
+            waypoints_rendering_mask=waypoints_rendering_mask)
         img = self.renderer.render_frame(scene, camera_xy, camera_sc, res=res, fov=fov, out=out)
         return img.reshape((self.batch_size, n_cameras) + img.shape[1:])
 
