@@ -68,6 +68,9 @@ def test_golden_reference_images():
     ("carla_Town02", 64, 100.0, 2, 0.1, True),
     ("carla_Town02", 64, 600.0, 0, 0.0, False),      # whole town in view: > 32 grid rows per camera, sub-pixel faces
     ("carla_Town01", 32, 20.0, 0, 0.0, True),
+    ("carla_Town02", 48, 35.0, 2, 0.2, True),        # tile sizes that are not a multiple of 32
+    ("carla_Town01", 100, 40.0, 3, 0.0, False),
+    ("carla_Town02", 320, 70.0, 0, 0.1, True),
 ])
 def test_vs_oracle_random_scenes(mapname, res, fov, ped_every, absent_p, lights):
     rng = np.random.default_rng(res * 7 + int(fov))
