@@ -121,6 +121,17 @@ int tds_traffic_light_violation(const float* d_agent_box, const float* d_tl_corn
                                 float rear_factor, uint8_t* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Non-visual observations.  Replaces Simulator.get_all_agents_relative (simulator.py:748-781) with
+ * utils.relative (utils.py:71-79): for every origin agent i < A and every agent j < N of the same environment
+ *   out = ( R(-psi_i) (xy_j - xy_i),  normalize_angle(psi_j - psi_i),  length_j, width_j, present_j ).
+ *   d_absolute [B,N,6] (x, y, psi, length, width, present) as get_all_agents_absolute returns it; the first A
+ *   agents are the origins.  d_out [B,A,N,6], or [B,A,N-1,6] with exclude_self (entry j == i removed; no
+ *   boolean-mask indexing and hence no host synchronisation, unlike the reference).
+ * ---------------------------------------------------------------------------------------- */
+int tds_agents_relative(const float* d_absolute, int32_t B, int32_t A, int32_t N, int32_t exclude_self,
+                        float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Static map: triangle mesh + uniform grids, built once per map per GPU.  Replaces the
  * per-camera / per-corner expansion of the mesh (mesh.py:1147-1157, infractions.py:219-226).
  * ---------------------------------------------------------------------------------------- */

@@ -199,6 +199,22 @@ def golden_waypoints():
     print("waypoints: image", img.shape, "goal-coloured px", int((img[:, :, 0] == np.floor(goal[0] / 255 * 256)).sum()))
 
 
+def golden_relative():
+    """Non-visual observations (simulator.py:730-781): get_all_agents_absolute / get_all_agents_relative."""
+    gen = torch.Generator().manual_seed(707)
+    B, A = 3, 9
+    present = torch.rand(B, A, generator=gen) > 0.2
+    sim, _ = make_sim("carla_Town01", B, A, gen, with_lights=False, present=present)
+    st = sim.get_state().clone()
+    st[..., :2] = st[:, :1, :2] + 30.0 * torch.randn(B, A, 2, generator=gen)
+    st[..., 2] = (torch.rand(B, A, generator=gen) - 0.5) * 12.0                     # beyond (-pi, pi): exercises the wrap
+    sim.set_state(st)
+    np.savez_compressed(os.path.join(HERE, "relative.npz"), absolute=sim.get_all_agents_absolute().numpy(),
+                        relative_excl=sim.get_all_agents_relative(exclude_self=True).numpy(),
+                        relative_all=sim.get_all_agents_relative(exclude_self=False).numpy())
+    print("relative:", tuple(sim.get_all_agents_relative().shape))
+
+
 def golden_traffic():
     """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
     simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
@@ -226,6 +242,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative"]
     for w in which:
         globals()["golden_" + w]()

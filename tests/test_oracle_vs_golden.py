@@ -104,3 +104,15 @@ def test_traffic_light_violation_oracle_matches_reference():
     masked = traffic.tl_violation(g["agent_box"], g["tl_corners"], g["tl_state"], int(g["red_index"]),
                                   float(g["rear_factor"]), g["present"])
     assert np.array_equal(masked, g["violation"])
+
+
+def test_agents_relative_oracle_matches_reference():
+    """oracle/observations.py against Simulator.get_all_agents_relative of the unmodified reference."""
+    from oracle import observations
+    g = util.golden("relative")
+    for key, excl in (("relative_excl", True), ("relative_all", False)):
+        got = observations.agents_relative(g["absolute"], exclude_self=excl)
+        assert got.shape == g[key].shape
+        np.testing.assert_allclose(got, g[key], rtol=1e-5, atol=2e-5)
+        assert np.array_equal(got[..., 3:], g[key][..., 3:])
+    assert np.abs(g["absolute"][..., 2]).max() > np.pi          # the angle wrap is exercised

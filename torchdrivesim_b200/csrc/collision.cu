@@ -190,6 +190,36 @@ __global__ void __launch_bounds__(128) tl_violation_kernel(const float* __restri
     out[g] = hit ? 1 : 0;
 }
 
+// ---- non-visual observations (Simulator.get_all_agents_relative, simulator.py:748-781; utils.relative /
+// rotate / normalize_angle, utils.py:31-79): the pose of every agent j in the frame of every origin agent i.
+// One thread per output row (b, i, k); with exclude_self row k of origin i is agent j = k + (k >= i), which is the
+// reference's boolean-mask removal of the diagonal without its host synchronisation.
+__global__ void __launch_bounds__(256) agents_relative_kernel(const float* __restrict__ absolute, int B, int A, int N,
+                                                              int exclude_self, float* __restrict__ out) {
+    const int M = exclude_self ? N - 1 : N;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (int64_t)B * A * M) return;
+    const int k = (int)(g % M);
+    const int64_t bi = g / M;
+    const int i = (int)(bi % A);
+    const int64_t b = bi / A;
+    const int j = exclude_self ? k + (k >= i) : k;
+    const float* o = absolute + (b * N + i) * 6;
+    const float* t = absolute + (b * N + j) * 6;
+    const float ang = -o[2];
+    float s, c;
+    tds::sincos_cr(ang, s, c);
+    const float dx = t[0] - o[0], dy = t[1] - o[1];
+    // remainder with the sign of the divisor (torch.remainder), then shift back: normalize_angle
+    const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+    float r = fmodf((t[2] - o[2]) + pi, two_pi);
+    if (r != 0.0f && r < 0.0f) r += two_pi;
+    float2* w = reinterpret_cast<float2*>(out + g * 6);
+    w[0] = make_float2(c * dx + (-s) * dy, s * dx + c * dy);
+    w[1] = make_float2(r - pi, t[3]);
+    w[2] = make_float2(t[4], t[5]);
+}
+
 // ---- IoU backward.  d(intersection area) is the boundary integral of the normal velocity: every edge of
 // the clipped polygon lies either on a face of box q (it moves with q's pose and size) or on a face of box p
 // (it moves with p's size).  Each polygon vertex carries the tag of the edge that leaves it:
@@ -508,6 +538,19 @@ extern "C" int tds_traffic_light_violation(const float* d_agent_box, const float
     tl_violation_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_agent_box, d_tl_corners, d_tl_state,
                                                                                    d_present, B, A, L, red_state,
                                                                                    rear_factor, d_out);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_agents_relative(const float* d_absolute, int32_t B, int32_t A, int32_t N, int32_t exclude_self,
+                                   float* d_out, void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0 && N >= 0 && A <= N, "agents_relative: need 0 <= A <= N");
+    const int64_t M = exclude_self ? N - 1 : N;
+    const int64_t n = (int64_t)B * A * M;
+    if (n <= 0) return TDS_OK;
+    TDS_REQUIRE(d_absolute && d_out, "agents_relative: null pointer");
+    TDS_REQUIRE((n + 255) / 256 <= 2147483647LL, "agents_relative: too many pairs");
+    agents_relative_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_absolute, B, A, N, exclude_self, d_out);
     TDS_LAUNCH_OK();
     return TDS_OK;
 }

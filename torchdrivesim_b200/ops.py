@@ -165,6 +165,25 @@ def traffic_light_violation(agent_box: torch.Tensor, tl_corners: torch.Tensor, t
     return out.view(torch.bool)
 
 
+def agents_relative(absolute: torch.Tensor, n_agents: Optional[int] = None, exclude_self: bool = True) -> torch.Tensor:
+    """absolute [B,N,6] (x, y, psi, length, width, present) -> [B,A,N(-1),6]: every agent in the frame of each of the
+    first `n_agents` agents (Simulator.get_all_agents_relative, simulator.py:748-781).  The self entry is removed on
+    the device without the reference's synchronising boolean-mask index.  Not differentiable."""
+    lib = _lib.load()
+    a = _lib.as_f32(absolute)
+    if a.dim() != 3 or a.shape[-1] != 6:
+        raise _lib.TdsError("agents_relative: absolute must be [B,N,6]")
+    B, N = a.shape[0], a.shape[1]
+    A = N if n_agents is None else int(n_agents)
+    if not 0 <= A <= N:
+        raise _lib.TdsError("agents_relative: n_agents must be in [0, N]")
+    M = max(N - 1, 0) if exclude_self else N
+    out = torch.empty(B, A, M, 6, dtype=torch.float32, device=a.device)
+    _lib.check(lib.tds_agents_relative(_lib.ptr(a), B, A, N, 1 if exclude_self else 0, _lib.ptr(out),
+                                       _lib.stream_ptr(a.device)))
+    return out
+
+
 # ------------------------------------------------------------------------------------ offroad
 class _Offroad(torch.autograd.Function):
     @staticmethod

@@ -253,6 +253,17 @@ class Simulator:
         main.wait_stream(self._copy_stream)
         return host_out
 
+    # ---- non-visual observations (simulator.py:730-781) --------------------------------------------
+    def get_all_agents_absolute(self) -> Tensor:
+        """Bx(A)x6: x, y, psi, length, width, present (simulator.py:730-738; no NPCs here)."""
+        return torch.cat([self.get_state()[..., :3], self.get_agent_size()[..., :2],
+                          self.get_present_mask().unsqueeze(-1).to(torch.float32)], dim=-1)
+
+    def get_all_agents_relative(self, exclude_self: bool = True) -> Tensor:
+        """BxAx(A-1 or A)x6: the pose of every agent in the frame of every agent (simulator.py:748-781), one launch
+        and no host synchronisation."""
+        return ops.agents_relative(self.get_all_agents_absolute(), self.agent_count, exclude_self)
+
     def compute_offroad(self) -> Tensor:
         """simulator.py:1035-1044: offroad_infraction_loss(...) * present mask."""
         return ops.offroad(self.get_state(), self.get_agent_size(), self.road_mesh, self.cfg.offroad_threshold,
