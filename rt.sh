@@ -1,4 +1,4 @@
-python -m pytest tests/test_gpu_raster.py tests/test_gpu_graph.py -x -q 2>&1 | tail -3
+python -m pytest tests/test_gpu_raster.py tests/test_gpu_graph.py tests/test_gpu_observations.py -x -q 2>&1 | tail -15
 python bench.py --steps 10 --warmup 3 --kernels-only 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:

@@ -1,3 +1,5 @@
-python -m pytest tests/test_gpu_raster.py -x -q 2>&1 | tail -2
-python profiles/time_raster.py
-for v in minb5 minb8; do TDS_B200_LIB=torchdrivesim_b200/_build/libtds_$v.so python profiles/time_raster.py; done
+python -m pytest tests/test_gpu_offroad.py -x -q 2>&1 | tail -3
+for s in 0 3 10; do
+TDS_OFFROAD_SIGMA=$s ncu --metrics gpu__time_duration.sum --clock-control none -k regex:offroad_fwd -s 5 -c 1 python profiles/exp_offroad.py 2>&1 | grep -E "gpu__time|sigma"
+done
+bash rt.sh

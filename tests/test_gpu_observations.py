@@ -9,8 +9,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _close(got, ref):
-    # positions 1e-5 relative (+ 2e-5 m: differences of coordinates of ~300 m); angles may sit on either side of the wrap
-    np.testing.assert_allclose(got[..., :2], ref[..., :2], rtol=1e-5, atol=2e-5)
+    # positions: 1e-5 relative to the distance between the two agents (sin/cos of the origin's heading differ by an ulp
+    # between the float64-rounded kernel and numpy's float32 libm) + 2e-5 m; angles may sit on either side of the wrap
+    dist = np.linalg.norm(ref[..., :2], axis=-1, keepdims=True)
+    assert (np.abs(got[..., :2] - ref[..., :2]) <= 1e-5 * dist + 2e-5).all()
     d = np.abs(got[..., 2] - ref[..., 2])
     assert np.minimum(d, np.abs(d - 2 * np.pi)).max() < 2e-5
     assert np.array_equal(got[..., 3:], ref[..., 3:])

@@ -71,7 +71,8 @@ __device__ __forceinline__ bool cannot_improve(float lower_bound2, float best) {
     return lower_bound2 > best * 1.00001f + 1e-9f;
 }
 
-__device__ __forceinline__ void visit_cell(const MapDev& m, int cx, int cy, float px, float py, float& best, int& bf) {
+// all faces of one grid cell, one lane
+__device__ __forceinline__ void visit_cell(const MapDev& m, int cx, int cy, float px, float py, float stop, float& best, int& bf) {
     // cell bounds (faces are binned with 1 mm of slack, see map.cu)
     const float x0 = m.ox0 + (float)cx * m.ocs, y0 = m.oy0 + (float)cy * m.ocs;
     if (cannot_improve(box_dist2(px, py, x0 - 2e-3f, y0 - 2e-3f, x0 + m.ocs + 2e-3f, y0 + m.ocs + 2e-3f), best)) return;
@@ -91,14 +92,53 @@ __device__ __forceinline__ void visit_cell(const MapDev& m, int cx, int cy, floa
             const float d = point_tri_dist2(px, py, a.x, a.y, a.z, a.w, b.x, b.y);
             const int f = __float_as_int(b.z);
             if (d < best || (d == best && f < bf)) { best = d; bf = f; }
-            if (best == 0.0f) return;       // inside a face: the minimum over all faces is 0
+            if (best <= stop) return;       // inside a face (or within the threshold): the result is 0
         }
         a = na; b = nb;
     }
 }
 
-// min over all faces of the map; returns the squared distance, *face = argmin
-__device__ float nearest_face(const MapDev& m, float px, float py, int* face) {
+constexpr int kGroup = 8;       // lanes that search for one point
+
+__device__ __forceinline__ void group_min(unsigned group_mask, float& best, int& bf) {
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) {
+        const float ob = __shfl_xor_sync(group_mask, best, o);
+        const int of = __shfl_xor_sync(group_mask, bf, o);
+        if (ob < best || (ob == best && of >= 0 && (bf < 0 || of < bf))) { best = ob; bf = of; }
+    }
+}
+
+// the point's own cell: the group evaluates kGroup faces at a time (largest first: a containing face is found in the
+// first round) and shares the minimum after every round, so a hit ends the search for all lanes
+__device__ __forceinline__ void visit_own_cell(const MapDev& m, int cx, int cy, float px, float py, float stop, float& best,
+                                               int& bf, int sub, unsigned group_mask) {
+    const int c = cy * m.ogx + cx;
+    const int e0 = __ldg(m.ocell + c), e1 = __ldg(m.ocell + c + 1);
+    for (int e = e0; e < e1; e += kGroup) {          // uniform over the group
+        const int mine = e + sub;
+        if (mine < e1) {
+            const float4 a = __ldg(m.orec + 2 * (int64_t)mine), b = __ldg(m.orec + 2 * (int64_t)mine + 1);
+            const float bx0 = fminf(fminf(a.x, a.z), b.x), bx1 = fmaxf(fmaxf(a.x, a.z), b.x);
+            const float by0 = fminf(fminf(a.y, a.w), b.y), by1 = fmaxf(fmaxf(a.y, a.w), b.y);
+            if (!cannot_improve(box_dist2(px, py, bx0, by0, bx1, by1), best)) {
+                const float d = point_tri_dist2(px, py, a.x, a.y, a.z, a.w, b.x, b.y);
+                const int f = __float_as_int(b.z);
+                if (d < best || (d == best && f < bf)) { best = d; bf = f; }
+            }
+        }
+        group_min(group_mask, best, bf);
+        if (best <= stop) return;
+    }
+}
+
+// min over all faces of the map; returns the squared distance, *face = argmin (lowest face index among equal
+// distances).  The search ends as soon as a face within `stop` (the threshold of the loss, >= 0) is found: the loss
+// of this corner and its gradient are then 0 whatever the true minimum is (F.threshold, infractions.py:172), and the
+// returned value / face are those of that face.  kGroup consecutive lanes search for ONE point: they split the faces of the point's own cell and the
+// cells of every ring, and share their minimum after each ring (the minimum does not depend on the visiting order).
+
+__device__ float nearest_face(const MapDev& m, float px, float py, float stop, int* face, int sub, unsigned group_mask) {
     float best = CUDART_INF_F;
     int bf = -1;
     if (m.nf == 0) { *face = -1; return 0.0f; }
@@ -108,21 +148,36 @@ __device__ float nearest_face(const MapDev& m, float px, float py, int* face) {
     // first ring that touches the grid at all
     int k0 = max(max(-cx, cx - (m.ogx - 1)), max(-cy, cy - (m.ogy - 1)));
     k0 = max(k0, 0);
+    // faces are binned by bounding box, so after ring k every unvisited face lies outside the square of visited
+    // cells: further away than k cells plus the distance from p to the border of its own cell
+    const float ux = px - (m.ox0 + (float)cx * m.ocs), uy = py - (m.oy0 + (float)cy * m.ocs);
+    const float inner = fminf(fmaxf(fminf(fminf(ux, m.ocs - ux), fminf(uy, m.ocs - uy)), 0.0f), m.ocs);
     for (int k = k0; k <= kmax; k++) {
-        const int xa = max(cx - k, 0), xb = min(cx + k, m.ogx - 1);
         if (k == 0) {
-            visit_cell(m, cx, cy, px, py, best, bf);
+            visit_own_cell(m, cx, cy, px, py, stop, best, bf, sub, group_mask);
         } else {
-            if (cy - k >= 0) for (int x = xa; x <= xb; x++) visit_cell(m, x, cy - k, px, py, best, bf);
-            if (cy + k < m.ogy) for (int x = xa; x <= xb; x++) visit_cell(m, x, cy + k, px, py, best, bf);
-            const int y0 = max(cy - k + 1, 0), y1 = min(cy + k - 1, m.ogy - 1);
-            if (cx - k >= 0) for (int y = y0; y <= y1; y++) visit_cell(m, cx - k, y, px, py, best, bf);
-            if (cx + k < m.ogx) for (int y = y0; y <= y1; y++) visit_cell(m, cx + k, y, px, py, best, bf);
+            // the in-grid cells of ring k: top row, bottom row, left column, right column
+            const int xa = max(cx - k, 0), xb = min(cx + k, m.ogx - 1);
+            const int ya = max(cy - k + 1, 0), yb = min(cy + k - 1, m.ogy - 1);
+            const int nx = max(xb - xa + 1, 0), ny = max(yb - ya + 1, 0);
+            const int nt = cy - k >= 0 ? nx : 0, nb = cy + k < m.ogy ? nx : 0;
+            const int nl = cx - k >= 0 ? ny : 0, nr = cx + k < m.ogx ? ny : 0;
+            const int n = nt + nb + nl + nr;
+            for (int i = sub; i < n; i += kGroup) {
+                int x, y;
+                if (i < nt) { x = xa + i; y = cy - k; }
+                else if (i < nt + nb) { x = xa + (i - nt); y = cy + k; }
+                else if (i < nt + nb + nl) { x = cx - k; y = ya + (i - nt - nb); }
+                else { x = cx + k; y = ya + (i - nt - nb - nl); }
+                visit_cell(m, x, y, px, py, stop, best, bf);
+                if (best <= stop) break;
+            }
         }
-        // every face with a point closer than k cells has been visited (1 mm slack for the cell
-        // assignment of p itself)
-        if (best == 0.0f) break;
-        const float reach = fmaxf((float)k * m.ocs - 1e-3f, 0.0f);
+        // share the minimum (and the lowest face index that attains it) within the group
+        if (k > 0) group_min(group_mask, best, bf);
+        // (1 mm slack for the cell assignment of p itself)
+        if (best <= stop) break;
+        const float reach = fmaxf((float)k * m.ocs + inner - 1e-3f, 0.0f);
         if (best <= reach * reach) break;
     }
     if (!(best < CUDART_INF_F)) best = 0.0f;   // NaN position / distance: nan_to_num, infractions.py:171
@@ -140,34 +195,33 @@ __device__ __forceinline__ void corner_of(const float* st, const float* lw, int 
     py = (ux * s + uy * c) + st[1];
 }
 
+// one warp per agent: 4 corners x kGroup lanes
 __global__ void __launch_bounds__(128) offroad_fwd_kernel(MapSetDev maps, const int32_t* __restrict__ env_map,
                                                           const float* __restrict__ state, const float* __restrict__ lenwid,
                                                           const uint8_t* __restrict__ present, int B, int A, float thr,
                                                           float* __restrict__ out, int32_t* __restrict__ face) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t agent = t >> 2;
-    const int k = (int)(t & 3);
-    const bool valid = agent < (int64_t)B * A;
+    static_assert(4 * kGroup == 32, "a warp holds the four corners of one agent");
+    const int64_t agent = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int k = lane / kGroup, sub = lane % kGroup;
+    if (agent >= (int64_t)B * A) return;           // warp-uniform
     float v = 0.0f;
     int bf = -1;
-    if (valid) {
-        const int b = (int)(agent / A);
-        const bool here = present ? present[agent] != 0 : true;
-        if (here) {
-            const MapDev& m = maps.m[env_map ? env_map[b] : 0];
-            float px, py, s, c;
-            corner_of(state + 4 * agent, lenwid + 2 * agent, k, px, py, s, c);
-            const float d2 = nearest_face(m, px, py, &bf);
-            v = d2 > thr ? d2 : 0.0f;           // F.threshold(d2, thr, 0), infractions.py:172
-        }
-        if (face) face[t] = bf;
+    const int b = (int)(agent / A);
+    const bool here = present ? present[agent] != 0 : true;
+    if (here) {
+        const MapDev& m = maps.m[env_map ? env_map[b] : 0];
+        float px, py, s, c;
+        corner_of(state + 4 * agent, lenwid + 2 * agent, k, px, py, s, c);
+        const float d2 = nearest_face(m, px, py, fmaxf(thr, 0.0f), &bf, sub, ((1u << kGroup) - 1u) << (k * kGroup));
+        v = d2 > thr ? d2 : 0.0f;           // F.threshold(d2, thr, 0), infractions.py:172
     }
-    // sum of the 4 corners (lanes 4a..4a+3), in corner order
+    if (face && sub == 0) face[4 * agent + k] = bf;
+    // sum of the 4 corners, in corner order
     const unsigned full = 0xffffffffu;
-    const int base = (threadIdx.x & 31) & ~3;
-    const float v0 = __shfl_sync(full, v, base), v1 = __shfl_sync(full, v, base + 1);
-    const float v2 = __shfl_sync(full, v, base + 2), v3 = __shfl_sync(full, v, base + 3);
-    if (valid && k == 0) out[agent] = ((v0 + v1) + v2) + v3;
+    const float v0 = __shfl_sync(full, v, 0), v1 = __shfl_sync(full, v, kGroup);
+    const float v2 = __shfl_sync(full, v, 2 * kGroup), v3 = __shfl_sync(full, v, 3 * kGroup);
+    if (lane == 0) out[agent] = ((v0 + v1) + v2) + v3;
 }
 
 __global__ void __launch_bounds__(128) offroad_bwd_kernel(MapSetDev maps, const int32_t* __restrict__ env_map,
@@ -238,7 +292,8 @@ extern "C" int tds_offroad_fwd(const tds_map_t* const* maps, int32_t n_maps, con
     TDS_REQUIRE(d_state && d_lenwid && d_out, "offroad: null pointer");
     MapSetDev set;
     if (int e = tds::gather_maps(maps, n_maps, set)) return e;
-    const int64_t threads = (int64_t)B * A * 4;
+    const int64_t threads = (int64_t)B * A * 32;       // a warp per agent
+    TDS_REQUIRE((threads + 127) / 128 <= 2147483647LL, "offroad: too many agents");
     offroad_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         set, d_env_map, d_state, d_lenwid, d_present, B, A, threshold, d_out, d_face);
     TDS_LAUNCH_OK();
