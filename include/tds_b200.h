@@ -121,6 +121,21 @@ int tds_traffic_light_violation(const float* d_agent_box, const float* d_tl_corn
                                 float rear_factor, uint8_t* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Replayed NPCs with spawning / despawning.  Replaces ReplayController.advance_npcs (behavior/replay.py:54-60)
+ * + SpawnController.spawn_despawn_npcs (simulator.py:71-85) + utils.is_inside_polygon (utils.py:99-122):
+ *   state, present <- replay[:, :, t_replay]                     (d_replay_states [B,Np,T,4], d_replay_present
+ *                                                                 [B,Np,T] uint8 or NULL = all present; both NULL: keep)
+ *   present &= inside the convex polygon d_exit_boundary [B,V,2]  (NULL: no despawning)
+ *   spawn = d_spawn_masks[:, :, t_spawn] & !present; present |= spawn; state <- d_spawn_states[:, :, t_spawn] where spawn
+ *                                                                (d_spawn_states [B,Np,Ts,4], d_spawn_masks [B,Np,Ts]; NULL: none)
+ * d_npc_state [B,Np,4] and d_npc_present [B,Np] uint8 are updated in place.
+ * ---------------------------------------------------------------------------------------- */
+int tds_npc_advance(const float* d_replay_states, const uint8_t* d_replay_present, int32_t T, int32_t t_replay,
+                    const float* d_exit_boundary, int32_t V, const float* d_spawn_states, const uint8_t* d_spawn_masks,
+                    int32_t Ts, int32_t t_spawn, float* d_npc_state, uint8_t* d_npc_present, int32_t B, int32_t Np,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Non-visual observations.  Replaces Simulator.get_all_agents_relative (simulator.py:748-781) with
  * utils.relative (utils.py:71-79): for every origin agent i < A and every agent j < N of the same environment
  *   out = ( R(-psi_i) (xy_j - xy_i),  normalize_angle(psi_j - psi_i),  length_j, width_j, present_j ).

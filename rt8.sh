@@ -1,0 +1,2 @@
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+tail -c 400 gpurun_out/bench_n8.err; cut -c1-600 gpurun_out/bench_n8.json

@@ -35,7 +35,7 @@ def road_points(mesh: BirdviewMesh, n: int, gen: torch.Generator) -> torch.Tenso
 
 
 def make_sim(map_name, B, A, gen, types=None, type_names=None, with_lights=True, present=None,
-             metric=CollisionMetric.discs, jitter=0.0, npc=0):
+             metric=CollisionMetric.discs, jitter=0.0, npc_controller=None):
     cfgm = find_map_config(map_name)
     mesh = cfgm.road_mesh
     xy = road_points(mesh, B * A, gen).reshape(B, A, 2) + jitter * torch.randn(B, A, 2, generator=gen)
@@ -60,7 +60,7 @@ def make_sim(map_name, B, A, gen, types=None, type_names=None, with_lights=True,
                            renderer=CV2RendererConfig(left_handed_coordinates=True))
     sim = Simulator(cfg=cfg, road_mesh=mesh.expand(B), kinematic_model=km, agent_size=size,
                     initial_present_mask=present, traffic_controls=tc, agent_types=types,
-                    agent_type_names=type_names)
+                    agent_type_names=type_names, npc_controller=npc_controller)
     return sim, cfgm
 
 
@@ -215,6 +215,58 @@ def golden_relative():
     print("relative:", tuple(sim.get_all_agents_relative().shape))
 
 
+def golden_npc():
+    """Replayed NPCs with spawning / despawning (simulator.py:54-124, behavior/replay.py:46-60): ReplayController +
+    SpawnController inside Simulator.step; states and masks after every step, collisions against all agents,
+    absolute / relative observations and one rendered frame."""
+    from torchdrivesim.simulator import SpawnController
+    from torchdrivesim.behavior.replay import ReplayController
+    gen = torch.Generator().manual_seed(808)
+    B, A, Np, T, S = 2, 4, 5, 4, 7
+    cfgm = find_map_config("carla_Town01")
+    base = road_points(cfgm.road_mesh, B, gen).reshape(B, 1, 1, 2)
+    xy = base + 12.0 * torch.randn(B, Np, T, 2, generator=gen)
+    replay = torch.cat([xy, torch.rand(B, Np, T, 1, generator=gen) * 6.28, torch.rand(B, Np, T, 1, generator=gen) * 5], -1)
+    replay_present = torch.rand(B, Np, T, generator=gen) > 0.25
+    # convex exit boundary: a rotated rectangle around the replayed positions, some of which fall outside
+    ang = torch.tensor([0.3, -0.5]).reshape(B, 1)
+    corners = torch.tensor([[14.0, 10.0], [-14.0, 10.0], [-14.0, -10.0], [14.0, -10.0]])
+    rot = torch.stack([torch.cos(ang) * corners[:, 0] - torch.sin(ang) * corners[:, 1],
+                       torch.sin(ang) * corners[:, 0] + torch.cos(ang) * corners[:, 1]], -1)
+    boundary = rot + base.reshape(B, 1, 2)
+    spawn_states = torch.cat([base + 5.0 * torch.randn(B, Np, S, 2, generator=gen), torch.rand(B, Np, S, 2, generator=gen)], -1)
+    spawn_masks = torch.rand(B, Np, S, generator=gen) > 0.6
+    npc_size = torch.tensor(VEH[:2]).expand(B, Np, 2).clone()
+    npc_size[:, ::2] = torch.tensor(PED)
+    npc_types = (torch.arange(Np) % 2 == 0).long().expand(B, Np).clone()
+    ctrl = ReplayController(npc_size, replay, replay_present, npc_types=npc_types, agent_type_names=["vehicle", "pedestrian"],
+                            spawn_controller=SpawnController(boundary, spawn_states, spawn_masks))
+    types = torch.zeros(B, A, dtype=torch.long)
+    sim, _ = make_sim("carla_Town01", B, A, gen, types=types, type_names=["vehicle", "pedestrian"], with_lights=False,
+                      npc_controller=ctrl)
+    st = sim.get_state().clone()
+    st[..., :2] = base.reshape(B, 1, 2) + 6.0 * torch.randn(B, A, 2, generator=gen)
+    sim.set_state(st)
+    out = dict(replay=replay.numpy(), replay_present=replay_present.numpy(), boundary=boundary.numpy(),
+               spawn_states=spawn_states.numpy(), spawn_masks=spawn_masks.numpy(), npc_size=npc_size.numpy(),
+               npc_types=npc_types.numpy(), agent_state0=st.numpy(), agent_size=sim.get_agent_size().numpy(),
+               lr=sim.kinematic_model.get_params()["lr"].numpy())
+    actions = torch.rand(6, B, A, 2, generator=gen) * 2 - 1
+    out["actions"] = actions.numpy()
+    states, presents, colls, absol = [], [], [], []
+    for t in range(6):
+        sim.step(actions[t])
+        states.append(sim.get_npc_state().numpy().copy())
+        presents.append(sim.get_npc_present_mask().numpy().copy())
+        colls.append(sim.compute_collision().numpy().copy())
+        absol.append(sim.get_all_agents_absolute().numpy().copy())
+    out.update(npc_state=np.stack(states), npc_present=np.stack(presents), collision=np.stack(colls), absolute=np.stack(absol),
+               relative=sim.get_all_agents_relative().numpy(), agent_state=sim.get_state().numpy(),
+               image=sim.render_egocentric().numpy())
+    np.savez_compressed(os.path.join(HERE, "npc.npz"), **out)
+    print("npc: present per step", np.stack(presents).sum((1, 2)), "collisions", np.stack(colls).sum(), "image", out["image"].shape)
+
+
 def golden_traffic():
     """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
     simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
@@ -242,6 +294,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc"]
     for w in which:
         globals()["golden_" + w]()

@@ -8,7 +8,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _make(B, A, seed, lights):
+def _make(B, A, seed, lights, npcs=0):
     import torchdrivesim_b200 as tds
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(seed)
@@ -23,17 +23,24 @@ def _make(B, A, seed, lights):
         pos = torch.tensor(town.traffic_light_poses(), device=dev)[None].expand(B, -1, -1).contiguous()
         replay = torch.tensor(rng.integers(0, 3, (B, pos.shape[1], 6)), device=dev)
         tc = {"traffic_light": tds.TrafficLightControl(pos, replay_states=replay)}
+    ctrl = None
+    if npcs:
+        log = np.concatenate([state[:, :1, None, :2] + rng.normal(0, 8, (B, npcs, 4, 2)), rng.uniform(0, 5, (B, npcs, 4, 2))], -1)
+        spawn = tds.SpawnController(None, torch.tensor(log[:, :, ::-1].copy(), dtype=torch.float32, device=dev).repeat(1, 1, 2, 1),
+                                    torch.tensor(rng.uniform(size=(B, npcs, 8)) > 0.5, device=dev))
+        ctrl = tds.ReplayController(torch.full((B, npcs, 2), 2.0, device=dev), torch.tensor(log, dtype=torch.float32, device=dev),
+                                    torch.tensor(rng.uniform(size=(B, npcs, 4)) > 0.4, device=dev), spawn_controller=spawn)
     sim = tds.Simulator(town, km, torch.tensor(size, device=dev), torch.tensor(present, device=dev),
-                        tds.TorchDriveConfig(left_handed_coordinates=True), traffic_controls=tc)
+                        tds.TorchDriveConfig(left_handed_coordinates=True), traffic_controls=tc, npc_controller=ctrl)
     acts = torch.tensor(rng.uniform(-1, 1, (5, B, A, 2)).astype(np.float32), device=dev)
     return sim, acts
 
 
-@pytest.mark.parametrize("lights", [False, True])
-def test_graph_replay_equals_eager(lights):
+@pytest.mark.parametrize("lights,npcs", [(False, 0), (True, 0), (True, 3)])
+def test_graph_replay_equals_eager(lights, npcs):
     import torchdrivesim_b200 as tds
-    eager, acts = _make(6, 5, 3, lights)
-    graphed_sim, _ = _make(6, 5, 3, lights)
+    eager, acts = _make(6, 5, 3, lights, npcs)
+    graphed_sim, _ = _make(6, 5, 3, lights, npcs)
     runner = tds.GraphedHotPath(graphed_sim)
     for t in range(acts.shape[0]):
         eager.step(acts[t])
@@ -43,4 +50,7 @@ def test_graph_replay_equals_eager(lights):
         assert torch.equal(runner.state, eager.get_state()), f"state differs at step {t}"
         assert torch.equal(img_g, img_e), f"image differs at step {t}"
         assert torch.equal(coll_g, coll_e) and torch.equal(off_g, off_e)
+        if npcs:
+            assert torch.equal(graphed_sim.get_npc_state(), eager.get_npc_state())
+            assert torch.equal(graphed_sim.get_npc_present_mask(), eager.get_npc_present_mask())
     assert graphed_sim.internal_time == eager.internal_time == acts.shape[0]

@@ -116,3 +116,21 @@ def test_agents_relative_oracle_matches_reference():
         np.testing.assert_allclose(got, g[key], rtol=1e-5, atol=2e-5)
         assert np.array_equal(got[..., 3:], g[key][..., 3:])
     assert np.abs(g["absolute"][..., 2]).max() > np.pi          # the angle wrap is exercised
+
+
+def test_npc_oracle_matches_reference():
+    """oracle/npc.py against ReplayController + SpawnController stepping inside the unmodified reference Simulator."""
+    from oracle import npc
+    g = util.golden("npc")
+    T = g["replay"].shape[2]
+    state, present = g["replay"][:, :, 0], g["replay_present"][:, :, 0]
+    t_replay = 0
+    for step in range(g["npc_state"].shape[0]):
+        t_replay = (t_replay + 1) % T
+        state, present = npc.npc_advance(state, present, g["replay"], g["replay_present"], t_replay, g["boundary"],
+                                         g["spawn_states"], g["spawn_masks"], step)
+        assert np.array_equal(present, g["npc_present"][step]), step
+        assert np.array_equal(state, g["npc_state"][step]), step
+    # despawning and spawning both happen in the fixture
+    inside = npc.is_inside_polygon(g["replay"][:, :, 1, :2], g["boundary"])
+    assert 0 < inside.sum() < inside.size and g["spawn_masks"].any()

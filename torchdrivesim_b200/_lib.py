@@ -65,6 +65,8 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tds_traffic_light_violation": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                               c_float, c_void_p, c_void_p]),
+    "tds_npc_advance": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                  c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "tds_agents_relative": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "tds_map_create": (c_void_p, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_float, c_float]),
     "tds_map_destroy": (None, [c_void_p]),

@@ -212,3 +212,64 @@ extern "C" int tds_kinematic_step_bwd(const float* d_state, const float* d_actio
     TDS_LAUNCH_OK();
     return TDS_OK;
 }
+
+// ---- replayed NPCs with spawning / despawning: ReplayController.advance_npcs (behavior/replay.py:54-60) followed by
+// SpawnController.spawn_despawn_npcs (simulator.py:71-85), one thread per NPC:
+//   state, present <- replay[t_replay]                       (if a replay log is given)
+//   present &= is_inside_polygon(xy, exit_boundary)          (utils.py:99-122; all edge functions >= 0 or all < 0)
+//   spawn = spawn_mask[t_spawn] & !present;  present |= spawn;  state <- spawn ? spawn_state[t_spawn] : state
+namespace {
+__global__ void __launch_bounds__(128) npc_advance_kernel(const float4* __restrict__ replay, const uint8_t* __restrict__ replay_present,
+                                                          int T, int t_replay, const float2* __restrict__ boundary, int V,
+                                                          const float4* __restrict__ spawn_states,
+                                                          const uint8_t* __restrict__ spawn_masks, int Ts, int t_spawn,
+                                                          float4* __restrict__ state, uint8_t* __restrict__ present, int B,
+                                                          int Np) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (int64_t)B * Np) return;
+    const int b = (int)(g / Np);
+    float4 s = state[g];
+    bool here = present[g] != 0;
+    if (replay) {
+        s = replay[g * T + t_replay];
+        here = replay_present ? replay_present[g * T + t_replay] != 0 : true;
+    }
+    if (boundary) {
+        const float2* poly = boundary + (int64_t)b * V;
+        int right = 0;
+        for (int i = 0; i < V; i++) {
+            const float2 p0 = poly[i], p1 = poly[i + 1 == V ? 0 : i + 1];
+            const float ea = p1.y - p0.y, eb = p0.x - p1.x;
+            const float ec = (-ea) * p0.x - eb * p0.y;
+            right += ((ea * s.x + eb * s.y) + ec) >= 0.0f;
+        }
+        here = here && (right == V || right == 0);
+    }
+    if (spawn_states) {
+        const bool spawn = spawn_masks[g * Ts + t_spawn] != 0 && !here;
+        here = here || spawn;
+        if (spawn) s = spawn_states[g * Ts + t_spawn];
+    }
+    state[g] = s;
+    present[g] = here ? 1 : 0;
+}
+}  // namespace
+
+extern "C" int tds_npc_advance(const float* d_replay_states, const uint8_t* d_replay_present, int32_t T, int32_t t_replay,
+                               const float* d_exit_boundary, int32_t V, const float* d_spawn_states,
+                               const uint8_t* d_spawn_masks, int32_t Ts, int32_t t_spawn, float* d_npc_state,
+                               uint8_t* d_npc_present, int32_t B, int32_t Np, void* stream) {
+    TDS_REQUIRE(B >= 0 && Np >= 0, "npc_advance: negative size");
+    if (B == 0 || Np == 0) return TDS_OK;
+    TDS_REQUIRE(d_npc_state && d_npc_present, "npc_advance: null pointer");
+    TDS_REQUIRE(!d_replay_states || (T > 0 && t_replay >= 0 && t_replay < T), "npc_advance: replay time %d outside [0,%d)", t_replay, T);
+    TDS_REQUIRE(!d_exit_boundary || V >= 1, "npc_advance: empty exit boundary");
+    TDS_REQUIRE(!d_spawn_states || (d_spawn_masks && Ts > 0 && t_spawn >= 0 && t_spawn < Ts),
+                "npc_advance: spawn time %d outside [0,%d) (or null spawn masks)", t_spawn, Ts);
+    const int64_t n = (int64_t)B * Np;
+    npc_advance_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const float4*)d_replay_states, d_replay_present, T, t_replay, (const float2*)d_exit_boundary, V,
+        (const float4*)d_spawn_states, d_spawn_masks, Ts, t_spawn, (float4*)d_npc_state, d_npc_present, B, Np);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}

@@ -39,6 +39,12 @@ class GraphedHotPath:
             buf = control.state.detach().clone()
             control.set_state(buf)
             self._control_state[name] = buf
+        # so do the NPCs: the controller advances eagerly (one launch) into static buffers
+        self._npc_state = self._npc_present = None
+        if sim.npc_count > 0:
+            self._npc_state = sim.npc_controller.npc_state.detach().to(torch.float32).clone()
+            self._npc_present = sim.npc_controller.npc_present_mask.detach().clone()
+            sim.npc_controller.npc_state, sim.npc_controller.npc_present_mask = self._npc_state, self._npc_present
         sim.kinematic_model.set_state(self.state)
         # warm up on a side stream (allocator, lazily built map handles), then capture
         s = torch.cuda.Stream(device=dev)
@@ -58,7 +64,7 @@ class GraphedHotPath:
     def _body(self) -> None:
         sim = self.sim
         sim.kinematic_model.set_state(self.state)
-        sim.kinematic_model.step(self.action)        # Simulator.step minus the host-side control stepping
+        sim.kinematic_model.step(self.action)        # Simulator.step minus the host-side control / NPC stepping
         self.state.copy_(sim.get_state())           # the graph chains steps through this static buffer
         sim.kinematic_model.set_state(self.state)
         if self._render:
@@ -77,6 +83,13 @@ class GraphedHotPath:
             if control.state is not buf:
                 buf.copy_(control.state)             # ... lands in the buffer the graph reads
                 control.set_state(buf)
+        if self._npc_state is not None:
+            ctrl = self.sim.npc_controller
+            ctrl.advance_npcs(self.sim)
+            if ctrl.npc_state is not self._npc_state:
+                self._npc_state.copy_(ctrl.npc_state)
+                self._npc_present.copy_(ctrl.npc_present_mask)
+                ctrl.npc_state, ctrl.npc_present_mask = self._npc_state, self._npc_present
         self.graph.replay()
         return self.images, self.collision, self.offroad
 

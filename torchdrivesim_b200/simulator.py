@@ -7,8 +7,9 @@ tensor conventions:
     compute_collision       :1161-1194             -> ONE all-pairs launch instead of a Python loop over agents
     compute_offroad         :1035-1044             -> grid-accelerated point-to-mesh kernel
 
-NPC / spawn controllers, waypoint goals, observation noise and lanelet-based losses are out of scope
-(SURVEY.md §2); all agents live in the kinematic model.
+    npc_controller.advance_npcs :854 (+ :54-124, behavior/replay.py:46-107) -> one replay / spawn / despawn launch
+
+Waypoint goal bookkeeping, observation noise and lanelet-based losses are out of scope.
 """
 import copy as _copy
 from dataclasses import dataclass, field
@@ -23,6 +24,7 @@ from . import _lib, ops
 from .kinematic import KinematicModel
 from .maps import MapSet, StaticMap
 from .mesh import B200BirdviewMeshGenerator
+from .npc import NPCController
 from .rendering import B200RendererConfig, BirdviewRenderer, RendererConfig, Resolution, renderer_from_config
 
 
@@ -47,7 +49,7 @@ class Simulator:
                  initial_present_mask: Tensor, cfg: TorchDriveConfig, renderer: Optional[BirdviewRenderer] = None,
                  birdview_mesh_generator: Optional[B200BirdviewMeshGenerator] = None, internal_time: int = 0,
                  traffic_controls: Optional[Dict[str, object]] = None, agent_types: Optional[Tensor] = None,
-                 agent_type_names: Optional[List[str]] = None):
+                 agent_type_names: Optional[List[str]] = None, npc_controller: Optional[NPCController] = None):
         self.road_mesh = road_mesh if isinstance(road_mesh, MapSet) else MapSet([road_mesh])
         self.kinematic_model = kinematic_model
         self.agent_size = agent_size
@@ -59,6 +61,15 @@ class Simulator:
         self.traffic_controls = traffic_controls
         self.internal_time = internal_time
         state = self.get_state()
+        if npc_controller is None:
+            # simulator.py:337-345: an empty controller, so that "all agents" are the controlled agents
+            dev = initial_present_mask.device
+            npc_controller = NPCController(npc_size=torch.zeros((self._batch_size, 0, 2), dtype=agent_size.dtype, device=dev),
+                                           npc_state=torch.zeros((self._batch_size, 0, 4), dtype=state.dtype, device=dev),
+                                           npc_present_mask=torch.zeros((self._batch_size, 0), dtype=torch.bool, device=dev),
+                                           npc_types=torch.zeros((self._batch_size, 0), dtype=torch.long, device=dev),
+                                           agent_type_names=self._agent_types)
+        self.npc_controller = npc_controller
         if state.dim() != 3 or agent_size.shape[:2] != state.shape[:2] or initial_present_mask.shape != state.shape[:2]:
             raise _lib.TdsError("expected state [B,A,4], agent_size [B,A,2] and present mask [B,A]")
         if renderer is None:
@@ -110,11 +121,37 @@ class Simulator:
     def get_present_mask(self) -> Tensor:
         return self.present_mask
 
-    # no NPCs: "all agents" are the controlled agents
-    get_all_agent_state = get_state
-    get_all_agent_size = get_agent_size
-    get_all_agent_type = get_agent_type
-    get_all_agent_present_mask = get_present_mask
+    # ---- NPCs and "all agents" = controlled agents followed by NPCs (simulator.py:526-532, 681-728)
+    @property
+    def npc_count(self) -> int:
+        return self.get_npc_size().shape[-2]
+
+    def get_npc_state(self) -> Tensor:
+        return self.npc_controller.get_npc_state()
+
+    def get_npc_size(self) -> Tensor:
+        return self.npc_controller.get_npc_size()
+
+    def get_npc_present_mask(self) -> Tensor:
+        return self.npc_controller.get_npc_present_mask()
+
+    def get_npc_types(self) -> Tensor:
+        return self.npc_controller.get_npc_types()
+
+    def _with_npcs(self, agents: Tensor, npcs: Tensor, dim: int) -> Tensor:
+        return agents if npcs.shape[1] == 0 else torch.cat([agents, npcs.to(agents.dtype)], dim=dim)
+
+    def get_all_agent_state(self) -> Tensor:
+        return self._with_npcs(self.get_state(), self.get_npc_state(), -2)
+
+    def get_all_agent_size(self) -> Tensor:
+        return self._with_npcs(self.get_agent_size(), self.get_npc_size(), -2)
+
+    def get_all_agent_type(self) -> Tensor:
+        return self._with_npcs(self.get_agent_type(), self.get_npc_types(), -1)
+
+    def get_all_agent_present_mask(self) -> Tensor:
+        return self._with_npcs(self.get_present_mask(), self.get_npc_present_mask(), -1)
 
     def get_traffic_controls(self):
         return self.traffic_controls
@@ -130,6 +167,7 @@ class Simulator:
         self.birdview_mesh_generator = self.birdview_mesh_generator.to(device)
         if self.traffic_controls is not None:
             self.traffic_controls = {k: v.to(device) for k, v in self.traffic_controls.items()}
+        self.npc_controller = self.npc_controller.to(device)
         return self
 
     def copy(self):
@@ -139,6 +177,7 @@ class Simulator:
         other.birdview_mesh_generator = self.birdview_mesh_generator.copy()
         if self.traffic_controls is not None:
             other.traffic_controls = {k: v.copy() for k, v in self.traffic_controls.items()}
+        other.npc_controller = self.npc_controller.copy()
         return other
 
     def select_batch_elements(self, idx: Tensor, in_place: bool = True):
@@ -152,6 +191,7 @@ class Simulator:
         other.birdview_mesh_generator = other.birdview_mesh_generator.select_batch_elements(idx)
         if other.traffic_controls is not None:
             other.traffic_controls = {k: v.select_batch_elements(idx, in_place=in_place) for k, v in other.traffic_controls.items()}
+        other.npc_controller = other.npc_controller.select_batch_elements(idx, in_place=in_place)
         other._batch_size = int(idx.numel())
         return other
 
@@ -161,6 +201,7 @@ class Simulator:
         if agent_action.dim() != 3 or agent_action.shape[0] != self.batch_size or agent_action.shape[-2] != self.agent_count:
             raise _lib.TdsError(f"action must be [B={self.batch_size}, A={self.agent_count}, Ac]")
         self.kinematic_model.step(agent_action)
+        self.npc_controller.advance_npcs(self)             # simulator.py:854
         if self.traffic_controls is not None:
             for control in self.traffic_controls.values():
                 control.step(self.internal_time)
@@ -255,13 +296,13 @@ class Simulator:
 
     # ---- non-visual observations (simulator.py:730-781) --------------------------------------------
     def get_all_agents_absolute(self) -> Tensor:
-        """Bx(A)x6: x, y, psi, length, width, present (simulator.py:730-738; no NPCs here)."""
-        return torch.cat([self.get_state()[..., :3], self.get_agent_size()[..., :2],
-                          self.get_present_mask().unsqueeze(-1).to(torch.float32)], dim=-1)
+        """Bx(A+Npc)x6: x, y, psi, length, width, present (simulator.py:730-738)."""
+        return torch.cat([self.get_all_agent_state()[..., :3], self.get_all_agent_size()[..., :2],
+                          self.get_all_agent_present_mask().unsqueeze(-1).to(torch.float32)], dim=-1)
 
     def get_all_agents_relative(self, exclude_self: bool = True) -> Tensor:
-        """BxAx(A-1 or A)x6: the pose of every agent in the frame of every agent (simulator.py:748-781), one launch
-        and no host synchronisation."""
+        """BxAx(A+Npc-1 or A+Npc)x6: the pose of every agent and NPC in the frame of every controlled agent
+        (simulator.py:748-781), one launch and no host synchronisation."""
         return ops.agents_relative(self.get_all_agents_absolute(), self.agent_count, exclude_self)
 
     def compute_offroad(self) -> Tensor:
@@ -287,4 +328,8 @@ class Simulator:
         if box.shape[-2] == 0:
             return torch.zeros_like(box[..., 0])
         metric = _lib.METRIC_IOU if self.cfg.collision_metric == CollisionMetric.iou else _lib.METRIC_DISCS
-        return ops.collision_allpairs(box, box, self.get_all_agent_present_mask(), metric, ego_is_prefix=True)
+        all_box = box
+        if self.npc_count > 0:
+            all_state, all_size = self.get_all_agent_state(), self.get_all_agent_size()[..., :2]
+            all_box = torch.cat([all_state[..., :2], all_size, all_state[..., 2:3]], dim=-1)
+        return ops.collision_allpairs(box, all_box, self.get_all_agent_present_mask(), metric, ego_is_prefix=True)
