@@ -136,6 +136,20 @@ int tds_npc_advance(const float* d_replay_states, const uint8_t* d_replay_presen
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Waypoint goals.  Replaces WaypointGoal.step (goals.py:159-217) and get_waypoints / get_masks (goals.py:33-105).
+ *   d_waypoints [n_agents,N,M,2]: N collections of M waypoints per agent; d_mask [n_agents,N,M] uint8 (0 = padding or
+ *   achieved); d_state [n_agents] int64 = current collection of each agent; d_agent_state [n_agents,4] (x, y, psi, v).
+ * step:   if the agent is within `threshold` of a masked-in waypoint of its current collection, the collection's mask
+ *         is cleared and the state advances (clamped to N-1); mask and state are updated in place.
+ * gather: the next `count` collections of every agent -> d_out_waypoints [n_agents,count*M,2], d_out_mask
+ *         [n_agents,count*M]; collections past the last one are zeros / masked out.
+ * ---------------------------------------------------------------------------------------- */
+int tds_waypoint_step(const float* d_agent_state, const float* d_waypoints, uint8_t* d_mask, int64_t* d_state,
+                      int64_t n_agents, int32_t N, int32_t M, float threshold, void* stream);
+int tds_waypoint_gather(const float* d_waypoints, const uint8_t* d_mask, const int64_t* d_state, int64_t n_agents,
+                        int32_t N, int32_t M, int32_t count, float* d_out_waypoints, uint8_t* d_out_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Non-visual observations.  Replaces Simulator.get_all_agents_relative (simulator.py:748-781) with
  * utils.relative (utils.py:71-79): for every origin agent i < A and every agent j < N of the same environment
  *   out = ( R(-psi_i) (xy_j - xy_i),  normalize_angle(psi_j - psi_i),  length_j, width_j, present_j ).

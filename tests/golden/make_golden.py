@@ -267,6 +267,44 @@ def golden_npc():
     print("npc: present per step", np.stack(presents).sum((1, 2)), "collisions", np.stack(colls).sum(), "image", out["image"].shape)
 
 
+def golden_goals():
+    """Waypoint goals (goals.py:11-217) inside Simulator.step (simulator.py:860-861): collections of M waypoints that
+    are achieved within 2 m and progressively enabled; state, masks and gathered waypoints after every step, and the
+    egocentric frame with the next two collections drawn."""
+    from torchdrivesim.goals import WaypointGoal
+    gen = torch.Generator().manual_seed(909)
+    B, A, N, M, steps = 2, 3, 4, 3, 8
+    sim, _ = make_sim("carla_Town01", B, A, gen, with_lights=False)
+    st = sim.get_state().clone()
+    st[:, 1:, :2] = st[:, :1, :2] + 10.0 * torch.randn(B, A - 1, 2, generator=gen)
+    st[..., 3] = 4.0
+    sim.set_state(st)
+    # collection n of an agent lies about 1.2 n metres ahead of it, so driving straight reaches them one after the other
+    ahead = torch.stack([torch.cos(st[..., 2]), torch.sin(st[..., 2])], -1)
+    wp = st[:, :, None, None, :2] + ahead[:, :, None, None] * (1.5 + 1.2 * torch.arange(N).reshape(1, 1, N, 1, 1)) \
+        + 1.5 * torch.randn(B, A, N, M, 2, generator=gen)
+    mask = torch.rand(B, A, N, M, generator=gen) > 0.3
+    mask[0, 0, 1] = False                       # a collection that is all padding
+    sim.waypoint_goals = WaypointGoal(wp.clone(), mask.clone())
+    out = dict(waypoints=wp.numpy(), mask=mask.numpy(), state0=st.numpy(), size=sim.get_agent_size().numpy(),
+               lr=sim.kinematic_model.get_params()["lr"].numpy())
+    actions = torch.zeros(steps, B, A, 2)
+    actions[..., 1] = 0.1 * (torch.rand(steps, B, A, generator=gen) - 0.5)
+    out["actions"] = actions.numpy()
+    gs, gm, w1, m1, w2, m2 = [], [], [], [], [], []
+    for t in range(steps):
+        sim.step(actions[t])
+        gs.append(sim.get_waypoints_state().numpy().copy())
+        gm.append(sim.waypoint_goals.mask.numpy().copy())
+        w1.append(sim.get_waypoints().numpy().copy()); m1.append(sim.get_waypoints_mask().numpy().copy())
+        w2.append(sim.get_waypoints(count=2).numpy().copy()); m2.append(sim.get_waypoints_mask(count=2).numpy().copy())
+    out.update(goal_state=np.stack(gs), goal_mask=np.stack(gm), wp1=np.stack(w1), m1=np.stack(m1), wp2=np.stack(w2),
+               m2=np.stack(m2), agent_state=sim.get_state().numpy(),
+               image=sim.render_egocentric(n_subsequent_waypoints=2).numpy())
+    np.savez_compressed(os.path.join(HERE, "goals.npz"), **out)
+    print("goals: final state", np.stack(gs)[-1, ..., 0].tolist(), "masks left", int(np.stack(gm)[-1].sum()), "of", int(mask.sum()))
+
+
 def golden_traffic():
     """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
     simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
@@ -294,6 +332,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals"]
     for w in which:
         globals()["golden_" + w]()

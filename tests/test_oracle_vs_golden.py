@@ -134,3 +134,21 @@ def test_npc_oracle_matches_reference():
     # despawning and spawning both happen in the fixture
     inside = npc.is_inside_polygon(g["replay"][:, :, 1, :2], g["boundary"])
     assert 0 < inside.sum() < inside.size and g["spawn_masks"].any()
+
+
+def test_goals_oracle_matches_reference():
+    """oracle/goals.py against WaypointGoal stepping inside the unmodified reference Simulator."""
+    from oracle import goals, kinematic as OK
+    import torch
+    g = util.golden("goals")
+    mask, state = g["mask"], np.zeros(g["mask"].shape[:2] + (1,), np.int64)
+    st = torch.tensor(g["state0"])
+    for t in range(g["actions"].shape[0]):
+        st = OK.bicycle_step(st, torch.tensor(g["actions"][t]), torch.tensor(g["lr"]), 0.1, True)
+        mask, state = goals.waypoint_step(st.numpy()[..., :2], g["waypoints"], mask, state, 2.0)
+        assert np.array_equal(state, g["goal_state"][t]), t
+        assert np.array_equal(mask, g["goal_mask"][t]), t
+        for count, kw, km in ((1, "wp1", "m1"), (2, "wp2", "m2")):
+            w, m = goals.gather(g["waypoints"], mask, state, count)
+            assert np.array_equal(w, g[kw][t]) and np.array_equal(m, g[km][t])
+    assert g["goal_state"][-1].max() == g["mask"].shape[2] - 1 and g["goal_state"][-1].min() < g["mask"].shape[2] - 1

@@ -13,6 +13,7 @@ from .rendering import (B200Renderer, B200RendererConfig, BirdviewRenderer, Rend
                         Resolution, renderer_from_config)
 from .infractions import (collision_allpairs, collision_detection_with_discs, iou_differentiable,  # noqa: F401
                           offroad_infraction_loss)
+from .goals import WaypointGoal  # noqa: F401
 from .npc import NPCController, ReplayController, SpawnController  # noqa: F401
 from .simulator import CollisionMetric, Simulator, TorchDriveConfig  # noqa: F401
 from .graph import GraphedHotPath  # noqa: F401

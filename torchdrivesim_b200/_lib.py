@@ -67,6 +67,8 @@ SIGNATURES = {
                                               c_float, c_void_p, c_void_p]),
     "tds_npc_advance": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                   c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "tds_waypoint_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
+    "tds_waypoint_gather": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tds_agents_relative": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "tds_map_create": (c_void_p, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_float, c_float]),
     "tds_map_destroy": (None, [c_void_p]),

@@ -273,3 +273,68 @@ extern "C" int tds_npc_advance(const float* d_replay_states, const uint8_t* d_re
     TDS_LAUNCH_OK();
     return TDS_OK;
 }
+
+// ---- waypoint goals (goals.py:159-217): collection state[b,a] of M waypoints is achieved when the agent is within
+// `threshold` of any of its non-padding waypoints; its mask entries are then cleared and the state advances
+// (clamped to the last collection).  One thread per agent.
+namespace {
+__global__ void __launch_bounds__(128) waypoint_step_kernel(const float4* __restrict__ agent_state, const float2* __restrict__ waypoints,
+                                                            uint8_t* __restrict__ mask, int64_t* __restrict__ state,
+                                                            int64_t n_agents, int N, int M, float threshold) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_agents) return;
+    const int64_t st = min(max(state[g], (int64_t)0), (int64_t)N - 1);
+    const int64_t base = (g * N + st) * M;
+    const float4 a = agent_state[g];
+    bool reached = false;
+    for (int m = 0; m < M; m++) {
+        const float2 w = waypoints[base + m];
+        const float dx = a.x - w.x, dy = a.y - w.y;
+        reached |= mask[base + m] != 0 && sqrtf(dx * dx + dy * dy) <= threshold;
+    }
+    if (reached) {
+        for (int m = 0; m < M; m++) mask[base + m] = 0;
+        state[g] = min(st + 1, (int64_t)N - 1);
+    }
+}
+
+// WaypointGoal.get_waypoints / get_masks (goals.py:33-105): the next `count` collections of every agent, zeros past the end
+__global__ void __launch_bounds__(256) waypoint_gather_kernel(const float2* __restrict__ waypoints, const uint8_t* __restrict__ mask,
+                                                              const int64_t* __restrict__ state, int64_t n_agents, int N, int M,
+                                                              int count, float2* __restrict__ out_wp, uint8_t* __restrict__ out_mask) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_agents * count * M) return;
+    const int m = (int)(t % M);
+    const int c = (int)((t / M) % count);
+    const int64_t g = t / ((int64_t)M * count);
+    const int64_t idx = state[g] + c;
+    const bool valid = idx < N;
+    const int64_t src = (g * N + min(max(idx, (int64_t)0), (int64_t)N - 1)) * M + m;
+    out_wp[t] = valid ? waypoints[src] : make_float2(0.0f, 0.0f);
+    out_mask[t] = valid ? mask[src] : 0;
+}
+}  // namespace
+
+extern "C" int tds_waypoint_step(const float* d_agent_state, const float* d_waypoints, uint8_t* d_mask, int64_t* d_state,
+                                 int64_t n_agents, int32_t N, int32_t M, float threshold, void* stream) {
+    TDS_REQUIRE(n_agents >= 0 && N >= 1 && M >= 0, "waypoint_step: need n_agents >= 0, N >= 1, M >= 0");
+    if (n_agents == 0 || M == 0) return TDS_OK;
+    TDS_REQUIRE(d_agent_state && d_waypoints && d_mask && d_state, "waypoint_step: null pointer");
+    waypoint_step_kernel<<<(unsigned)((n_agents + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const float4*)d_agent_state, (const float2*)d_waypoints, d_mask, d_state, n_agents, N, M, threshold);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_waypoint_gather(const float* d_waypoints, const uint8_t* d_mask, const int64_t* d_state, int64_t n_agents,
+                                   int32_t N, int32_t M, int32_t count, float* d_out_waypoints, uint8_t* d_out_mask,
+                                   void* stream) {
+    TDS_REQUIRE(n_agents >= 0 && N >= 1 && M >= 0 && count >= 1, "waypoint_gather: need n_agents >= 0, N >= 1, M >= 0, count >= 1");
+    const int64_t n = n_agents * count * M;
+    if (n == 0) return TDS_OK;
+    TDS_REQUIRE(d_waypoints && d_mask && d_state && d_out_waypoints && d_out_mask, "waypoint_gather: null pointer");
+    waypoint_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)d_waypoints, d_mask, d_state, n_agents, N, M, count, (float2*)d_out_waypoints, d_out_mask);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}

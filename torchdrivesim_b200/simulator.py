@@ -24,6 +24,7 @@ from . import _lib, ops
 from .kinematic import KinematicModel
 from .maps import MapSet, StaticMap
 from .mesh import B200BirdviewMeshGenerator
+from .goals import WaypointGoal
 from .npc import NPCController
 from .rendering import B200RendererConfig, BirdviewRenderer, RendererConfig, Resolution, renderer_from_config
 
@@ -41,6 +42,7 @@ class TorchDriveConfig:
     single_agent_rendering: bool = False
     collision_metric: CollisionMetric = CollisionMetric.discs
     offroad_threshold: float = 0.5
+    waypoint_removal_threshold: float = 2.0    # how close an agent must get to a waypoint to achieve it
     left_handed_coordinates: bool = False
 
 
@@ -49,7 +51,8 @@ class Simulator:
                  initial_present_mask: Tensor, cfg: TorchDriveConfig, renderer: Optional[BirdviewRenderer] = None,
                  birdview_mesh_generator: Optional[B200BirdviewMeshGenerator] = None, internal_time: int = 0,
                  traffic_controls: Optional[Dict[str, object]] = None, agent_types: Optional[Tensor] = None,
-                 agent_type_names: Optional[List[str]] = None, npc_controller: Optional[NPCController] = None):
+                 agent_type_names: Optional[List[str]] = None, npc_controller: Optional[NPCController] = None,
+                 waypoint_goals: Optional[WaypointGoal] = None):
         self.road_mesh = road_mesh if isinstance(road_mesh, MapSet) else MapSet([road_mesh])
         self.kinematic_model = kinematic_model
         self.agent_size = agent_size
@@ -70,6 +73,7 @@ class Simulator:
                                            npc_types=torch.zeros((self._batch_size, 0), dtype=torch.long, device=dev),
                                            agent_type_names=self._agent_types)
         self.npc_controller = npc_controller
+        self.waypoint_goals = waypoint_goals
         if state.dim() != 3 or agent_size.shape[:2] != state.shape[:2] or initial_present_mask.shape != state.shape[:2]:
             raise _lib.TdsError("expected state [B,A,4], agent_size [B,A,2] and present mask [B,A]")
         if renderer is None:
@@ -156,6 +160,16 @@ class Simulator:
     def get_traffic_controls(self):
         return self.traffic_controls
 
+    # ---- waypoint goals (simulator.py:589-605)
+    def get_waypoints(self, count: int = 1) -> Optional[Tensor]:
+        return self.waypoint_goals.get_waypoints(count=count) if self.waypoint_goals is not None else None
+
+    def get_waypoints_state(self) -> Optional[Tensor]:
+        return self.waypoint_goals.state if self.waypoint_goals is not None else None
+
+    def get_waypoints_mask(self, count: int = 1) -> Optional[Tensor]:
+        return self.waypoint_goals.get_masks(count=count) if self.waypoint_goals is not None else None
+
     # ---- batch plumbing (simulator.py:401-517) -------------------------------------------------
     def to(self, device):
         self.kinematic_model = self.kinematic_model.to(device)
@@ -168,6 +182,7 @@ class Simulator:
         if self.traffic_controls is not None:
             self.traffic_controls = {k: v.to(device) for k, v in self.traffic_controls.items()}
         self.npc_controller = self.npc_controller.to(device)
+        self.waypoint_goals = self.waypoint_goals.to(device) if self.waypoint_goals is not None else None
         return self
 
     def copy(self):
@@ -178,6 +193,7 @@ class Simulator:
         if self.traffic_controls is not None:
             other.traffic_controls = {k: v.copy() for k, v in self.traffic_controls.items()}
         other.npc_controller = self.npc_controller.copy()
+        other.waypoint_goals = self.waypoint_goals.copy() if self.waypoint_goals is not None else None
         return other
 
     def select_batch_elements(self, idx: Tensor, in_place: bool = True):
@@ -192,6 +208,8 @@ class Simulator:
         if other.traffic_controls is not None:
             other.traffic_controls = {k: v.select_batch_elements(idx, in_place=in_place) for k, v in other.traffic_controls.items()}
         other.npc_controller = other.npc_controller.select_batch_elements(idx, in_place=in_place)
+        if other.waypoint_goals is not None:
+            other.waypoint_goals = other.waypoint_goals.select_batch_elements(idx, in_place=in_place)
         other._batch_size = int(idx.numel())
         return other
 
@@ -200,11 +218,13 @@ class Simulator:
         self.internal_time += 1
         if agent_action.dim() != 3 or agent_action.shape[0] != self.batch_size or agent_action.shape[-2] != self.agent_count:
             raise _lib.TdsError(f"action must be [B={self.batch_size}, A={self.agent_count}, Ac]")
-        self.kinematic_model.step(agent_action)
         self.npc_controller.advance_npcs(self)             # simulator.py:854
+        self.kinematic_model.step(agent_action)
         if self.traffic_controls is not None:
             for control in self.traffic_controls.values():
                 control.step(self.internal_time)
+        if self.waypoint_goals is not None:                # simulator.py:860-861
+            self.waypoint_goals.step(self.get_state(), self.internal_time, threshold=self.cfg.waypoint_removal_threshold)
 
     def set_state(self, agent_state: Tensor, mask: Optional[Tensor] = None) -> None:
         if mask is None:
@@ -241,8 +261,10 @@ class Simulator:
         return img.reshape((self.batch_size, n_cameras) + img.shape[1:])
 
     def render_egocentric(self, ego_rotate: bool = True, res: Optional[Resolution] = None, fov: Optional[float] = None,
-                          visibility_matrix: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
-        """One camera per agent -> BxAx3xHxW (simulator.py:994-1033)."""
+                          visibility_matrix: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                          n_subsequent_waypoints: int = 1) -> Tensor:
+        """One camera per agent -> BxAx3xHxW (simulator.py:994-1033); with waypoint goals every agent sees the discs of
+        its next `n_subsequent_waypoints` collections."""
         state = self.get_state().detach()
         camera_xy, camera_psi = state[..., :2], state[..., 2:3]
         if not ego_rotate:
@@ -251,7 +273,11 @@ class Simulator:
         if self.cfg.single_agent_rendering:
             rendering_mask = torch.eye(self.agent_count, dtype=torch.bool, device=state.device).unsqueeze(0).expand(
                 self.batch_size, -1, -1)
-        return self.render(camera_xy, camera_psi, rendering_mask=rendering_mask, res=res, fov=fov, out=out)
+        waypoints = waypoints_mask = None
+        if self.waypoint_goals is not None:
+            waypoints, waypoints_mask = self.waypoint_goals.get_waypoints_and_masks(count=n_subsequent_waypoints)
+        return self.render(camera_xy, camera_psi, rendering_mask=rendering_mask, res=res, fov=fov, out=out,
+                           waypoints=waypoints, waypoints_rendering_mask=waypoints_mask)
 
     def render_egocentric_to_host(self, host_out: Tensor, chunk_envs: int = 128, res: Optional[Resolution] = None,
                                   fov: Optional[float] = None) -> Tensor:
