@@ -129,7 +129,7 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     value = sample_envs * AGENTS * args.steps / dt
     sample = f"{sample_envs} of {ENVS_PER_GPU} environments x {AGENTS} agents per step, one process per core"
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "agent-env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -381,9 +381,18 @@ def run_ours(args):
             "infraction_metrics": {"collision_sum": float(metrics[0]), "offroad_sum": float(metrics[1]),
                                    "colliding_agent_steps": float(metrics[2]), "offroad_agent_steps": float(metrics[3])},
         }
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def _emit(text: str) -> None:
+    """The result line goes to the process's original stdout (see main)."""
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (text + "\n").encode())
 
 
 def main():
@@ -395,6 +404,12 @@ def main():
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling aid: only the device-resident loop (no e2e legs, no CPU baseline)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything else written to file descriptor 1 by this process or
+    # its libraries (NCCL prints its version banner there) goes to stderr instead
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
