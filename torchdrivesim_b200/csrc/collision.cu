@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(kWarps * 32) allpairs_fwd_kernel(const float* 
                                                                   int ego_is_prefix, float* __restrict__ out,
                                                                   int32_t* __restrict__ argmax) {
     extern __shared__ float smem[];
+    __shared__ int s_queue[METRIC == TDS_METRIC_IOU ? kWarps : 1][64];      // columns waiting for the clipping (IoU)
     constexpr int STRIDE = METRIC == TDS_METRIC_DISCS ? 13 : 7;   // odd strides: conflict-free column reads
     const int b = blockIdx.y;
     const int row0 = blockIdx.x * kRowsPerCta;
@@ -451,16 +452,50 @@ __global__ void __launch_bounds__(kWarps * 32) allpairs_fwd_kernel(const float* 
                 if (o > best) { best = o; besti = j; }
             }
         } else {
+            // Most pairs of a crowded scene end at the bounding-circle test and the few that need the clipping would
+            // each hold up their warp: the columns that pass the test are queued per warp and clipped 32 at a time,
+            // one per lane.  (best, besti) = the largest overlap and the lowest column that attains it, whatever
+            // the order the columns are visited in.
             const Box bp = make_box(p[0], p[1], p[2], p[3], p[4]);
-            for (int j = lane; j < N; j += 32) {
+            const float rp = 0.5f * sqrtf(bp.l * bp.l + bp.w * bp.w);
+            int* queue = s_queue[warp];
+            int nq = 0;                                   // uniform over the warp
+            auto take = [&](int j, float o) {
+                sum += o;
+                if (o > best || (o == best && j < besti)) { best = o; besti = j; }
+            };
+            auto clip = [&](int j) {
                 const float* s = smem + j * STRIDE;
                 Box bq;
                 bq.x = s[0]; bq.y = s[1]; bq.l = s[2]; bq.w = s[3]; bq.s = s[4]; bq.c = s[5];
-                float o = (ego_is_prefix && j == i) ? 1.0f : iou_pair(bp, bq);
-                o *= s[6];
-                sum += o;
-                if (o > best) { best = o; besti = j; }
+                take(j, iou_pair(bp, bq) * s[6]);
+            };
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const int j = j0 + lane;
+                bool cand = false;
+                if (j < N) {
+                    const float* s = smem + j * STRIDE;
+                    if (ego_is_prefix && j == i) {
+                        take(j, 1.0f * s[6]);
+                    } else {
+                        const float dx = s[0] - bp.x, dy = s[1] - bp.y;
+                        const float reach = rp + 0.5f * sqrtf(s[2] * s[2] + s[3] * s[3]);
+                        cand = s[6] != 0.0f && !(dx * dx + dy * dy > reach * reach * 1.0001f + 1e-6f);   // inter_area's own test
+                        if (!cand) take(j, 0.0f);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (cand) queue[nq + __popc(m & ((1u << lane) - 1u))] = j;
+                nq += __popc(m);
+                __syncwarp();
+                if (nq >= 32) {
+                    nq -= 32;
+                    clip(queue[nq + lane]);
+                    __syncwarp();
+                }
             }
+            if (lane < nq) clip(queue[lane]);
+            __syncwarp();
         }
         sum = tds::warp_sum(sum);
 #pragma unroll
