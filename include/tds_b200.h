@@ -158,7 +158,23 @@ int tds_waypoint_gather(const float* d_waypoints, const uint8_t* d_mask, const i
  *   boolean-mask indexing and hence no host synchronisation, unlike the reference).
  * ---------------------------------------------------------------------------------------- */
 int tds_agents_relative(const float* d_absolute, int32_t B, int32_t A, int32_t N, int32_t exclude_self,
-                        float* d_out, void* stream);
+                        int32_t per_origin, float* d_out, void* stream);
+/* per_origin != 0: d_absolute is [B,A,N,6], what each origin agent perceives (get_noisy_all_agents_relative,
+ * simulator.py:784-821); the origin of row i is its own entry d_absolute[b,i,i]. */
+
+/* ------------------------------------------------------------------------------------------
+ * Noisy observations.  Replaces StandardSensingObservationNoise (observation_noise.py:69-132):
+ * sensing_noise:     d_out[b,a,e,:] = d_all_state[b,e,:] + d_eps[b,a,e,:] * deviation(|xy_a - xy_e|), deviation = 0.19 /
+ *                    1.6 / 3.2 / 3.83 beyond 0.5 / 25 / 50 / 100 m (get_noisy_state; d_eps = standard normal deviates,
+ *                    [B,A,N,4]; the first A of the N agents are the observers).
+ * sensing_occlusion: d_out[b,a,e] = d_base_mask[b,e] and no third agent's circle (radius width/2) crosses the segment
+ *                    from observer a to agent e (get_noisy_present_mask with utils.line_circle_intersection,
+ *                    utils.py:139-187).  d_all_state [B,N,4], d_all_size [B,N,2], d_base_mask [B,N] uint8, d_out [B,A,N].
+ * ---------------------------------------------------------------------------------------- */
+int tds_sensing_noise(const float* d_all_state, const float* d_eps, int32_t B, int32_t A, int32_t N, float* d_out,
+                      void* stream);
+int tds_sensing_occlusion(const float* d_all_state, const float* d_all_size, const uint8_t* d_base_mask, int32_t B,
+                          int32_t A, int32_t N, uint8_t* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Static map: triangle mesh + uniform grids, built once per map per GPU.  Replaces the

@@ -25,3 +25,46 @@ def agents_relative(absolute, n_agents=None, exclude_self=True):
         keep = ~np.eye(A, N, dtype=bool)
         out = out[:, keep].reshape(B, A, N - 1, 6)
     return out
+
+
+def noisy_state(all_state, n_agents, eps):
+    """StandardSensingObservationNoise.get_noisy_state (observation_noise.py:74-89): all_state [B,N,4], eps [B,A,N,4]."""
+    s = np.asarray(all_state, np.float32)
+    A = n_agents
+    d = s[:, :A, None, :2] - s[:, None, :, :2]
+    dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1], dtype=np.float32)
+    dev = np.max(np.stack([np.float32(0.19) * (dist > 0.5), np.float32(1.6) * (dist > 25), np.float32(3.2) * (dist > 50),
+                           np.float32(3.83) * (dist > 100)], -1), -1).astype(np.float32)
+    return (s[:, None] + np.asarray(eps, np.float32) * dev[..., None]).astype(np.float32)
+
+
+def line_circle_intersection(p1, p2, centre, radius):
+    """utils.py:139-187, float32 operation by operation."""
+    f32 = np.float32
+    d = (p2 - p1).astype(f32)
+    f = (p1 - centre).astype(f32)
+    a = d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]
+    b = f32(2) * (f[..., 0] * d[..., 0] + f[..., 1] * d[..., 1])
+    c = (f[..., 0] * f[..., 0] + f[..., 1] * f[..., 1]) - radius * radius
+    disc = b * b - f32(4) * a * c
+    sq = np.sqrt(np.maximum(disc, f32(0)))
+    a_safe = np.where(np.abs(a) < f32(1e-8), f32(1e-8), a)
+    t1, t2 = (-b - sq) / (f32(2) * a_safe), (-b + sq) / (f32(2) * a_safe)
+    return (disc >= 0) & (np.minimum(t1, t2) <= 1) & (np.maximum(t1, t2) >= 0)
+
+
+def noisy_present_mask(all_state, all_size, base_mask, n_agents):
+    """StandardSensingObservationNoise.get_noisy_present_mask (observation_noise.py:91-132) -> bool [B,A,N]."""
+    s = np.asarray(all_state, np.float32)
+    r = (np.asarray(all_size, np.float32)[..., 1] / np.float32(2))
+    B, N = s.shape[:2]
+    A = n_agents
+    ego = s[:, :A, None, None, :2]
+    target = s[:, None, :, None, :2]
+    occ = s[:, None, None, :, :2]
+    hit = line_circle_intersection(np.broadcast_to(ego, (B, A, N, N, 2)), np.broadcast_to(target, (B, A, N, N, 2)),
+                                   np.broadcast_to(occ, (B, A, N, N, 2)), np.broadcast_to(r[:, None, None, :], (B, A, N, N)))
+    hit &= ~np.eye(N, dtype=bool)[None, None]
+    for a in range(A):
+        hit[:, a, :, a] = False
+    return np.asarray(base_mask, bool)[:, None] & ~hit.any(-1)

@@ -305,6 +305,43 @@ def golden_goals():
     print("goals: final state", np.stack(gs)[-1, ..., 0].tolist(), "masks left", int(np.stack(gm)[-1].sum()), "of", int(mask.sum()))
 
 
+def golden_noise():
+    """Noisy observations (observation_noise.py:69-132, simulator.py:663-679, 740-746, 784-821): distance-dependent
+    sensing noise (the normal deviates are re-drawn from the same seed and saved) and line-of-sight occlusion."""
+    from torchdrivesim.observation_noise import StandardSensingObservationNoise, StandardSensingObservationNoiseConfig
+    from torchdrivesim.simulator import NPCController
+    gen = torch.Generator().manual_seed(1010)
+    B, A, Np = 2, 6, 4
+    npc_state = torch.cat([40.0 * torch.randn(B, Np, 2, generator=gen), torch.rand(B, Np, 2, generator=gen) * 3], -1)
+    npc_size = torch.tensor(VEH[:2]).expand(B, Np, 2).clone()
+    npc_present = torch.rand(B, Np, generator=gen) > 0.3
+    present = torch.rand(B, A, generator=gen) > 0.2
+    sim, _ = make_sim("carla_Town01", B, A, gen, with_lights=False, present=present,
+                      npc_controller=NPCController(npc_size, npc_state, npc_present))
+    st = sim.get_state().clone()
+    st[..., :2] = 35.0 * torch.randn(B, A, 2, generator=gen)
+    st[0, 1, :2] = st[0, 0, :2] + 0.3                              # closer than 0.5 m: no noise
+    st[1, 2, :2] = st[1, 0, :2] * 0.5 + st[1, 1, :2] * 0.5         # exactly between two agents: occludes them
+    sim.set_state(st)
+    sim.npc_controller.npc_state[..., :2] += st[:, :1, :2] * 0.0
+    sim.observation_noise_model = StandardSensingObservationNoise(StandardSensingObservationNoiseConfig())
+    E = A + Np
+    out = dict(agent_state=st.numpy(), agent_size=sim.get_agent_size().numpy(), present=present.numpy(),
+               npc_state=npc_state.numpy(), npc_size=npc_size.numpy(), npc_present=npc_present.numpy())
+    torch.manual_seed(5); out["eps"] = torch.randn(B, A, E, 4).numpy()
+    torch.manual_seed(5); out["noisy_state"] = sim.get_noisy_state().numpy()
+    out["noisy_present"] = sim.get_noisy_present_mask().numpy()
+    out["noisy_size"] = sim.get_noisy_agent_size().numpy()
+    torch.manual_seed(5); out["noisy_absolute"] = sim.get_noisy_all_agents_absolute().numpy()
+    torch.manual_seed(5); out["noisy_relative"] = sim.get_noisy_all_agents_relative().numpy()
+    torch.manual_seed(5); out["noisy_relative_all"] = sim.get_noisy_all_agents_relative(exclude_self=False).numpy()
+    np.savez_compressed(os.path.join(HERE, "noise.npz"), **out)
+    base = np.concatenate([present.numpy(), npc_present.numpy()], -1)[:, None].repeat(A, 1)
+    print("noise: occluded", int((base & ~out["noisy_present"]).sum()), "of", int(base.sum()),
+          "deviations", np.unique(np.round(np.abs(out["noisy_state"] - np.concatenate([st.numpy(), npc_state.numpy()], 1)[:, None])
+                                           / np.maximum(np.abs(out["eps"]), 1e-9), 2)).tolist()[:8])
+
+
 def golden_traffic():
     """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
     simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
@@ -332,6 +369,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals", "noise"]
     for w in which:
         globals()["golden_" + w]()

@@ -152,3 +152,19 @@ def test_goals_oracle_matches_reference():
             w, m = goals.gather(g["waypoints"], mask, state, count)
             assert np.array_equal(w, g[kw][t]) and np.array_equal(m, g[km][t])
     assert g["goal_state"][-1].max() == g["mask"].shape[2] - 1 and g["goal_state"][-1].min() < g["mask"].shape[2] - 1
+
+
+def test_noise_oracle_matches_reference():
+    """oracle/observations.py against StandardSensingObservationNoise of the unmodified reference (same normal deviates)."""
+    from oracle import observations
+    g = util.golden("noise")
+    A = g["agent_state"].shape[1]
+    all_state = np.concatenate([g["agent_state"], g["npc_state"]], 1)
+    all_size = np.concatenate([g["agent_size"], g["npc_size"]], 1)
+    base = np.concatenate([g["present"], g["npc_present"]], 1)
+    np.testing.assert_allclose(observations.noisy_state(all_state, A, g["eps"]), g["noisy_state"], rtol=1e-6, atol=1e-6)
+    mask = observations.noisy_present_mask(all_state, all_size, base, A)
+    assert np.array_equal(mask, g["noisy_present"])
+    assert (base[:, None] & ~mask).sum() > 10                    # occlusion happens in the fixture
+    absolute = np.concatenate([g["noisy_state"][..., :3], g["noisy_size"], g["noisy_present"][..., None]], -1).astype(np.float32)
+    np.testing.assert_allclose(absolute, g["noisy_absolute"], rtol=1e-6, atol=1e-6)

@@ -15,6 +15,8 @@ from .infractions import (collision_allpairs, collision_detection_with_discs, io
                           offroad_infraction_loss)
 from .goals import WaypointGoal  # noqa: F401
 from .npc import NPCController, ReplayController, SpawnController  # noqa: F401
+from .observation_noise import (ObservationNoise, ObservationNoiseConfig, StandardSensingObservationNoise,  # noqa: F401
+                                StandardSensingObservationNoiseConfig)
 from .simulator import CollisionMetric, Simulator, TorchDriveConfig  # noqa: F401
 from .graph import GraphedHotPath  # noqa: F401
 from . import distributed, ops  # noqa: F401

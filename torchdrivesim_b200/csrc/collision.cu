@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128) tl_violation_kernel(const float* __restri
 // One thread per output row (b, i, k); with exclude_self row k of origin i is agent j = k + (k >= i), which is the
 // reference's boolean-mask removal of the diagonal without its host synchronisation.
 __global__ void __launch_bounds__(256) agents_relative_kernel(const float* __restrict__ absolute, int B, int A, int N,
-                                                              int exclude_self, float* __restrict__ out) {
+                                                              int exclude_self, int per_origin, float* __restrict__ out) {
     const int M = exclude_self ? N - 1 : N;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (int64_t)B * A * M) return;
@@ -204,8 +204,10 @@ __global__ void __launch_bounds__(256) agents_relative_kernel(const float* __res
     const int i = (int)(bi % A);
     const int64_t b = bi / A;
     const int j = exclude_self ? k + (k >= i) : k;
-    const float* o = absolute + (b * N + i) * 6;
-    const float* t = absolute + (b * N + j) * 6;
+    // per_origin: absolute is [B,A,N,6], what each origin agent perceives (simulator.py:784-821)
+    const float* base = per_origin ? absolute + (b * A + i) * (int64_t)N * 6 : absolute + b * (int64_t)N * 6;
+    const float* o = base + (int64_t)i * 6;
+    const float* t = base + (int64_t)j * 6;
     const float ang = -o[2];
     float s, c;
     tds::sincos_cr(ang, s, c);
@@ -218,6 +220,59 @@ __global__ void __launch_bounds__(256) agents_relative_kernel(const float* __res
     w[0] = make_float2(c * dx + (-s) * dy, s * dx + c * dy);
     w[1] = make_float2(r - pi, t[3]);
     w[2] = make_float2(t[4], t[5]);
+}
+
+// ---- noisy observations (StandardSensingObservationNoise, observation_noise.py:69-132).
+// get_noisy_state: what origin agent a perceives of agent e = its state + eps * deviation(distance), the deviation
+// growing in steps at 0.5, 25, 50 and 100 m.  The normal deviates eps are an input (torch.randn on the device).
+__global__ void __launch_bounds__(256) sensing_noise_kernel(const float4* __restrict__ all_state, const float4* __restrict__ eps,
+                                                            int64_t n, int A, int N, float4* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int e = (int)(g % N);
+    const int a = (int)((g / N) % A);
+    const int64_t b = g / ((int64_t)N * A);
+    const float4 ego = all_state[b * N + a], t = all_state[b * N + e], z = eps[g];
+    const float dx = ego.x - t.x, dy = ego.y - t.y;
+    const float dist = sqrtf(dx * dx + dy * dy);
+    const float dev = dist > 100.0f ? 3.83f : (dist > 50.0f ? 3.2f : (dist > 25.0f ? 1.6f : (dist > 0.5f ? 0.19f : 0.0f)));
+    out[g] = make_float4(t.x + z.x * dev, t.y + z.y * dev, t.z + z.z * dev, t.w + z.w * dev);
+}
+
+// get_noisy_present_mask: agent e is hidden from origin a if the segment a -> e crosses the circle (radius = half the
+// width) of any third agent o, o != e, o != a (utils.line_circle_intersection, utils.py:139-187; absent agents occlude
+// too, as in the reference).  One CTA per (environment, origin), the agents' circles staged in shared memory.
+__global__ void __launch_bounds__(128) sensing_occlusion_kernel(const float4* __restrict__ all_state, const float2* __restrict__ all_size,
+                                                                const uint8_t* __restrict__ base_mask, int A, int N,
+                                                                uint8_t* __restrict__ out) {
+    extern __shared__ float s_circ[];            // [N][3] x, y, radius
+    const int a = blockIdx.x;
+    const int64_t b = blockIdx.y;
+    for (int o = threadIdx.x; o < N; o += blockDim.x) {
+        const float4 st = all_state[b * N + o];
+        s_circ[3 * o] = st.x; s_circ[3 * o + 1] = st.y; s_circ[3 * o + 2] = all_size[b * N + o].y / 2.0f;
+    }
+    __syncthreads();
+    const float ex = s_circ[3 * a], ey = s_circ[3 * a + 1];
+    for (int e = threadIdx.x; e < N; e += blockDim.x) {
+        const float dx = s_circ[3 * e] - ex, dy = s_circ[3 * e + 1] - ey;
+        const float qa = dx * dx + dy * dy;
+        const float a_safe = fabsf(qa) < 1e-8f ? 1e-8f : qa;
+        bool hidden = false;
+        for (int o = 0; o < N && !hidden; o++) {
+            if (o == e || o == a) continue;
+            const float fx = ex - s_circ[3 * o], fy = ey - s_circ[3 * o + 1], r = s_circ[3 * o + 2];
+            const float qb = 2.0f * (fx * dx + fy * dy);
+            const float qc = (fx * fx + fy * fy) - r * r;
+            const float disc = qb * qb - (4.0f * qa) * qc;
+            if (disc >= 0.0f) {
+                const float sq = sqrtf(fmaxf(disc, 0.0f));
+                const float t1 = ((-qb) - sq) / (2.0f * a_safe), t2 = ((-qb) + sq) / (2.0f * a_safe);
+                hidden = fminf(t1, t2) <= 1.0f && fmaxf(t1, t2) >= 0.0f;
+            }
+        }
+        out[(b * A + a) * N + e] = (base_mask[b * N + e] != 0 && !hidden) ? 1 : 0;
+    }
 }
 
 // ---- IoU backward.  d(intersection area) is the boundary integral of the normal velocity: every edge of
@@ -577,15 +632,43 @@ extern "C" int tds_traffic_light_violation(const float* d_agent_box, const float
     return TDS_OK;
 }
 
+extern "C" int tds_sensing_noise(const float* d_all_state, const float* d_eps, int32_t B, int32_t A, int32_t N,
+                                 float* d_out, void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0 && N >= 0 && A <= N, "sensing_noise: need 0 <= A <= N");
+    const int64_t n = (int64_t)B * A * N;
+    if (n == 0) return TDS_OK;
+    TDS_REQUIRE(d_all_state && d_eps && d_out, "sensing_noise: null pointer");
+    sensing_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_all_state, (const float4*)d_eps,
+                                                                                    n, A, N, (float4*)d_out);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_sensing_occlusion(const float* d_all_state, const float* d_all_size, const uint8_t* d_base_mask,
+                                     int32_t B, int32_t A, int32_t N, uint8_t* d_out, void* stream) {
+    TDS_REQUIRE(B >= 0 && A >= 0 && N >= 0 && A <= N, "sensing_occlusion: need 0 <= A <= N");
+    if (B == 0 || A == 0 || N == 0) return TDS_OK;
+    TDS_REQUIRE(d_all_state && d_all_size && d_base_mask && d_out, "sensing_occlusion: null pointer");
+    TDS_REQUIRE(B <= 65535, "sensing_occlusion: B=%d exceeds 65535 (shard the batch)", B);
+    const size_t smem = (size_t)N * 3 * sizeof(float);
+    TDS_REQUIRE(smem <= 200 * 1024, "sensing_occlusion: N=%d does not fit shared memory", N);
+    if (smem > 48 * 1024)
+        TDS_CUDA_OK(cudaFuncSetAttribute(sensing_occlusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sensing_occlusion_kernel<<<dim3(A, B), 128, smem, (cudaStream_t)stream>>>((const float4*)d_all_state, (const float2*)d_all_size,
+                                                                             d_base_mask, A, N, d_out);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
 extern "C" int tds_agents_relative(const float* d_absolute, int32_t B, int32_t A, int32_t N, int32_t exclude_self,
-                                   float* d_out, void* stream) {
+                                   int32_t per_origin, float* d_out, void* stream) {
     TDS_REQUIRE(B >= 0 && A >= 0 && N >= 0 && A <= N, "agents_relative: need 0 <= A <= N");
     const int64_t M = exclude_self ? N - 1 : N;
     const int64_t n = (int64_t)B * A * M;
     if (n <= 0) return TDS_OK;
     TDS_REQUIRE(d_absolute && d_out, "agents_relative: null pointer");
     TDS_REQUIRE((n + 255) / 256 <= 2147483647LL, "agents_relative: too many pairs");
-    agents_relative_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_absolute, B, A, N, exclude_self, d_out);
+    agents_relative_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_absolute, B, A, N, exclude_self, per_origin, d_out);
     TDS_LAUNCH_OK();
     return TDS_OK;
 }

@@ -167,21 +167,58 @@ def traffic_light_violation(agent_box: torch.Tensor, tl_corners: torch.Tensor, t
 
 def agents_relative(absolute: torch.Tensor, n_agents: Optional[int] = None, exclude_self: bool = True) -> torch.Tensor:
     """absolute [B,N,6] (x, y, psi, length, width, present) -> [B,A,N(-1),6]: every agent in the frame of each of the
-    first `n_agents` agents (Simulator.get_all_agents_relative, simulator.py:748-781).  The self entry is removed on
-    the device without the reference's synchronising boolean-mask index.  Not differentiable."""
+    first `n_agents` agents (Simulator.get_all_agents_relative, simulator.py:748-781).  With absolute [B,A,N,6] (what
+    each agent perceives, get_noisy_all_agents_absolute) row i is relative to its own entry [b,i,i]
+    (get_noisy_all_agents_relative, simulator.py:784-821).  The self entry is removed on the device without the
+    reference's synchronising boolean-mask index.  Not differentiable."""
     lib = _lib.load()
     a = _lib.as_f32(absolute)
-    if a.dim() != 3 or a.shape[-1] != 6:
-        raise _lib.TdsError("agents_relative: absolute must be [B,N,6]")
-    B, N = a.shape[0], a.shape[1]
-    A = N if n_agents is None else int(n_agents)
+    per_origin = a.dim() == 4
+    if a.dim() not in (3, 4) or a.shape[-1] != 6:
+        raise _lib.TdsError("agents_relative: absolute must be [B,N,6] or [B,A,N,6]")
+    B, N = a.shape[0], a.shape[-2]
+    A = a.shape[1] if per_origin else (N if n_agents is None else int(n_agents))
     if not 0 <= A <= N:
         raise _lib.TdsError("agents_relative: n_agents must be in [0, N]")
     M = max(N - 1, 0) if exclude_self else N
     out = torch.empty(B, A, M, 6, dtype=torch.float32, device=a.device)
-    _lib.check(lib.tds_agents_relative(_lib.ptr(a), B, A, N, 1 if exclude_self else 0, _lib.ptr(out),
+    _lib.check(lib.tds_agents_relative(_lib.ptr(a), B, A, N, 1 if exclude_self else 0, 1 if per_origin else 0, _lib.ptr(out),
                                        _lib.stream_ptr(a.device)))
     return out
+
+
+def sensing_noise(all_state: torch.Tensor, n_agents: int, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """all_state [B,N,4] -> [B,A,N,4]: the states the first `n_agents` agents perceive, with noise growing with the
+    distance (StandardSensingObservationNoise.get_noisy_state, observation_noise.py:74-89).  `eps` [B,A,N,4] are the
+    standard normal deviates (drawn on the device when omitted)."""
+    lib = _lib.load()
+    s = _lib.as_f32(all_state)
+    if s.dim() != 3 or s.shape[-1] != 4:
+        raise _lib.TdsError("sensing_noise: all_state must be [B,N,4]")
+    B, N = s.shape[0], s.shape[1]
+    A = int(n_agents)
+    if eps is None:
+        eps = torch.randn(B, A, N, 4, dtype=torch.float32, device=s.device)
+    eps = _lib.as_f32(eps)
+    if tuple(eps.shape) != (B, A, N, 4):
+        raise _lib.TdsError("sensing_noise: eps must be [B,A,N,4]")
+    out = torch.empty(B, A, N, 4, dtype=torch.float32, device=s.device)
+    _lib.check(lib.tds_sensing_noise(_lib.ptr(s), _lib.ptr(eps), B, A, N, _lib.ptr(out), _lib.stream_ptr(s.device)))
+    return out
+
+
+def sensing_occlusion(all_state: torch.Tensor, all_size: torch.Tensor, base_mask: torch.Tensor, n_agents: int) -> torch.Tensor:
+    """all_state [B,N,4], all_size [B,N,2], base_mask [B,N] -> bool [B,A,N]: present and in the line of sight of each of
+    the first `n_agents` agents (StandardSensingObservationNoise.get_noisy_present_mask, observation_noise.py:91-132)."""
+    lib = _lib.load()
+    s, z, m = _lib.as_f32(all_state), _lib.as_f32(all_size), _lib.as_u8(base_mask)
+    B, N = s.shape[0], s.shape[1]
+    if s.dim() != 3 or s.shape[-1] != 4 or tuple(z.shape) != (B, N, 2) or tuple(m.shape) != (B, N):
+        raise _lib.TdsError("sensing_occlusion: expected all_state [B,N,4], all_size [B,N,2], base_mask [B,N]")
+    A = int(n_agents)
+    out = torch.empty(B, A, N, dtype=torch.uint8, device=s.device)
+    _lib.check(lib.tds_sensing_occlusion(_lib.ptr(s), _lib.ptr(z), _lib.ptr(m), B, A, N, _lib.ptr(out), _lib.stream_ptr(s.device)))
+    return out.view(torch.bool)
 
 
 # ------------------------------------------------------------------------------------ offroad

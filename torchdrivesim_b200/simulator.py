@@ -26,6 +26,7 @@ from .maps import MapSet, StaticMap
 from .mesh import B200BirdviewMeshGenerator
 from .goals import WaypointGoal
 from .npc import NPCController
+from .observation_noise import ObservationNoise
 from .rendering import B200RendererConfig, BirdviewRenderer, RendererConfig, Resolution, renderer_from_config
 
 
@@ -52,7 +53,7 @@ class Simulator:
                  birdview_mesh_generator: Optional[B200BirdviewMeshGenerator] = None, internal_time: int = 0,
                  traffic_controls: Optional[Dict[str, object]] = None, agent_types: Optional[Tensor] = None,
                  agent_type_names: Optional[List[str]] = None, npc_controller: Optional[NPCController] = None,
-                 waypoint_goals: Optional[WaypointGoal] = None):
+                 waypoint_goals: Optional[WaypointGoal] = None, observation_noise_model: Optional[ObservationNoise] = None):
         self.road_mesh = road_mesh if isinstance(road_mesh, MapSet) else MapSet([road_mesh])
         self.kinematic_model = kinematic_model
         self.agent_size = agent_size
@@ -74,6 +75,7 @@ class Simulator:
                                            agent_type_names=self._agent_types)
         self.npc_controller = npc_controller
         self.waypoint_goals = waypoint_goals
+        self.observation_noise_model = observation_noise_model or ObservationNoise()     # simulator.py:378-381
         if state.dim() != 3 or agent_size.shape[:2] != state.shape[:2] or initial_present_mask.shape != state.shape[:2]:
             raise _lib.TdsError("expected state [B,A,4], agent_size [B,A,2] and present mask [B,A]")
         if renderer is None:
@@ -330,6 +332,25 @@ class Simulator:
         """BxAx(A+Npc-1 or A+Npc)x6: the pose of every agent and NPC in the frame of every controlled agent
         (simulator.py:748-781), one launch and no host synchronisation."""
         return ops.agents_relative(self.get_all_agents_absolute(), self.agent_count, exclude_self)
+
+    # ---- noisy observations (simulator.py:663-679, 740-746, 784-821): what every agent perceives of all agents
+    def get_noisy_state(self) -> Tensor:
+        return self.observation_noise_model.get_noisy_state(self)
+
+    def get_noisy_agent_size(self) -> Tensor:
+        return self.observation_noise_model.get_noisy_agent_size(self)
+
+    def get_noisy_present_mask(self) -> Tensor:
+        return self.observation_noise_model.get_noisy_present_mask(self)
+
+    def get_noisy_all_agents_absolute(self) -> Tensor:
+        """BxAx(A+Npc)x6: x, y, psi, length, width, present as perceived by each agent."""
+        return torch.cat([self.get_noisy_state()[..., :3], self.get_noisy_agent_size()[..., :2],
+                          self.get_noisy_present_mask()[..., None].to(torch.float32)], dim=-1)
+
+    def get_noisy_all_agents_relative(self, exclude_self: bool = True) -> Tensor:
+        """BxAx(A+Npc-1 or A+Npc)x6: the perceived agents in the frame of the perceiving agent's own perceived pose."""
+        return ops.agents_relative(self.get_noisy_all_agents_absolute(), exclude_self=exclude_self)
 
     def compute_offroad(self) -> Tensor:
         """simulator.py:1035-1044: offroad_infraction_loss(...) * present mask."""
