@@ -1,3 +1,4 @@
+# the end-of-round measurement run: GPU tests, bench (both arms), ncu launch list, collision / kinematic pipe metrics
 set -x
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err
