@@ -18,6 +18,7 @@
 //     through a colour LUT to 3 float planes with coalesced streaming 128-bit stores.
 // HBM traffic per camera: 12 * res^2 bytes of image out (49 KB at 64x64); the map records are L2 hits.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tds_map.cuh"
 #include "tds_raster_tri.h"
@@ -352,7 +353,8 @@ constexpr int kQueues = 3;                          // short inside, tall inside
 constexpr int kGroupExtra = kRows * 8 + 16 + 48;    // row tables, counters, view-quad edge functions
 
 __host__ __device__ constexpr int raster_group_bytes(int res, int n_planes, int G) {
-    return n_planes * res * ((res + 31) / 32) * 4 + kQueues * 2 * G * 16 + kGroupExtra;
+    // planes of the camera | three queues of 64 faces for every warp of the group | tables
+    return n_planes * res * ((res + 31) / 32) * 4 + (G / 32) * kQueues * 64 * 16 + kGroupExtra;
 }
 // The 64x64 / <= 7 classes variant (the benchmark configuration) reserves 7 planes per camera in STATIC shared
 // memory: every address is then a compile-time offset and nothing has to be re-derived from the dynamic base.
@@ -360,7 +362,9 @@ constexpr int kStaticPlanes = 7;
 __host__ __device__ constexpr bool raster_static_smem(int G, int RES, int NS) { return G == 32 && RES == 64 && NS == 3; }
 
 // G = threads cooperating on one camera: 32 (one warp per camera, 4 cameras in flight per CTA, no block barriers)
-// for tiles up to 64x64, or the whole CTA for larger tiles.
+// for tiles up to 64x64, or the whole CTA for larger tiles.  The warps of a CTA group share the camera's bitplanes
+// (atomic ORs) but nothing else: each takes every (G/32)-th batch of 32 candidates and keeps its own three queues,
+// so the only block barriers of a camera are after the set-up and before the resolve.
 template <int G>
 __device__ __forceinline__ void group_sync() {
     if (G == 32) __syncwarp();
@@ -371,15 +375,15 @@ __device__ __forceinline__ void group_sync() {
 #define TDS_RASTER_MINB 7
 #endif
 // NS = bits of the per-pixel draw rank (0 = background): 3 for up to 7 active classes, 5 for up to 31
-template <int G, int RES, int NS>
+template <int G, int RES, int NS, bool SMALL>
 #ifndef TDS_RASTER_MINB_BIG
 #define TDS_RASTER_MINB_BIG 2
 #endif
-__global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB : (G == 256 ? 2 * TDS_RASTER_MINB_BIG : TDS_RASTER_MINB_BIG)) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
+__global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB : (G == 256 ? 2 * TDS_RASTER_MINB_BIG : TDS_RASTER_MINB_BIG)) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int GROUPS = G == 32 ? 4 : 1;
-    constexpr int QN = 2 * G;
-    constexpr bool SMALL = G <= 256;            // images up to 128 pixels: slopes through the reciprocal table
+    constexpr int QN = 64;                      // queue capacity per warp and kind
+    // SMALL: images up to 128 pixels, slopes through the reciprocal table
     constexpr bool POW2 = RES == 64;
     const int res = RES ? RES : a.res;          // RES = 64 is compiled with constant strides
     const int W32 = RES ? RES / 32 : (res + 31) >> 5;
@@ -419,10 +423,12 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
     const uint32_t planes_sa = smem_addr(base);                            // [KS][W32][res] words
     const uint32_t rcp_sa = planes_sa - (uint32_t)(rcp_bytes + group * group_bytes);
     const uint32_t plane_bytes = 4u * (uint32_t)plane_words;
-    const uint32_t queue_sa = planes_sa + (uint32_t)KS * plane_bytes;      // [kQueues][QN] x 16 B
-    const uint32_t start_sa = queue_sa + kQueues * QN * 16;                // [kRows] first record of a grid row
+    constexpr int WARPS = G / 32;
+    const uint32_t queues_sa = planes_sa + (uint32_t)KS * plane_bytes;     // [WARPS][kQueues][QN] x 16 B
+    const uint32_t queue_sa = queues_sa + (G == 32 ? 0u : (uint32_t)(threadIdx.x >> 5) * (kQueues * QN * 16));   // this warp's
+    const uint32_t start_sa = queues_sa + WARPS * kQueues * QN * 16;       // [kRows] first record of a grid row
     const uint32_t count_sa = start_sa + kRows * 4;                        // [kRows] records of a grid row
-    int* s_cnt = reinterpret_cast<int*>(base + KS * plane_words * 4 + kQueues * QN * 16 + kRows * 8);   // queue fill levels (G > 32)
+    int* s_cnt = reinterpret_cast<int*>(base + KS * plane_words * 4 + WARPS * kQueues * QN * 16 + kRows * 8);   // [3] = next camera (G > 32)
     float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
 
     // persistent grid: every group (warp or CTA) pulls the next camera from a global counter, so uneven cameras
@@ -449,7 +455,6 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
         make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy, s_edges, tid == 0);
         {
             for (int i = tid; i < K * plane_words / 4; i += G) ssts4(planes_sa + 16u * (uint32_t)i, make_uint4(0u, 0u, 0u, 0u));
-            if (tid < 4) s_cnt[tid] = 0;
         }
 
         // ---- grid rows touched by the view quad (world coordinates), with a 5 cm safety margin
@@ -491,12 +496,12 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
 
         // ---- ONE pass over the candidates: segment r < nrows = the record range of grid row r, segment nrows =
         // the dynamic primitives of the environment.  Stage 1 (cull + project + truncate) plots the faces that are
-        // just their vertices and queues the others by kind; whenever G faces of a kind are queued, stage 2 turns
+        // just their vertices and queues the others by kind; whenever a warp has queued 32 faces of a kind, stage 2 turns
         // them into row intervals, one face per thread, so stage 2 always runs with full warps.  The last
         // iteration (seg > nrows) only drains the queues.
         int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? (int)slds(count_sa) : T + a.Tc;
         if (nrows > 0) seg_start = (int)slds(start_sa);
-        int nq0 = 0, nq1 = 0, nq2 = 0;                 // queue fill levels (uniform over the group)
+        int nq0 = 0, nq1 = 0, nq2 = 0;                 // fill levels of this warp's queues (uniform over the warp)
         while (true) {
             while (j0 >= seg_count && seg <= nrows) {
                 seg++;
@@ -508,7 +513,9 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
             if (!drain) {
                 // uniform control flow: every lane fetches a valid record (the last one of the segment past its end)
                 const int j = j0 + tid;
+                const bool warp_has_work = j0 + (tid & ~31) < seg_count;
                 j0 += G;
+                if (G != 32 && !warp_has_work) continue;      // this warp's slice of the batch is past the segment's end
                 const bool valid = j < seg_count;
                 const int jj = valid ? j : seg_count - 1;
                 float x0, y0, x1, y1, x2, y2;
@@ -566,19 +573,8 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                 const unsigned m0 = __ballot_sync(0xffffffffu, kind == kShort), m1 = __ballot_sync(0xffffffffu, kind == kTall),
                                m2 = __ballot_sync(0xffffffffu, kind == kClipped);
                 if (m0 | m1 | m2) {
-                    int b0 = nq0, b1 = nq1, b2 = nq2;
-                    if (G != 32) {
-                        if (lane == 0) {
-                            if (m0) b0 = atomicAdd(&s_cnt[0], __popc(m0));
-                            if (m1) b1 = atomicAdd(&s_cnt[1], __popc(m1));
-                            if (m2) b2 = atomicAdd(&s_cnt[2], __popc(m2));
-                        }
-                        b0 = __shfl_sync(0xffffffffu, b0, 0);
-                        b1 = __shfl_sync(0xffffffffu, b1, 0);
-                        b2 = __shfl_sync(0xffffffffu, b2, 0);
-                    } else {
-                        nq0 += __popc(m0); nq1 += __popc(m1); nq2 += __popc(m2);
-                    }
+                    const int b0 = nq0, b1 = nq1, b2 = nq2;
+                    nq0 += __popc(m0); nq1 += __popc(m1); nq2 += __popc(m2);
                     if (kind >= kShort) {
                         const unsigned mine = kind == kShort ? m0 : (kind == kTall ? m1 : m2);
                         const int qb = kind == kShort ? b0 : (kind == kTall ? QN + b1 : 2 * QN + b2);
@@ -589,44 +585,35 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G == 32 ? TDS_RASTER_MINB :
                                          (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane));
                     }
                 }
-                group_sync<G>();
-                if (G != 32) { nq0 = s_cnt[0]; nq1 = s_cnt[1]; nq2 = s_cnt[2]; }
+                __syncwarp();
             }
-            if (!(drain | (nq0 >= G) | (nq1 >= G) | (nq2 >= G))) continue;
+            if (!(drain | (nq0 >= 32) | (nq1 >= 32) | (nq2 >= 32))) continue;
             // stage 2: a queue is drawn when it holds a full group (or, at the end, whatever is left)
 #pragma unroll 1
             for (int which = 0; which < 2; which++) {
                 const int nq = which ? nq1 : nq0;
-                if (nq >= G || (drain && nq > 0)) {
-                    const int take = min(nq, G);
-                    if (tid < take) {
-                        const uint4 q = slds4(queue_sa + 16u * (uint32_t)(which * QN + nq - take + tid));
+                if (nq >= 32 || (drain && nq > 0)) {
+                    const int take = min(nq, 32);
+                    if (lane < take) {
+                        const uint4 q = slds4(queue_sa + 16u * (uint32_t)(which * QN + nq - take + lane));
                         draw_inside<RES, SMALL>(planes_sa + q.w * plane_bytes, res, rcp_sa,
                                                 (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
                                                 (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
                     }
                     if (which) nq1 -= take; else nq0 -= take;
-                    group_sync<G>();
-                    if (G != 32) {
-                        if (tid == 0) s_cnt[which] = nq - take;
-                        group_sync<G>();
-                    }
+                    __syncwarp();
                 }
             }
-            if (nq2 >= G || (drain && nq2 > 0)) {
-                const int take = min(nq2, G);
-                if (tid < take) {
-                    const uint4 q = slds4(queue_sa + 16u * (uint32_t)(2 * QN + nq2 - take + tid));
+            if (nq2 >= 32 || (drain && nq2 > 0)) {
+                const int take = min(nq2, 32);
+                if (lane < take) {
+                    const uint4 q = slds4(queue_sa + 16u * (uint32_t)(2 * QN + nq2 - take + lane));
                     draw_clipped<RES>(planes_sa + q.w * plane_bytes, res, rcp_sa,
                                       (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
                                       (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
                 }
                 nq2 -= take;
-                group_sync<G>();
-                if (G != 32) {
-                    if (tid == 0) s_cnt[2] = nq2;
-                    group_sync<G>();
-                }
+                __syncwarp();
             }
             if (drain) {
                 if ((nq0 | nq1 | nq2) == 0) break;     // a queue held more than one group: drain again
@@ -793,18 +780,40 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
         TDS_LAUNCH_OK();
         return TDS_OK;
     };
-    // warp per camera (4 cameras in flight per CTA) while two such CTAs fit an SM - measured faster than a CTA per
-    // camera up to 128x128 (96x96: +21 %, 128x128: +3 %) -, a 256/512-thread CTA per camera above
-    const size_t warp_smem = ((((size_t)res + 1) * 4 + 15) & ~(size_t)15) + (size_t)raster_group_bytes(res, K, 32) * 4;
-    const bool warp_kernel = res <= 64 || (res <= 128 && warp_smem <= 113 * 1024);
-    if (K <= 7) {
-        if (res == 64) return launch(raster_kernel<32, 64, 3>, 4, 128, raster_static_smem(32, 64, 3));
-        if (warp_kernel) return launch(raster_kernel<32, 0, 3>, 4, 128, raster_static_smem(32, 0, 3));
-        if (res <= 128) return launch(raster_kernel<256, 0, 3>, 1, 256, raster_static_smem(256, 0, 3));
-        return launch(raster_kernel<512, 0, 3>, 1, 512, raster_static_smem(512, 0, 3));
+    // Threads per camera.  Tiles up to 96x96: a warp per camera, 4 cameras in flight per CTA (at 128x128 only 16 such
+    // warps fit an SM: 4 sets of bitplanes per CTA).  Above: a CTA of 4, 8 or 16 independent warps per camera - the
+    // fewest warps that still leave 16 warps resident on an SM, because a warp that sees a smaller share of the
+    // camera's faces fills its queues of 32 less often (256x256: 2.34 / 2.56 / 3.02 ms with 4 / 8 / 16 warps).
+    // TDS_RASTER_G = 32 / 128 / 256 / 512 forces a variant (profiling aid).
+    const size_t rcp_smem = (((size_t)res + 1) * 4 + 15) & ~(size_t)15;
+    const size_t warp_smem = rcp_smem + (size_t)raster_group_bytes(res, K, 32) * 4;
+    int G = 32;
+    if (res > 96 || warp_smem > 227 * 1024) {
+        int best_warps = -1;
+        const int cand[3] = {128, 256, 512}, reg_cap[3] = {TDS_RASTER_MINB, 2 * TDS_RASTER_MINB_BIG, TDS_RASTER_MINB_BIG};
+        for (int i = 0; i < 3; i++) {
+            const size_t smem_g = rcp_smem + (size_t)raster_group_bytes(res, K, cand[i]) + 1024;
+            const int warps = std::min<int>(reg_cap[i], (int)(233472 / smem_g)) * (cand[i] / 32);
+            if (warps > best_warps) { best_warps = warps; G = cand[i]; }
+            if (warps >= 16) break;
+        }
     }
-    if (res == 64) return launch(raster_kernel<32, 64, 5>, 4, 128, raster_static_smem(32, 64, 5));
-    if (warp_kernel) return launch(raster_kernel<32, 0, 5>, 4, 128, raster_static_smem(32, 0, 5));
-    if (res <= 128) return launch(raster_kernel<256, 0, 5>, 1, 256, raster_static_smem(256, 0, 5));
-    return launch(raster_kernel<512, 0, 5>, 1, 512, raster_static_smem(512, 0, 5));
+    if (const char* e = getenv("TDS_RASTER_G")) {
+        const int g = atoi(e);
+        if (g == 32 || g == 128 || g == 256 || g == 512) G = g;
+    }
+    if (G == 32 && (warp_smem > 227 * 1024 || res > 128)) G = 128;
+    const bool small = res <= 128;
+    if (K <= 7) {
+        if (G == 32 && res == 64) return launch(raster_kernel<32, 64, 3, true>, 4, 128, raster_static_smem(32, 64, 3));
+        if (G == 32) return launch(raster_kernel<32, 0, 3, true>, 4, 128, false);
+        if (G == 128) return small ? launch(raster_kernel<128, 0, 3, true>, 1, 128, false) : launch(raster_kernel<128, 0, 3, false>, 1, 128, false);
+        if (G == 256) return small ? launch(raster_kernel<256, 0, 3, true>, 1, 256, false) : launch(raster_kernel<256, 0, 3, false>, 1, 256, false);
+        return launch(raster_kernel<512, 0, 3, false>, 1, 512, false);
+    }
+    if (G == 32 && res == 64) return launch(raster_kernel<32, 64, 5, true>, 4, 128, raster_static_smem(32, 64, 5));
+    if (G == 32) return launch(raster_kernel<32, 0, 5, true>, 4, 128, false);
+    if (G == 128) return small ? launch(raster_kernel<128, 0, 5, true>, 1, 128, false) : launch(raster_kernel<128, 0, 5, false>, 1, 128, false);
+    if (G == 256) return small ? launch(raster_kernel<256, 0, 5, true>, 1, 256, false) : launch(raster_kernel<256, 0, 5, false>, 1, 256, false);
+    return launch(raster_kernel<512, 0, 5, false>, 1, 512, false);
 }
