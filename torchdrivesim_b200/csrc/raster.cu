@@ -340,6 +340,7 @@ struct RasterArgs {
     const uint8_t* ws;
     float* out;
     int32_t B, Nc, N, T, present_per_camera, res;
+    int32_t LR;                // traffic lights + extra rectangles of an environment (T = 3 N + 2 LR)
     int32_t ncam;
     float scale;
     int32_t* next_cam;         // work counter of the persistent grid (zeroed before the launch)
@@ -350,7 +351,8 @@ struct RasterArgs {
 
 constexpr int kRows = tds::kMaxRasterRows;
 constexpr int kQueues = 3;                          // short inside, tall inside, clipped
-constexpr int kGroupExtra = kRows * 8 + 16 + 48;    // row tables, counters, view-quad edge functions
+constexpr int kCullCap = 128;                       // dynamic primitives in view that a camera can list
+constexpr int kGroupExtra = kRows * 8 + 16 + 48 + kCullCap * 2;    // row tables, counters, view-quad edge functions, that list
 
 __host__ __device__ constexpr int raster_group_bytes(int res, int n_planes, int G) {
     // planes of the camera | three queues of 64 faces for every warp of the group | tables
@@ -430,6 +432,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
     const uint32_t count_sa = start_sa + kRows * 4;                        // [kRows] records of a grid row
     int* s_cnt = reinterpret_cast<int*>(base + KS * plane_words * 4 + WARPS * kQueues * QN * 16 + kRows * 8);   // [3] = next camera (G > 32)
     float* s_edges = reinterpret_cast<float*>(s_cnt + 4);                   // [12]
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_edges + 12);          // [kCullCap] dynamic primitives in view
 
     // persistent grid: every group (warp or CTA) pulls the next camera from a global counter, so uneven cameras
     // (a junction full of lane markings next to an empty field) do not leave SMs idle at the end
@@ -455,6 +458,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res, qx, qy, s_edges, tid == 0);
         {
             for (int i = tid; i < K * plane_words / 4; i += G) ssts4(planes_sa + 16u * (uint32_t)i, make_uint4(0u, 0u, 0u, 0u));
+            if (G != 32 && tid < 3) s_cnt[tid] = 0;
         }
 
         // ---- grid rows touched by the view quad (world coordinates), with a 5 cm safety margin
@@ -494,19 +498,69 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         const uint8_t* pres = a.present ? (a.present_per_camera ? a.present + (int64_t)camid * a.N : a.present + (int64_t)b * a.N)
                                         : nullptr;
 
+        // ---- dynamic primitives in view.  An agent (rectangle + direction triangle, 3 faces) or a traffic light /
+        // sign (2 faces) lies within the circle around its rectangle's diagonal (the corners 1 and 3 of its first
+        // face); if that circle misses the quad none of its vertices is inside and all its faces are culled, so
+        // only the primitives that pass are listed (in any order: the bitplanes do not depend on it).  Absent
+        // agents are not listed: they all draw the SAME degenerate face (mesh.py:1083-1089), added once below.
+        const int items = a.N + a.LR;
+        int n_view = 0;
+        bool any_absent = false;
+        for (int i0 = 0; i0 < items; i0 += G) {
+            const int i = i0 + tid;
+            bool keep = false;
+            if (i < items) {
+                const bool agent = i < a.N;
+                if (agent && pres && !pres[i]) {
+                    any_absent = true;
+                } else {
+                    const float* p = dtri + (int64_t)(agent ? 3 * i : 3 * a.N + 2 * (i - a.N)) * 6;
+                    const float mx = 0.5f * (p[2] + p[4]), my = 0.5f * (p[3] + p[5]);
+                    const float hx = p[2] - mx, hy = p[3] - my;
+                    float u, v;
+                    project_f<POW2>(cam, mx + cam.ncx, my + cam.ncy, u, v);
+                    const float dd = fmaxf(fabsf(u - cam.half), fabsf(v - cam.half));
+                    keep = !(dd > (cam.r_out + 0.05f) + sqrtf(hx * hx + hy * hy) * (a.scale * cam.half) * 1.0001f);   // NaN: kept
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            int base = n_view;
+            if (G == 32) {
+                n_view += __popc(m);
+            } else {
+                if (lane == 0 && m) base = atomicAdd(&s_cnt[0], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (keep && pos < kCullCap) s_list[pos] = (uint16_t)i;
+        }
+        any_absent = __any_sync(0xffffffffu, any_absent);
+        if (G != 32) {
+            if (any_absent && lane == 0) s_cnt[1] = 1;
+            __syncthreads();
+            n_view = s_cnt[0];
+            any_absent = s_cnt[1] != 0;
+        } else {
+            __syncwarp();
+        }
+        // more primitives in view than the list holds (or more than 65535 of them): take them all, in order
+        const bool listed = n_view <= kCullCap && items <= 65535;
+        const int n_dyn = 3 * (listed ? n_view : items);
+        const int dyn_count = n_dyn + a.Tc + (any_absent ? 1 : 0);
+
         // ---- ONE pass over the candidates: segment r < nrows = the record range of grid row r, segment nrows =
         // the dynamic primitives of the environment.  Stage 1 (cull + project + truncate) plots the faces that are
         // just their vertices and queues the others by kind; whenever a warp has queued 32 faces of a kind, stage 2 turns
         // them into row intervals, one face per thread, so stage 2 always runs with full warps.  The last
         // iteration (seg > nrows) only drains the queues.
-        int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? (int)slds(count_sa) : T + a.Tc;
+        int seg = 0, j0 = 0, seg_start = 0, seg_count = nrows > 0 ? (int)slds(count_sa) : dyn_count;
         if (nrows > 0) seg_start = (int)slds(start_sa);
         int nq0 = 0, nq1 = 0, nq2 = 0;                 // fill levels of this warp's queues (uniform over the warp)
         while (true) {
             while (j0 >= seg_count && seg <= nrows) {
                 seg++;
                 j0 = 0;
-                seg_count = seg < nrows ? (int)slds(count_sa + 4u * seg) : (seg == nrows ? T + a.Tc : 0);
+                seg_count = seg < nrows ? (int)slds(count_sa + 4u * seg) : (seg == nrows ? dyn_count : 0);
                 seg_start = seg < nrows ? (int)slds(start_sa + 4u * seg) : 0;
             }
             const bool drain = seg > nrows;
@@ -528,25 +582,26 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                     const int meta = __float_as_int(v2o.z);
                     own = meta & 7;
                     cls = meta >> 8;
-                } else if (jj >= T) {
+                } else if (jj >= n_dyn && jj < n_dyn + a.Tc) {
                     // triangles of this camera only (goal-waypoint discs, mesh.py:1120-1145)
-                    const int64_t ct = (int64_t)camid * a.Tc + (jj - T);
+                    const int64_t ct = (int64_t)camid * a.Tc + (jj - n_dyn);
                     const int c = a.cam_cls[ct];
                     cls = c < 0 ? 255 : c;
                     const float* p = a.cam_tris + ct * 6;
                     x0 = p[0]; y0 = p[1]; x1 = p[2]; y1 = p[3]; x2 = p[4]; y2 = p[5];
                 } else {
-                    // dynamic primitives (agents, direction triangles, traffic lights, signs)
-                    int t = jj;
-                    bool degenerate = false;
-                    if (t < 3 * a.N && pres && !pres[t / 3]) {
-                        // absent agent: faces * 0 -> degenerate triangle at actor vertex 0 with agent 0's class
-                        // (mesh.py:1083-1089)
-                        t = 0;
-                        degenerate = true;
-                    }
-                    cls = dcls[t];
-                    const float* p = dtri + (int64_t)t * 6;
+                    // dynamic primitives in view: slot 3 k + f = face f of the k-th listed agent / light / sign; the
+                    // last slot is the degenerate face of the absent agents: actor vertex 0 with agent 0's class
+                    const bool degenerate = jj >= n_dyn;
+                    const int k = jj / 3, f = jj - 3 * k;
+                    const int item = degenerate ? 0 : (listed ? (int)s_list[k] : k);
+                    const bool agent = item < a.N;
+                    const int t = degenerate ? 0 : (agent ? 3 * item + f : 3 * a.N + 2 * (item - a.N) + f);
+                    // a sign has two faces; without the list an absent agent shows up here as well
+                    const bool skip = !degenerate && ((!agent && f == 2) || (!listed && agent && pres && !pres[item]));
+                    const int ts = skip ? 0 : t;
+                    cls = skip ? 255 : dcls[ts];
+                    const float* p = dtri + (int64_t)ts * 6;
                     x0 = p[0]; y0 = p[1];
                     x1 = degenerate ? x0 : p[2]; y1 = degenerate ? y0 : p[3];
                     x2 = degenerate ? x0 : p[4]; y2 = degenerate ? y0 : p[5];
@@ -753,7 +808,7 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     RasterArgs a;
     a.env_map = d_env_map; a.cam_xy = d_cam_xy; a.cam_sc = d_cam_sc; a.present = d_present;
     a.ws = (const uint8_t*)d_workspace; a.out = d_out;
-    a.B = B; a.Nc = Nc; a.N = N; a.T = T; a.present_per_camera = present_per_camera; a.res = res; a.scale = scale;
+    a.B = B; a.Nc = Nc; a.N = N; a.LR = L + R; a.T = T; a.present_per_camera = present_per_camera; a.res = res; a.scale = scale;
     const int64_t ncam = (int64_t)B * Nc;
     TDS_REQUIRE(ncam <= 2147483647LL, "raster: too many cameras");
     a.ncam = (int32_t)ncam;
