@@ -7,6 +7,7 @@
 // reference's, operation for operation (fp32, no FMA), so the minimum over the visited faces is
 // the reference's minimum over all faces.  The grid (~1 MB per map) is L2 resident; HBM traffic is
 // the 28 B per agent of state/size in and 4 B out.
+#include <algorithm>
 #include <math_constants.h>
 
 #include "tds_map.cuh"
@@ -71,63 +72,67 @@ __device__ __forceinline__ bool cannot_improve(float lower_bound2, float best) {
     return lower_bound2 > best * 1.00001f + 1e-9f;
 }
 
-// all faces of one grid cell, one lane
-__device__ __forceinline__ void visit_cell(const MapDev& m, int cx, int cy, float px, float py, float stop, float& best, int& bf) {
-    // cell bounds (faces are binned with 1 mm of slack, see map.cu)
-    const float x0 = m.ox0 + (float)cx * m.ocs, y0 = m.oy0 + (float)cy * m.ocs;
-    if (cannot_improve(box_dist2(px, py, x0 - 2e-3f, y0 - 2e-3f, x0 + m.ocs + 2e-3f, y0 + m.ocs + 2e-3f), best)) return;
-    const int c = cy * m.ogx + cx;
-    const int e0 = __ldg(m.ocell + c), e1 = __ldg(m.ocell + c + 1);
-    if (e0 >= e1) return;
-    const float4* rec = m.orec + 2 * (int64_t)e0;
-    float4 a = __ldg(rec), b = __ldg(rec + 1);
-    for (int e = e0; e < e1; e++) {
-        // prefetch the next entry while this one is evaluated
-        float4 na = a, nb = b;
-        if (e + 1 < e1) { na = __ldg(rec + 2); nb = __ldg(rec + 3); }
-        rec += 2;
-        const float bx0 = fminf(fminf(a.x, a.z), b.x), bx1 = fmaxf(fmaxf(a.x, a.z), b.x);
-        const float by0 = fminf(fminf(a.y, a.w), b.y), by1 = fmaxf(fmaxf(a.y, a.w), b.y);
-        if (!cannot_improve(box_dist2(px, py, bx0, by0, bx1, by1), best)) {
-            const float d = point_tri_dist2(px, py, a.x, a.y, a.z, a.w, b.x, b.y);
-            const int f = __float_as_int(b.z);
-            if (d < best || (d == best && f < bf)) { best = d; bf = f; }
-            if (best <= stop) return;       // inside a face (or within the threshold): the result is 0
+// ---- nearest face of ONE point by ONE warp.  The faces of the visited cells are spread over the 32 lanes (cells are
+// pruned by their box first, then a prefix sum of the cells' face counts maps a flat face index back to its cell), the
+// lanes share their minimum after every round of 32 faces, so the bounding-box pruning of the next round uses it.
+__device__ __forceinline__ void warp_min(float& best, int& bf) {
+    // squared distances are >= 0 (or +inf) and never NaN here, so they order like their bit patterns: two warp
+    // reductions (redux.sync) give the minimum and the lowest face index that attains it (-1 = none, the largest)
+    const unsigned mn = __reduce_min_sync(0xffffffffu, __float_as_uint(best));
+    const unsigned f = __reduce_min_sync(0xffffffffu, __float_as_uint(best) == mn ? (unsigned)bf : 0xffffffffu);
+    best = __uint_as_float(mn);
+    bf = (int)f;
+}
+
+// lane l proposes cell (cx, cy) (valid or not); all their faces are evaluated, 32 per round.  SINGLE: every lane
+// proposes the same cell (the point's own), so a flat face index is an offset into that cell.
+template <bool SINGLE>
+__device__ __forceinline__ void visit_cells(const MapDev& m, bool valid, int cx, int cy, float px, float py, float stop,
+                                            float& best, int& bf, int lane) {
+    int e0 = 0, cnt = 0;
+    if (valid) {
+        // cell bounds (faces are binned with 1 mm of slack, see map.cu)
+        const float x0 = m.ox0 + (float)cx * m.ocs, y0 = m.oy0 + (float)cy * m.ocs;
+        if (!cannot_improve(box_dist2(px, py, x0 - 2e-3f, y0 - 2e-3f, x0 + m.ocs + 2e-3f, y0 + m.ocs + 2e-3f), best)) {
+            const int c = cy * m.ogx + cx;
+            e0 = __ldg(m.ocell + c);
+            cnt = __ldg(m.ocell + c + 1) - e0;
         }
-        a = na; b = nb;
     }
-}
-
-constexpr int kGroup = 8;       // lanes that search for one point
-
-__device__ __forceinline__ void group_min(unsigned group_mask, float& best, int& bf) {
+    int incl = cnt;
+    if (!SINGLE) {
 #pragma unroll
-    for (int o = 1; o < kGroup; o <<= 1) {
-        const float ob = __shfl_xor_sync(group_mask, best, o);
-        const int of = __shfl_xor_sync(group_mask, bf, o);
-        if (ob < best || (ob == best && of >= 0 && (bf < 0 || of < bf))) { best = ob; bf = of; }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
     }
-}
-
-// the point's own cell: the group evaluates kGroup faces at a time (largest first: a containing face is found in the
-// first round) and shares the minimum after every round, so a hit ends the search for all lanes
-__device__ __forceinline__ void visit_own_cell(const MapDev& m, int cx, int cy, float px, float py, float stop, float& best,
-                                               int& bf, int sub, unsigned group_mask) {
-    const int c = cy * m.ogx + cx;
-    const int e0 = __ldg(m.ocell + c), e1 = __ldg(m.ocell + c + 1);
-    for (int e = e0; e < e1; e += kGroup) {          // uniform over the group
-        const int mine = e + sub;
-        if (mine < e1) {
-            const float4 a = __ldg(m.orec + 2 * (int64_t)mine), b = __ldg(m.orec + 2 * (int64_t)mine + 1);
+    const int excl = incl - cnt;
+    const int total = SINGLE ? cnt : __shfl_sync(0xffffffffu, incl, 31);
+    for (int f0 = 0; f0 < total; f0 += 32) {              // uniform over the warp
+        const int f = f0 + lane;
+        int e = e0 + f;
+        if (!SINGLE) {
+            // owner of flat face f = the last lane whose exclusive prefix is <= f
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, excl, lo + step);     // lo + step <= 31
+                if (v <= f) lo += step;
+            }
+            e = __shfl_sync(0xffffffffu, e0, lo) + (f - __shfl_sync(0xffffffffu, excl, lo));
+        }
+        if (f < total) {
+            const float4 a = __ldg(m.orec + 2 * (int64_t)e), b = __ldg(m.orec + 2 * (int64_t)e + 1);
             const float bx0 = fminf(fminf(a.x, a.z), b.x), bx1 = fmaxf(fmaxf(a.x, a.z), b.x);
             const float by0 = fminf(fminf(a.y, a.w), b.y), by1 = fmaxf(fmaxf(a.y, a.w), b.y);
             if (!cannot_improve(box_dist2(px, py, bx0, by0, bx1, by1), best)) {
                 const float d = point_tri_dist2(px, py, a.x, a.y, a.z, a.w, b.x, b.y);
-                const int f = __float_as_int(b.z);
-                if (d < best || (d == best && f < bf)) { best = d; bf = f; }
+                const int fi = __float_as_int(b.z);
+                if (d < best || (d == best && fi < bf)) { best = d; bf = fi; }
             }
         }
-        group_min(group_mask, best, bf);
+        warp_min(best, bf);
         if (best <= stop) return;
     }
 }
@@ -135,10 +140,9 @@ __device__ __forceinline__ void visit_own_cell(const MapDev& m, int cx, int cy, 
 // min over all faces of the map; returns the squared distance, *face = argmin (lowest face index among equal
 // distances).  The search ends as soon as a face within `stop` (the threshold of the loss, >= 0) is found: the loss
 // of this corner and its gradient are then 0 whatever the true minimum is (F.threshold, infractions.py:172), and the
-// returned value / face are those of that face.  kGroup consecutive lanes search for ONE point: they split the faces of the point's own cell and the
-// cells of every ring, and share their minimum after each ring (the minimum does not depend on the visiting order).
-
-__device__ float nearest_face(const MapDev& m, float px, float py, float stop, int* face, int sub, unsigned group_mask) {
+// returned value / face are those of that face.  All 32 lanes of the warp search for the same point and return the
+// same result.
+__device__ float nearest_face(const MapDev& m, float px, float py, float stop, int* face, int lane) {
     float best = CUDART_INF_F;
     int bf = -1;
     if (m.nf == 0) { *face = -1; return 0.0f; }
@@ -154,7 +158,7 @@ __device__ float nearest_face(const MapDev& m, float px, float py, float stop, i
     const float inner = fminf(fmaxf(fminf(fminf(ux, m.ocs - ux), fminf(uy, m.ocs - uy)), 0.0f), m.ocs);
     for (int k = k0; k <= kmax; k++) {
         if (k == 0) {
-            visit_own_cell(m, cx, cy, px, py, stop, best, bf, sub, group_mask);
+            visit_cells<true>(m, true, cx, cy, px, py, stop, best, bf, lane);
         } else {
             // the in-grid cells of ring k: top row, bottom row, left column, right column
             const int xa = max(cx - k, 0), xb = min(cx + k, m.ogx - 1);
@@ -163,18 +167,17 @@ __device__ float nearest_face(const MapDev& m, float px, float py, float stop, i
             const int nt = cy - k >= 0 ? nx : 0, nb = cy + k < m.ogy ? nx : 0;
             const int nl = cx - k >= 0 ? ny : 0, nr = cx + k < m.ogx ? ny : 0;
             const int n = nt + nb + nl + nr;
-            for (int i = sub; i < n; i += kGroup) {
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
                 int x, y;
                 if (i < nt) { x = xa + i; y = cy - k; }
                 else if (i < nt + nb) { x = xa + (i - nt); y = cy + k; }
                 else if (i < nt + nb + nl) { x = cx - k; y = ya + (i - nt - nb); }
                 else { x = cx + k; y = ya + (i - nt - nb - nl); }
-                visit_cell(m, x, y, px, py, stop, best, bf);
+                visit_cells<false>(m, i < n, x, y, px, py, stop, best, bf, lane);
                 if (best <= stop) break;
             }
         }
-        // share the minimum (and the lowest face index that attains it) within the group
-        if (k > 0) group_min(group_mask, best, bf);
         // (1 mm slack for the cell assignment of p itself)
         if (best <= stop) break;
         const float reach = fmaxf((float)k * m.ocs + inner - 1e-3f, 0.0f);
@@ -195,33 +198,43 @@ __device__ __forceinline__ void corner_of(const float* st, const float* lw, int 
     py = (ux * s + uy * c) + st[1];
 }
 
-// one warp per agent: 4 corners x kGroup lanes
-__global__ void __launch_bounds__(128) offroad_fwd_kernel(MapSetDev maps, const int32_t* __restrict__ env_map,
+// one CTA of 4 warps per agent, one warp per box corner
+#ifndef TDS_OFFROAD_MINB
+#define TDS_OFFROAD_MINB 12
+#endif
+__global__ void __launch_bounds__(128, TDS_OFFROAD_MINB) offroad_fwd_kernel(MapSetDev maps, const int32_t* __restrict__ env_map,
                                                           const float* __restrict__ state, const float* __restrict__ lenwid,
                                                           const uint8_t* __restrict__ present, int B, int A, float thr,
                                                           float* __restrict__ out, int32_t* __restrict__ face) {
-    static_assert(4 * kGroup == 32, "a warp holds the four corners of one agent");
-    const int64_t agent = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int k = lane / kGroup, sub = lane % kGroup;
-    if (agent >= (int64_t)B * A) return;           // warp-uniform
+    __shared__ float s_v[4];
+    __shared__ float2 s_corner[4];
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    for (int64_t agent = blockIdx.x; agent < (int64_t)B * A; agent += gridDim.x) {
     float v = 0.0f;
     int bf = -1;
     const int b = (int)(agent / A);
     const bool here = present ? present[agent] != 0 : true;
+    if (here && threadIdx.x < 4) {                 // the (double precision) sin / cos is evaluated by 4 lanes of ONE warp
+        float px, py, s, c;
+        corner_of(state + 4 * agent, lenwid + 2 * agent, threadIdx.x, px, py, s, c);
+        s_corner[threadIdx.x] = make_float2(px, py);
+    }
+    __syncthreads();
     if (here) {
         const MapDev& m = maps.m[env_map ? env_map[b] : 0];
-        float px, py, s, c;
-        corner_of(state + 4 * agent, lenwid + 2 * agent, k, px, py, s, c);
-        const float d2 = nearest_face(m, px, py, fmaxf(thr, 0.0f), &bf, sub, ((1u << kGroup) - 1u) << (k * kGroup));
+        const float px = s_corner[k].x, py = s_corner[k].y;
+        const float d2 = nearest_face(m, px, py, fmaxf(thr, 0.0f), &bf, lane);
         v = d2 > thr ? d2 : 0.0f;           // F.threshold(d2, thr, 0), infractions.py:172
     }
-    if (face && sub == 0) face[4 * agent + k] = bf;
+    if (lane == 0) {
+        if (face) face[4 * agent + k] = bf;
+        s_v[k] = v;
+    }
+    __syncthreads();
     // sum of the 4 corners, in corner order
-    const unsigned full = 0xffffffffu;
-    const float v0 = __shfl_sync(full, v, 0), v1 = __shfl_sync(full, v, kGroup);
-    const float v2 = __shfl_sync(full, v, 2 * kGroup), v3 = __shfl_sync(full, v, 3 * kGroup);
-    if (lane == 0) out[agent] = ((v0 + v1) + v2) + v3;
+    if (threadIdx.x == 0) out[agent] = ((s_v[0] + s_v[1]) + s_v[2]) + s_v[3];
+    __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(128) offroad_bwd_kernel(MapSetDev maps, const int32_t* __restrict__ env_map,
@@ -292,9 +305,10 @@ extern "C" int tds_offroad_fwd(const tds_map_t* const* maps, int32_t n_maps, con
     TDS_REQUIRE(d_state && d_lenwid && d_out, "offroad: null pointer");
     MapSetDev set;
     if (int e = tds::gather_maps(maps, n_maps, set)) return e;
-    const int64_t threads = (int64_t)B * A * 32;       // a warp per agent
-    TDS_REQUIRE((threads + 127) / 128 <= 2147483647LL, "offroad: too many agents");
-    offroad_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    // agents are dealt round-robin to a grid that fills the GPU a few times over (a CTA per agent would spend a
+    // good part of its life being launched)
+    const int64_t grid = std::min<int64_t>((int64_t)B * A, (int64_t)tds::sm_count() * 64);
+    offroad_fwd_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(
         set, d_env_map, d_state, d_lenwid, d_present, B, A, threshold, d_out, d_face);
     TDS_LAUNCH_OK();
     return TDS_OK;
