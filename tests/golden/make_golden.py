@@ -342,6 +342,26 @@ def golden_noise():
                                            / np.maximum(np.abs(out["eps"]), 1e-9), 2)).tolist()[:8])
 
 
+def golden_mesh_formats():
+    """The reference's two mesh wire formats (mesh.py:238-297, 700-719) written by the reference itself for a 50 m
+    window of Town02: BirdviewMesh.pickle and BirdviewMesh.save (json), plus the arrays they hold."""
+    import dataclasses
+    mesh = find_map_config("carla_Town02").road_mesh
+    v, f, vc = mesh.verts[0], mesh.faces[0], mesh.vert_category[0]
+    centre = v[f[100]].mean(0)
+    keep = ((v[f] - centre).abs().amax(-1) < 25.0).all(-1)                  # faces entirely inside the window
+    fk = f[keep]
+    used, inv = torch.unique(fk, return_inverse=True)
+    small = dataclasses.replace(mesh, verts=v[used][None], faces=inv[None], vert_category=vc[used][None])
+    os.makedirs(os.path.join(HERE, "maps"), exist_ok=True)
+    small.pickle(os.path.join(HERE, "maps", "town02_window.pkl"))
+    small.save(os.path.join(HERE, "maps", "town02_window_mesh.json"))
+    np.savez_compressed(os.path.join(HERE, "maps", "town02_window_arrays.npz"), verts=small.verts[0].numpy(),
+                        faces=small.faces[0].numpy(), vert_category=small.vert_category[0].numpy(),
+                        categories=np.array(small.categories))
+    print("mesh formats:", tuple(small.verts.shape), tuple(small.faces.shape), small.categories)
+
+
 def golden_traffic():
     """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
     simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
@@ -369,6 +389,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals", "noise"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals", "noise", "mesh_formats"]
     for w in which:
         globals()["golden_" + w]()

@@ -153,3 +153,27 @@ def test_traffic_control_corners_and_masking():
     assert float(tc.corners[0, 1].max()) == -1000.0          # masked controls sit at -1000 (traffic_controls.py:33)
     assert tc.allowed_states == ["red", "yellow", "green"]
     assert tc.extend(3, in_place=False).corners.shape[0] == 3
+
+
+def test_reference_mesh_wire_formats():
+    """StaticMap reads the files the reference's BirdviewMesh.pickle / BirdviewMesh.save wrote (no reference needed)."""
+    import os
+    import pickle
+    import tempfile
+    import torchdrivesim_b200 as tds
+    d = os.path.join(os.path.dirname(__file__), "golden", "maps")
+    arrays = np.load(os.path.join(d, "town02_window_arrays.npz"))
+    for m in (tds.StaticMap.from_mesh_pickle(os.path.join(d, "town02_window.pkl")),
+              tds.StaticMap.from_mesh_json(os.path.join(d, "town02_window_mesh.json"))):
+        assert np.array_equal(m.verts, arrays["verts"]) and np.array_equal(m.faces, arrays["faces"])
+        assert np.array_equal(m.vert_category, arrays["vert_category"])
+        assert list(m.categories) == [str(c) for c in arrays["categories"]]
+        assert m.faces.shape[0] > 100 and set(m.face_category_names) == {"road", "left_lane", "right_lane"}
+    # anything but tensors inside the mesh object is refused
+    with tempfile.NamedTemporaryFile(suffix=".pkl", delete=False) as f:
+        pickle.dump({"verts": os.system}, f)
+    try:
+        with pytest.raises(pickle.UnpicklingError):
+            tds.StaticMap.from_mesh_pickle(f.name)
+    finally:
+        os.unlink(f.name)

@@ -77,6 +77,37 @@ class StaticMap:
         vcat = mesh.vert_category[batch_index].detach().cpu().numpy()
         return cls(verts, faces, list(mesh.categories), vcat, **kw)
 
+    @classmethod
+    def from_mesh_pickle(cls, path: str, batch_index: int = 0, **kw) -> "StaticMap":
+        """Reads a mesh stored by the reference's `BirdviewMesh.pickle` (mesh.py:238-256) WITHOUT the reference
+        package: the pickled `torchdrivesim.mesh.*` object is rebuilt as a plain attribute bag, and only tensor /
+        array reconstruction helpers are allowed besides it (anything else in the file raises)."""
+        import pickle
+
+        class _Bag:
+            def __setstate__(self, state):
+                self.__dict__.update(state)
+
+        allowed = {("collections", "OrderedDict"), ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"),
+                   ("torch.storage", "_load_from_bytes"), ("torch", "Size"), ("numpy", "ndarray"), ("numpy", "dtype"),
+                   ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct")}
+
+        class _Unpickler(pickle.Unpickler):
+            def find_class(self, module, name):
+                if module.startswith("torchdrivesim."):
+                    return _Bag
+                if (module, name) in allowed or (module == "torch" and (name.endswith("Storage") or name in
+                                                                         ("float32", "float64", "int64", "int32", "bool", "uint8"))):
+                    return super().find_class(module, name)
+                raise pickle.UnpicklingError(f"{module}.{name} is not allowed in a mesh pickle")
+
+        with open(path, "rb") as f:
+            mesh = _Unpickler(f).load()
+        for attr in ("verts", "faces", "categories", "vert_category"):
+            if not hasattr(mesh, attr):
+                raise _lib.TdsError(f"{path} does not hold a BirdviewMesh (no `{attr}`)")
+        return cls.from_birdview_mesh(mesh, batch_index=batch_index, name=os.path.basename(path), **kw)
+
     # ---- queries ------------------------------------------------------------------------------
     @property
     def face_category_names(self) -> List[str]:
