@@ -221,7 +221,7 @@ def run_ours(args):
     state0 = torch.tensor(state, device=dev)
     act_dev = torch.tensor(actions, device=dev)
     images = torch.empty(B, A, 3, RES, RES, dtype=torch.float32, device=dev)
-    metrics = torch.zeros(4, dtype=torch.float64, device=dev)
+    metrics = torch.zeros(6, dtype=torch.float64, device=dev)     # distributed.METRIC_NAMES
     lib = tds._lib.load()
 
     def step(action, out_images, ev=None):
@@ -265,7 +265,7 @@ def run_ours(args):
         sampler.start()
     def full_step(i):
         img, coll, off = runner.run(act_dev[i])
-        metrics.add_(torch.stack([coll.sum(), off.sum(), (coll > 0).sum(), (off > 0).sum()]).double())
+        tds.ops.infraction_metrics(coll, off, None, metrics)        # one launch, accumulated over the steps
 
     # W warm-up steps identical to the timed ones, continued until the GPU has been busy for 0.5 s so that the
     # timed region starts at sustained clocks (lazy module loading, allocator and caches are warm)
@@ -370,7 +370,7 @@ def run_ours(args):
             "e2e_device_images": {"value": e2e["device_images"], "unit": "agent-env-steps/s",
                                   "h2d_bytes_per_step": int(h_act[0].numel() * 4), "d2h_bytes_per_step": int(small_out),
                                   "note": "same, images stay in HBM for a GPU consumer (the reference API returns device tensors)"},
-            "gpu_launches": 5 * K, "eager_ms_per_step": eager_ms,
+            "gpu_launches": 6 * K, "eager_ms_per_step": eager_ms,
             "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "raster_ms_per_launch": raster_ms, "algorithmic_bytes_per_launch": B * A * 12 * RES * RES,

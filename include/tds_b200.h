@@ -150,6 +150,16 @@ int tds_waypoint_gather(const float* d_waypoints, const uint8_t* d_mask, const i
                         int32_t N, int32_t M, int32_t count, float* d_out_waypoints, uint8_t* d_out_mask, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Aggregate infraction metrics of a step: the vector a multi-GPU job all-reduces (no reference counterpart: the
+ * reference leaves the aggregation of compute_collision / compute_offroad to its callers).
+ *   d_acc[0..5] (float64, accumulated in place) += sum of d_collision over present agents, sum of d_offroad,
+ *   agents with collision > 0, agents with offroad > 0, present agents, agent slots n.  d_present [n] uint8 or NULL.
+ * One launch, fixed reduction order (reproducible sums).
+ * ---------------------------------------------------------------------------------------- */
+int tds_infraction_metrics(const float* d_collision, const float* d_offroad, const uint8_t* d_present, int64_t n,
+                           double* d_acc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Non-visual observations.  Replaces Simulator.get_all_agents_relative (simulator.py:748-781) with
  * utils.relative (utils.py:71-79): for every origin agent i < A and every agent j < N of the same environment
  *   out = ( R(-psi_i) (xy_j - xy_i),  normalize_angle(psi_j - psi_i),  length_j, width_j, present_j ).

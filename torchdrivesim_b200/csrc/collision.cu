@@ -275,6 +275,35 @@ __global__ void __launch_bounds__(128) sensing_occlusion_kernel(const float4* __
     }
 }
 
+// ---- aggregate infraction metrics of a step (the vector that is all-reduced over the GPUs):
+// acc[0..5] += sum of collision over present agents, sum of offroad, agents with collision > 0, agents with
+// offroad > 0, present agents, agent slots.  ONE CTA with a fixed reduction order: the sums are reproducible.
+__global__ void __launch_bounds__(1024) infraction_metrics_kernel(const float* __restrict__ collision, const float* __restrict__ offroad,
+                                                                  const uint8_t* __restrict__ present, int64_t n,
+                                                                  double* __restrict__ acc) {
+    __shared__ double s_part[32][5];
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const bool here = present ? present[i] != 0 : true;
+        const float c = collision[i], o = offroad[i];
+        if (here) { v[0] += (double)c; v[1] += (double)o; v[2] += c > 0.0f; v[3] += o > 0.0f; v[4] += 1.0; }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 5; k++) s_part[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w][threadIdx.x];
+        acc[threadIdx.x] += t;
+    }
+    if (threadIdx.x == 5) acc[5] += (double)n;
+}
+
 // ---- IoU backward.  d(intersection area) is the boundary integral of the normal velocity: every edge of
 // the clipped polygon lies either on a face of box q (it moves with q's pose and size) or on a face of box p
 // (it moves with p's size).  Each polygon vertex carries the tag of the edge that leaves it:
@@ -628,6 +657,15 @@ extern "C" int tds_traffic_light_violation(const float* d_agent_box, const float
     tl_violation_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_agent_box, d_tl_corners, d_tl_state,
                                                                                    d_present, B, A, L, red_state,
                                                                                    rear_factor, d_out);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+extern "C" int tds_infraction_metrics(const float* d_collision, const float* d_offroad, const uint8_t* d_present,
+                                      int64_t n, double* d_acc, void* stream) {
+    TDS_REQUIRE(n >= 0, "infraction_metrics: negative size");
+    TDS_REQUIRE(d_acc && (n == 0 || (d_collision && d_offroad)), "infraction_metrics: null pointer");
+    infraction_metrics_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_collision, d_offroad, d_present, n, d_acc);
     TDS_LAUNCH_OK();
     return TDS_OK;
 }

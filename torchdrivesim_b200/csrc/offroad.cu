@@ -209,14 +209,15 @@ __global__ void __launch_bounds__(128, TDS_OFFROAD_MINB) offroad_fwd_kernel(MapS
     __shared__ float s_v[4];
     __shared__ float2 s_corner[4];
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    for (int64_t agent = blockIdx.x; agent < (int64_t)B * A; agent += gridDim.x) {
+    const unsigned n_agents = (unsigned)B * (unsigned)A;          // < 2^31, checked by the host
+    for (unsigned agent = blockIdx.x; agent < n_agents; agent += gridDim.x) {
     float v = 0.0f;
     int bf = -1;
-    const int b = (int)(agent / A);
+    const int b = (int)(agent / (unsigned)A);
     const bool here = present ? present[agent] != 0 : true;
     if (here && threadIdx.x < 4) {                 // the (double precision) sin / cos is evaluated by 4 lanes of ONE warp
         float px, py, s, c;
-        corner_of(state + 4 * agent, lenwid + 2 * agent, threadIdx.x, px, py, s, c);
+        corner_of(state + 4 * (size_t)agent, lenwid + 2 * (size_t)agent, threadIdx.x, px, py, s, c);
         s_corner[threadIdx.x] = make_float2(px, py);
     }
     __syncthreads();
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(128, TDS_OFFROAD_MINB) offroad_fwd_kernel(MapS
         v = d2 > thr ? d2 : 0.0f;           // F.threshold(d2, thr, 0), infractions.py:172
     }
     if (lane == 0) {
-        if (face) face[4 * agent + k] = bf;
+        if (face) face[4 * (size_t)agent + k] = bf;
         s_v[k] = v;
     }
     __syncthreads();
@@ -307,6 +308,7 @@ extern "C" int tds_offroad_fwd(const tds_map_t* const* maps, int32_t n_maps, con
     if (int e = tds::gather_maps(maps, n_maps, set)) return e;
     // agents are dealt round-robin to a grid that fills the GPU a few times over (a CTA per agent would spend a
     // good part of its life being launched)
+    TDS_REQUIRE((int64_t)B * A <= 2147483647LL, "offroad: too many agents");
     const int64_t grid = std::min<int64_t>((int64_t)B * A, (int64_t)tds::sm_count() * 64);
     offroad_fwd_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(
         set, d_env_map, d_state, d_lenwid, d_present, B, A, threshold, d_out, d_face);

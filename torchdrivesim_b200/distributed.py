@@ -41,7 +41,12 @@ def shard_indices(n_envs: int, rank: int, world: int, device=None) -> torch.Tens
 
 
 def infraction_metrics(collision: torch.Tensor, offroad: torch.Tensor, present: torch.Tensor) -> torch.Tensor:
-    """[6] float64: collision sum, offroad sum, colliding agents, offroad agents, present agents, agent slots."""
+    """[6] float64: collision sum, offroad sum, colliding agents, offroad agents, present agents, agent slots.
+    CUDA tensors: one launch of tds_infraction_metrics (ops.infraction_metrics, which can also accumulate over steps);
+    CPU tensors (the gloo tests of the host logic): the same vector with torch ops."""
+    if collision.is_cuda:
+        from . import ops
+        return ops.infraction_metrics(collision, offroad, present)
     p = present.to(collision.dtype)
     return torch.stack([(collision * p).sum(), (offroad * p).sum(), ((collision > 0) & present).sum(),
                         ((offroad > 0) & present).sum(), present.sum(), torch.tensor(present.numel(), device=present.device)]

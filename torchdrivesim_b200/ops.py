@@ -108,8 +108,8 @@ class _AllPairs(torch.autograd.Function):
         a = _lib.as_f32(all_box)
         m = _lib.as_u8(mask)
         B, A, N = e.shape[0], e.shape[1], a.shape[1]
-        out = torch.zeros(B, A, dtype=torch.float32, device=e.device)
-        arg = torch.zeros(B, A, dtype=torch.int32, device=e.device)
+        out = torch.empty(B, A, dtype=torch.float32, device=e.device)       # the kernel writes every row
+        arg = torch.empty(B, A, dtype=torch.int32, device=e.device)
         _lib.check(lib.tds_collision_allpairs_fwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), B, A, N, metric,
                                                   1 if ego_is_prefix else 0, _lib.ptr(out), _lib.ptr(arg),
                                                   _lib.stream_ptr(e.device)))
@@ -221,6 +221,25 @@ def sensing_occlusion(all_state: torch.Tensor, all_size: torch.Tensor, base_mask
     return out.view(torch.bool)
 
 
+def infraction_metrics(collision: torch.Tensor, offroad: torch.Tensor, present: Optional[torch.Tensor] = None,
+                       acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[6] float64, accumulated into `acc` when given: collision sum, offroad sum, colliding agents, offroad agents,
+    present agents, agent slots (distributed.METRIC_NAMES) - the vector a multi-GPU job all-reduces.  One launch."""
+    lib = _lib.load()
+    c, o = _lib.as_f32(collision), _lib.as_f32(offroad)
+    if c.shape != o.shape:
+        raise _lib.TdsError("infraction_metrics: collision and offroad must have the same shape")
+    p = None if present is None else _lib.as_u8(present)
+    if p is not None and p.shape != c.shape:
+        raise _lib.TdsError("infraction_metrics: present must have the shape of collision")
+    if acc is None:
+        acc = torch.zeros(6, dtype=torch.float64, device=c.device)
+    elif acc.dtype != torch.float64 or acc.numel() != 6 or not acc.is_contiguous():
+        raise _lib.TdsError("infraction_metrics: acc must be a contiguous float64 tensor of 6 elements")
+    _lib.check(lib.tds_infraction_metrics(_lib.ptr(c), _lib.ptr(o), _lib.ptr(p), c.numel(), _lib.ptr(acc), _lib.stream_ptr(c.device)))
+    return acc
+
+
 # ------------------------------------------------------------------------------------ offroad
 class _Offroad(torch.autograd.Function):
     @staticmethod
@@ -232,7 +251,7 @@ class _Offroad(torch.autograd.Function):
         B, A = s.shape[0], s.shape[1]
         handles, n_maps = mapset.handles(s.device)
         env_map = mapset.env_map_on(s.device)
-        out = torch.zeros(B, A, dtype=torch.float32, device=s.device)
+        out = torch.empty(B, A, dtype=torch.float32, device=s.device)       # the kernel writes every agent
         face = torch.empty(B, A, 4, dtype=torch.int32, device=s.device)
         _lib.check(lib.tds_offroad_fwd(handles, n_maps, _lib.ptr(env_map), _lib.ptr(s), _lib.ptr(lw), _lib.ptr(p), B, A,
                                        float(threshold), _lib.ptr(out), _lib.ptr(face), _lib.stream_ptr(s.device)))
