@@ -111,3 +111,20 @@ def test_batch_plumbing():
     assert sim.npc_controller.time == 0                    # the copy stepped, the original did not
     big = sim.npc_controller.copy().extend(3)
     assert big.npc_states.shape[0] == 6 and big.spawn_controller.spawn_masks.shape[0] == 6
+
+
+def test_simulator_extend_repeats_environments():
+    """Simulator.extend(n) (simulator.py:443-478): every environment n times in a row, all components included."""
+    dev = torch.device("cuda:0")
+    g = util.golden("npc")
+    sim = _sim_from_golden(g, dev)
+    twice = sim.extend(2, in_place=False)
+    assert twice.batch_size == 2 * sim.batch_size and sim.batch_size == g["agent_state0"].shape[0]
+    for step in range(3):
+        act = torch.as_tensor(g["actions"][step], device=dev)
+        sim.step(act)
+        twice.step(act.repeat_interleave(2, dim=0))
+    for got, ref in ((twice.get_state(), sim.get_state()), (twice.get_npc_state(), sim.get_npc_state()),
+                     (twice.get_npc_present_mask(), sim.get_npc_present_mask()), (twice.compute_collision(), sim.compute_collision()),
+                     (twice.compute_offroad(), sim.compute_offroad()), (twice.render_egocentric(), sim.render_egocentric())):
+        assert torch.equal(got, ref.repeat_interleave(2, dim=0))

@@ -198,6 +198,23 @@ class Simulator:
         other.waypoint_goals = self.waypoint_goals.copy() if self.waypoint_goals is not None else None
         return other
 
+    def extend(self, n: int, in_place: bool = True):
+        """Multiplies the batch dimension by n: every environment is repeated n times in a row (simulator.py:443-478)."""
+        if not in_place:
+            return self.copy().extend(n, in_place=True)
+        grow = lambda x: x.unsqueeze(1).expand((x.shape[0], n) + x.shape[1:]).reshape((n * x.shape[0],) + x.shape[1:])
+        self.road_mesh = self.road_mesh.extend(n)
+        self.agent_size, self.agent_type, self.present_mask = grow(self.agent_size), grow(self.agent_type), grow(self.present_mask)
+        self.kinematic_model.extend(n)                      # kinematic models are modified in place
+        self._batch_size *= n
+        self.birdview_mesh_generator = self.birdview_mesh_generator.expand(n)
+        if self.traffic_controls is not None:
+            self.traffic_controls = {k: v.extend(n) for k, v in self.traffic_controls.items()}
+        if self.waypoint_goals is not None:
+            self.waypoint_goals = self.waypoint_goals.extend(n)
+        self.npc_controller = self.npc_controller.extend(n)
+        return self
+
     def select_batch_elements(self, idx: Tensor, in_place: bool = True):
         """Picks environments `idx` (the batch shard of one GPU in a multi-GPU run)."""
         other = self if in_place else self.copy()
