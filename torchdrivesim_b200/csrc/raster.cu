@@ -195,7 +195,10 @@ __device__ __forceinline__ void project_f(const Camera& cam, float x, float y, f
 
 // kind of a candidate after cull + projection + truncation (rendering/cv2.py:52-56)
 enum { kCulled = 0, kVerts = 1, kHuge = 2, kShort = 3, kTall = 4, kClipped = 5 };
-constexpr int kShortRows = 5;      // inside triangles spanning at most this many row steps go to the "short" queue
+#ifndef TDS_SHORT_ROWS
+#define TDS_SHORT_ROWS 5
+#endif
+constexpr int kShortRows = TDS_SHORT_ROWS;      // inside triangles spanning at most this many row steps go to the "short" queue
 
 template <bool POW2>
 __device__ __forceinline__ int setup_triangle(const Camera& cam, float x0, float y0, float x1, float y1, float x2,
