@@ -1,6 +1,5 @@
-# raster parity tests + timings at the bench size and at configs 3 / 4
-python -m pytest tests/test_gpu_raster.py tests/test_gpu_graph.py tests/test_gpu_goals.py tests/test_gpu_npc.py -x -q 2>&1 | tail -3
+# raster parity tests + timings at the bench size and at the tile sizes of configs 3 / 4
+python -m pytest tests/test_gpu_raster.py tests/test_gpu_graph.py -x -q 2>&1 | tail -3
 python profiles/time_raster.py
 python profiles/time_raster_res.py 128 256 128
 python profiles/time_raster_res.py 256 64 128
-python profiles/bench_configs.py 3 4

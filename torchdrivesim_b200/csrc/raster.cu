@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
     constexpr int GROUPS = G == 32 ? 4 : 1;
     constexpr int QN = 64;                      // queue capacity per warp and kind
     // SMALL: images up to 128 pixels, slopes through the reciprocal table
-    constexpr bool POW2 = RES == 64;
+    constexpr bool POW2 = RES != 0 && (RES & (RES - 1)) == 0;     // compile-time tile size that is a power of two
     const int res = RES ? RES : a.res;          // RES = 64 is compiled with constant strides
     const int W32 = RES ? RES / 32 : (res + 31) >> 5;
     const int group = G == 32 ? (threadIdx.x >> 5) : 0;
@@ -865,6 +865,8 @@ extern "C" int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps,
     if (K <= 7) {
         if (G == 32 && res == 64) return launch(raster_kernel<32, 64, 3, true>, 4, 128, raster_static_smem(32, 64, 3));
         if (G == 32) return launch(raster_kernel<32, 0, 3, true>, 4, 128, false);
+        if (G == 128 && res == 128) return launch(raster_kernel<128, 128, 3, true>, 1, 128, false);     // configs 3 and 4: constant strides
+        if (G == 128 && res == 256) return launch(raster_kernel<128, 256, 3, false>, 1, 128, false);
         if (G == 128) return small ? launch(raster_kernel<128, 0, 3, true>, 1, 128, false) : launch(raster_kernel<128, 0, 3, false>, 1, 128, false);
         if (G == 256) return small ? launch(raster_kernel<256, 0, 3, true>, 1, 256, false) : launch(raster_kernel<256, 0, 3, false>, 1, 256, false);
         return launch(raster_kernel<512, 0, 3, false>, 1, 512, false);
