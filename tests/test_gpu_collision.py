@@ -180,7 +180,8 @@ def test_iou_backward_matches_float64_finite_differences():
 
 
 def test_infraction_metrics_vector():
-    """tds_infraction_metrics against the torch expression of distributed.infraction_metrics, accumulation included."""
+    """tds_infraction_metrics against the torch expression of distributed.infraction_metrics, accumulation included;
+    there is no CPU implementation of the op."""
     import torchdrivesim_b200 as tds
     from torchdrivesim_b200 import distributed as D
     dev = torch.device("cuda:0")
@@ -189,14 +190,16 @@ def test_infraction_metrics_vector():
         coll = torch.tensor(rng.uniform(-0.5, 2, shape).clip(0).astype(np.float32), device=dev)
         off = torch.tensor(rng.uniform(-3, 5, shape).clip(0).astype(np.float32), device=dev)
         present = torch.tensor(rng.uniform(size=shape) > 0.25, device=dev)
-        got = D.infraction_metrics(coll, off, present)
+        got = tds.ops.infraction_metrics(coll, off, present)
         ref = D.infraction_metrics(coll.cpu(), off.cpu(), present.cpu())
         assert got.dtype == torch.float64 and got.shape == (6,)
         np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-6)
         assert np.array_equal(got[2:].cpu().numpy(), ref[2:].numpy())          # the counts are exact
         twice = tds.ops.infraction_metrics(coll, off, present, got.clone())
         np.testing.assert_allclose(twice.cpu().numpy(), 2 * ref.numpy(), rtol=1e-6)
-        again = D.infraction_metrics(coll, off, present)
+        again = tds.ops.infraction_metrics(coll, off, present)
         assert torch.equal(again, got)                                           # fixed reduction order
     everyone = tds.ops.infraction_metrics(coll, off)
     assert float(everyone[4]) == float(everyone[5]) == coll.numel()
+    with pytest.raises(tds._lib.TdsError):
+        tds.ops.infraction_metrics(coll.cpu(), off.cpu())

@@ -41,12 +41,10 @@ def shard_indices(n_envs: int, rank: int, world: int, device=None) -> torch.Tens
 
 
 def infraction_metrics(collision: torch.Tensor, offroad: torch.Tensor, present: torch.Tensor) -> torch.Tensor:
-    """[6] float64: collision sum, offroad sum, colliding agents, offroad agents, present agents, agent slots.
-    CUDA tensors: one launch of tds_infraction_metrics (ops.infraction_metrics, which can also accumulate over steps);
-    CPU tensors (the gloo tests of the host logic): the same vector with torch ops."""
-    if collision.is_cuda:
-        from . import ops
-        return ops.infraction_metrics(collision, offroad, present)
+    """[6] float64: collision sum, offroad sum, colliding agents, offroad agents, present agents, agent slots - the
+    definition of the metric vector as a torch expression (host-side logic, any device; the gloo tests use it).
+    The hot path computes and accumulates the same vector with ONE launch: `ops.infraction_metrics`
+    (tds_infraction_metrics, CUDA only)."""
     p = present.to(collision.dtype)
     return torch.stack([(collision * p).sum(), (offroad * p).sum(), ((collision > 0) & present).sum(),
                         ((offroad > 0) & present).sum(), present.sum(), torch.tensor(present.numel(), device=present.device)]
