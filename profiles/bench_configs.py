@@ -1,7 +1,7 @@
 """Configs 3-5 of BASELINE.json at the size ONE GPU of the 8-GPU job holds, timed with CUDA events.
 These are parity-test configurations, not bench.py lines; this script records what they cost on a B200.
 
-  config 3: Town01 + Town02 alternating by environment, 512 envs x 128 agents (96 bicycle vehicles + 32 unicycle
+  config 3: Town01 / Town02 / Town10HD alternating by environment, 512 envs x 128 agents (96 bicycle vehicles + 32 unicycle
             pedestrians), traffic lights cycling every 30 steps, 128x128 birdviews, discs collisions + offroad
   config 4: Town01, 64 envs x 512 agents inside a 120 m box, 256x256 birdviews, IoU collisions + offroad
   config 5: Town01, 256 envs x 64 agents, 20-step rollout, loss = collisions (discs) + offroad + MSE, backward to actions
@@ -45,9 +45,10 @@ def timed(fn, n):
 def config3():
     rng = np.random.default_rng(3)
     B, A, res = 512, 128, 128
-    maps = [load("carla_Town01"), load("carla_Town02")]
-    env_map = torch.arange(B, dtype=torch.int32) % 2
-    xy = np.stack([maps[b % 2][1][rng.integers(0, len(maps[b % 2][1]), A)] for b in range(B)])
+    maps = [load("carla_Town01"), load("carla_Town02"), load("carla_Town10HD")]     # Town10HD is built from its OSM file
+    M = len(maps)
+    env_map = torch.arange(B, dtype=torch.int32) % M
+    xy = np.stack([maps[b % M][1][rng.integers(0, len(maps[b % M][1]), A)] for b in range(B)])
     state = np.concatenate([xy, rng.uniform(0, 6.28, (B, A, 1)), rng.uniform(0, 5, (B, A, 1))], -1).astype(np.float32)
     types = torch.tensor((np.arange(A) >= 96).astype(np.int64)).expand(B, A).contiguous().to(dev)
     size = torch.where(types[..., None] == 1, torch.tensor(PED, device=dev), torch.tensor(VEH[:2], device=dev))
@@ -59,7 +60,7 @@ def config3():
     pos = np.zeros((B, L, 5), np.float32)
     mask = np.zeros((B, L), bool)
     for b in range(B):
-        p = poses[b % 2]
+        p = poses[b % M]
         pos[b, :len(p)], mask[b, :len(p)] = p, True
     replay = torch.tensor((np.arange(120)[None, None] // 30 + rng.integers(0, 3, (B, L, 1))) % 3, device=dev)
     tl = tds.TrafficLightControl(torch.tensor(pos, device=dev), replay_states=replay, mask=torch.tensor(mask, device=dev))

@@ -37,6 +37,33 @@ def convert(name: str) -> None:
     print(name, verts.shape, faces.shape, d["categories"], lines.shape, sorted(set(types)))
 
 
+def convert_osm(name: str, with_npz: bool) -> None:
+    """Maps that the reference derives from their lanelet2 OSM file (map.py:61-74): the OSM (gzipped) and stop lines are
+    copied as data fixtures; with_npz also stores the mesh that torchdrivesim_b200.osm builds from them in the schema
+    above, as the INPUT of the oracle-vs-GPU parity tests on that map (the reference needs lanelet2 to load it)."""
+    import gzip
+    import shutil
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    import torchdrivesim_b200 as tds
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(REF_MAPS, name, f"{name}.osm"), "rb") as f, gzip.GzipFile(os.path.join(OUT, f"{name}.osm.gz"), "wb", 9, mtime=0) as g:
+        shutil.copyfileobj(f, g)
+    shutil.copy(os.path.join(REF_MAPS, name, f"{name}_stoplines.json"), os.path.join(OUT, f"{name}_stoplines.json"))
+    os.chmod(os.path.join(OUT, f"{name}_stoplines.json"), 0o644)
+    if with_npz:
+        meta = json.load(open(os.path.join(REF_MAPS, name, "metadata.json")))
+        m = tds.StaticMap.from_lanelet_osm(os.path.join(OUT, f"{name}.osm.gz"), origin=tuple(meta["lanelet_map_origin"]),
+                                           stoplines_path=os.path.join(OUT, f"{name}_stoplines.json"),
+                                           left_handed=bool(meta["left_handed_coordinates"]))
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), verts=m.verts, faces=m.faces, vert_category=m.vert_category.astype(np.uint8),
+                            categories=np.array(m.categories), stoplines=m.stoplines, stopline_types=np.array(m.stopline_types),
+                            left_handed=np.array(m.left_handed))
+        print(name, "from osm:", m.verts.shape, m.faces.shape, m.categories, m.stoplines.shape)
+
+
 if __name__ == "__main__":
     for n in sys.argv[1:] or ["carla_Town01", "carla_Town02"]:
         convert(n)
+    if not sys.argv[1:]:
+        convert_osm("carla_Town02", with_npz=False)       # pins the OSM path against the shipped Town02 mesh
+        convert_osm("carla_Town10HD", with_npz=True)      # a map that ships without a mesh

@@ -19,7 +19,7 @@ def test_golden_offroad():
         np.testing.assert_allclose(out, g[key], rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("mapname", ["carla_Town01", "carla_Town02"])
+@pytest.mark.parametrize("mapname", ["carla_Town01", "carla_Town02", "carla_Town10HD"])
 def test_vs_oracle_random(mapname):
     from oracle import offroad as OF
     import torchdrivesim_b200 as tds

@@ -71,6 +71,8 @@ def test_golden_reference_images():
     ("carla_Town02", 48, 35.0, 2, 0.2, True),        # tile sizes that are not a multiple of 32
     ("carla_Town01", 100, 40.0, 3, 0.0, False),
     ("carla_Town02", 320, 70.0, 0, 0.1, True),
+    ("carla_Town10HD", 64, 35.0, 3, 0.1, True),      # a map built from its lanelet2 OSM file (joint lane markings)
+    ("carla_Town10HD", 128, 60.0, 0, 0.0, True),
 ])
 def test_vs_oracle_random_scenes(mapname, res, fov, ped_every, absent_p, lights):
     rng = np.random.default_rng(res * 7 + int(fov))

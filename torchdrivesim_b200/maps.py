@@ -57,14 +57,7 @@ class StaticMap:
         verts = np.asarray(d["verts"], np.float32)[0][:, :2]
         faces = np.asarray(d["faces"], np.int32)[0]
         vcat = np.asarray(d["vert_category"])[0]
-        lines, types = None, None
-        if stoplines_path is not None:
-            with open(stoplines_path) as f:
-                sl = json.load(f)
-            norm = {"traffic-light": "traffic_light", "stop-sign": "stop_sign", "yield-sign": "yield_sign",
-                    "yield": "yield_sign"}
-            types = [norm.get(s["agent_type"], s["agent_type"]) for s in sl]
-            lines = np.array([[s["x"], s["y"], s["length"], s["width"], s["orientation"]] for s in sl], np.float32)
+        lines, types = cls._read_stoplines(stoplines_path)
         return cls(verts, faces, d["categories"], vcat, name=os.path.basename(path), left_handed=left_handed,
                    stoplines=lines, stopline_types=types, **kw)
 
@@ -76,6 +69,29 @@ class StaticMap:
         faces = mesh.faces[batch_index].detach().cpu().numpy()
         vcat = mesh.vert_category[batch_index].detach().cpu().numpy()
         return cls(verts, faces, list(mesh.categories), vcat, **kw)
+
+    @classmethod
+    def from_lanelet_osm(cls, path: str, origin=(0.0, 0.0), stoplines_path: Optional[str] = None, left_handed: bool = False,
+                         **kw) -> "StaticMap":
+        """Builds the road + lane-marking mesh of a lanelet2 OSM map (plain or .gz) without the lanelet2 package, as
+        `MapConfig.road_mesh` does for the maps that ship without a mesh (map.py:61-74; see osm.py).  `left_handed` is
+        the coordinate convention recorded with the map; the markings are derived with left_handed=False, as there."""
+        from . import osm
+        verts, faces, cats, vcat = osm.birdview_mesh_arrays(osm.LaneletOsm.load(path, origin))
+        lines, types = cls._read_stoplines(stoplines_path)
+        name = os.path.basename(path).replace(".gz", "").replace(".osm", "")
+        return cls(verts, faces, cats, vcat, name=name, left_handed=left_handed, stoplines=lines, stopline_types=types, **kw)
+
+    @staticmethod
+    def _read_stoplines(stoplines_path: Optional[str]):
+        if stoplines_path is None:
+            return None, None
+        with open(stoplines_path) as f:
+            sl = json.load(f)
+        norm = {"traffic-light": "traffic_light", "stop-sign": "stop_sign", "yield-sign": "yield_sign", "yield": "yield_sign"}
+        types = [norm.get(s["agent_type"], s["agent_type"]) for s in sl]
+        lines = np.array([[s["x"], s["y"], s["length"], s["width"], s["orientation"]] for s in sl], np.float32)
+        return lines, types
 
     @classmethod
     def from_mesh_pickle(cls, path: str, batch_index: int = 0, **kw) -> "StaticMap":
