@@ -362,6 +362,29 @@ def golden_mesh_formats():
     print("mesh formats:", tuple(small.verts.shape), tuple(small.faces.shape), small.categories)
 
 
+def golden_light_schedule():
+    """TrafficLightController (traffic_lights.py:159-301) of carla_Town02 ticked 400 times by 0.1 s from a fixed
+    state: group states, remaining times and the state index of every traffic light of the map after every tick."""
+    import json
+    import shutil
+    from torchdrivesim.traffic_lights import current_light_state_tensor_from_controller
+    cfgm = find_map_config("carla_Town02")
+    ctrl = cfgm.traffic_light_controller
+    ids = [s.actor_id for s in cfgm.stoplines if s.agent_type == "traffic_light"]
+    start = [(i % len(f.states), 0.37 * (i + 1)) for i, f in enumerate(ctrl.traffic_fsms)]
+    ctrl.set_to(start)
+    machine, remaining, lights = [], [], []
+    for t in range(400):
+        machine.append(list(ctrl.state_per_machine)); remaining.append(list(ctrl.time_remaining))
+        lights.append(current_light_state_tensor_from_controller(ctrl, ids).numpy())
+        ctrl.tick(0.1)
+    shutil.copy(cfgm.traffic_light_controller_path, os.path.join(HERE, "maps", "carla_Town02_traffic_light_controller.json"))
+    os.chmod(os.path.join(HERE, "maps", "carla_Town02_traffic_light_controller.json"), 0o644)
+    np.savez_compressed(os.path.join(HERE, "light_schedule.npz"), ids=np.array(ids), start=np.array(start), machine=np.array(machine),
+                        remaining=np.array(remaining), lights=np.stack(lights))
+    print("light schedule:", len(ids), "lights,", len(ctrl.traffic_fsms), "groups, states seen", np.unique(np.stack(lights)).tolist())
+
+
 def golden_traffic():
     """TrafficLightControl.compute_violation / Simulator.compute_traffic_lights_violations (traffic_controls.py:152-178,
     simulator.py:1046-1062): agents placed on and around the stop lines of Town01, random light states."""
@@ -389,6 +412,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals", "noise", "mesh_formats"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals", "noise", "mesh_formats", "light_schedule"]
     for w in which:
         globals()["golden_" + w]()

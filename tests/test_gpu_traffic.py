@@ -83,3 +83,46 @@ def test_simulator_method_and_edge_cases():
     with pytest.raises(tds._lib.TdsError):
         tds.ops.traffic_light_violation(torch.zeros(2, 3, 4, device=dev), torch.zeros(2, 1, 4, 2, device=dev),
                                         torch.zeros(2, 1, dtype=torch.long, device=dev), 0)
+
+
+def test_unrolled_schedule_steps_the_lights_on_the_device():
+    """TrafficLightController.unroll -> replay_states: Simulator.step advances the lights by a device-side gather and
+    the red-light violations follow the schedule (traffic_lights.py + traffic_controls.py:127-136 of the reference)."""
+    import os
+    import torchdrivesim_b200 as tds
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "light_schedule.npz"))
+    ctrl = tds.TrafficLightController.from_json(os.path.join(os.path.dirname(__file__), "golden", "maps",
+                                                             "carla_Town02_traffic_light_controller.json"))
+    ctrl.set_to([(int(s), float(r)) for s, r in g["start"]])
+    steps = 60
+    replay = ctrl.unroll(g["ids"].tolist(), 0.1, steps)
+    town = tds.StaticMap.from_npz(util.map_path("carla_Town02"))
+    B = 2
+    pos = torch.tensor(town.traffic_light_poses(), device=dev)[None].expand(B, -1, -1).contiguous()
+    L = pos.shape[1]
+    assert L == replay.shape[0]
+    tl = tds.TrafficLightControl(pos, replay_states=replay[None].expand(B, -1, -1).contiguous().to(dev))
+    # one stationary agent per stop line, its rear 10 % on the line (the part compute_violation tests)
+    ahead = 0.45 * util.VEH[0] * torch.cat([torch.cos(pos[..., 4:5]), torch.sin(pos[..., 4:5])], -1)
+    state = torch.cat([pos[..., :2] + ahead, pos[..., 4:5], torch.zeros(B, L, 1, device=dev)], -1)
+    km = tds.KinematicBicycle(left_handed=True)
+    km.set_params(lr=torch.full((B, L), util.VEH[2], device=dev))
+    km.set_state(state)
+    size = torch.tensor(util.VEH[:2], device=dev).expand(B, L, 2).contiguous()
+    sim = tds.Simulator(town, km, size, torch.ones(B, L, dtype=torch.bool, device=dev),
+                        tds.TorchDriveConfig(left_handed_coordinates=True), traffic_controls={"traffic_light": tl})
+    red = tl.allowed_states.index("red")
+    from oracle import traffic
+    box = torch.cat([state[:1, :, :2], size[:1], state[:1, :, 2:3]], -1).cpu().numpy()
+    corners = tl.corners[:1].cpu().numpy()
+    seen = set()
+    for t in range(1, steps):
+        sim.step(torch.zeros(B, L, 2, device=dev))
+        assert np.array_equal(tl.state[0].cpu().numpy(), g["lights"][t]), t
+        viol = sim.compute_traffic_lights_violations()[0].cpu().numpy()
+        assert np.array_equal(viol, traffic.tl_violation(box, corners, g["lights"][t][None], red, 0.1)[0]), t
+        on_red = g["lights"][t] == red
+        assert viol[on_red].all()                 # the agent whose rear is on a red light's stop line violates it
+        seen.update(np.unique(g["lights"][t]).tolist())
+    assert seen == {0, 1, 2}

@@ -177,3 +177,31 @@ def test_reference_mesh_wire_formats():
             tds.StaticMap.from_mesh_pickle(f.name)
     finally:
         os.unlink(f.name)
+
+
+def test_traffic_light_schedule_matches_reference():
+    """The light schedule of carla_Town02 (TrafficLightController, traffic_lights.py:159-301) ticked 400 x 0.1 s from
+    a fixed state equals the reference tick for tick, and `unroll` produces the same states as a replay tensor."""
+    import json
+    import os
+    import torchdrivesim_b200 as tds
+    d = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(d, "light_schedule.npz"))
+    path = os.path.join(d, "maps", "carla_Town02_traffic_light_controller.json")
+    ctrl = tds.TrafficLightController.from_json(path)
+    assert ctrl.get_number_of_light_groups() == g["machine"].shape[1]
+    start = [(int(s), float(r)) for s, r in g["start"]]
+    ctrl.set_to(start)
+    ids = g["ids"].tolist()
+    for t in range(g["lights"].shape[0]):
+        assert ctrl.state_per_machine == g["machine"][t].tolist(), t
+        assert ctrl.time_remaining == g["remaining"][t].tolist(), t           # the same float arithmetic
+        assert ctrl.current_state_tensor(ids).tolist() == g["lights"][t].tolist(), t
+        ctrl.tick(0.1)
+    ctrl.set_to(start)
+    replay = ctrl.unroll(ids, 0.1, g["lights"].shape[0])
+    assert replay.dtype == torch.int64 and np.array_equal(replay.numpy(), g["lights"].T)
+    assert len(np.unique(replay.numpy())) == 3                                 # red, yellow and green all occur
+    # the stop lines of the map name the same lights as the schedule
+    stop = json.load(open(os.path.join(d, "maps", "carla_Town02_stoplines.json")))
+    assert [s["actor_id"] for s in stop if s["agent_type"] == "traffic_light"] == ids
