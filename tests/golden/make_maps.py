@@ -65,5 +65,6 @@ if __name__ == "__main__":
     for n in sys.argv[1:] or ["carla_Town01", "carla_Town02"]:
         convert(n)
     if not sys.argv[1:]:
-        convert_osm("carla_Town02", with_npz=False)       # pins the OSM path against the shipped Town02 mesh
+        convert_osm("carla_Town01", with_npz=False)       # pin the OSM path against the shipped meshes
+        convert_osm("carla_Town02", with_npz=False)
         convert_osm("carla_Town10HD", with_npz=True)      # a map that ships without a mesh
