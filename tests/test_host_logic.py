@@ -205,3 +205,21 @@ def test_traffic_light_schedule_matches_reference():
     # the stop lines of the map name the same lights as the schedule
     stop = json.load(open(os.path.join(d, "maps", "carla_Town02_stoplines.json")))
     assert [s["actor_id"] for s in stop if s["agent_type"] == "traffic_light"] == ids
+
+
+def test_compound_npc_controller_gathers_by_assignment():
+    """CompoundNPCController (simulator.py:206-250): NPC tensors are taken from the controller each NPC is assigned to
+    and handed back to all controllers (host-side plumbing; the per-step advance is the CUDA path of test_gpu_npc)."""
+    B, Np = 2, 5
+    mk = lambda v: tds.NPCController(torch.full((B, Np, 2), float(v)), torch.full((B, Np, 4), float(v)),
+                                     torch.full((B, Np), bool(v % 2)), torch.full((B, Np), v, dtype=torch.long))
+    a, b = mk(1), mk(2)
+    idx = torch.tensor([[0, 1, 0, 1, 1], [1, 1, 0, 0, 0]])
+    c = tds.CompoundNPCController([a, b], idx)
+    want = (idx + 1).float()
+    assert torch.equal(c.get_npc_state()[..., 0], want) and torch.equal(c.get_npc_size()[..., 1], want)
+    assert torch.equal(c.get_npc_present_mask(), idx == 0) and torch.equal(c.get_npc_types(), idx + 1)
+    assert a.npc_state is c.npc_state and b.npc_present_mask is c.npc_present_mask
+    one = c.select_batch_elements(torch.tensor([1]), in_place=False).extend(3)
+    assert one.npc_state.shape == (3, Np, 4) and one.controller_indices.shape == (3, Np) and c.npc_state.shape == (B, Np, 4)
+    assert torch.equal(one.get_npc_state()[0, :, 0], want[1])

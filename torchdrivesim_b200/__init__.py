@@ -14,7 +14,7 @@ from .rendering import (B200Renderer, B200RendererConfig, BirdviewRenderer, Rend
 from .infractions import (collision_allpairs, collision_detection_with_discs, iou_differentiable,  # noqa: F401
                           offroad_infraction_loss)
 from .goals import WaypointGoal  # noqa: F401
-from .npc import NPCController, ReplayController, SpawnController  # noqa: F401
+from .npc import CompoundNPCController, NPCController, ReplayController, SpawnController  # noqa: F401
 from .observation_noise import (ObservationNoise, ObservationNoiseConfig, StandardSensingObservationNoise,  # noqa: F401
                                 StandardSensingObservationNoiseConfig)
 from .simulator import CollisionMetric, Simulator, TorchDriveConfig  # noqa: F401

@@ -122,6 +122,65 @@ class NPCController:
         return self
 
 
+class CompoundNPCController(NPCController):
+    """Several controllers, each responsible for the NPCs that `controller_indices` [B,Np] assigns to it
+    (simulator.py:206-250): after every advance the NPC tensors are gathered from the controllers by assignment and
+    handed back to all of them."""
+
+    def __init__(self, controllers: List[NPCController], controller_indices: Tensor):
+        batch_size, num_agents = controller_indices.shape
+        dev = controller_indices.device
+        super().__init__(torch.zeros((batch_size, num_agents, 2), device=dev), torch.zeros((batch_size, num_agents, 4), device=dev),
+                         torch.zeros((batch_size, num_agents), device=dev, dtype=torch.bool),
+                         torch.zeros((batch_size, num_agents), device=dev, dtype=torch.long), controllers[0].agent_type_names)
+        self.controllers = controllers
+        self.controller_indices = controller_indices
+        self.gather_npc_states()
+
+    def gather_npc_states(self) -> None:
+        for i, controller in enumerate(self.controllers):
+            mask = self.controller_indices == i
+            self.npc_size = controller.npc_size.where(mask.unsqueeze(-1), self.npc_size)
+            self.npc_state = controller.npc_state.where(mask.unsqueeze(-1), self.npc_state)
+            self.npc_present_mask = controller.npc_present_mask.where(mask, self.npc_present_mask)
+            self.npc_types = controller.npc_types.where(mask, self.npc_types)
+        for controller in self.controllers:          # every controller sees all NPCs
+            controller.npc_size, controller.npc_state = self.npc_size, self.npc_state
+            controller.npc_present_mask, controller.npc_types = self.npc_present_mask, self.npc_types
+
+    def advance_npcs(self, simulator) -> None:
+        for controller in self.controllers:
+            controller.advance_npcs(simulator)
+        self.gather_npc_states()
+
+    def to(self, device):
+        super().to(device)
+        self.controller_indices = self.controller_indices.to(device)
+        self.controllers = [c.to(device) for c in self.controllers]
+        return self
+
+    def copy(self):
+        return self.__class__([c.copy() for c in self.controllers], self.controller_indices.clone())
+
+    def extend(self, n: int, in_place: bool = True):
+        if not in_place:
+            return self.copy().extend(n, in_place=True)
+        super().extend(n, in_place=True)
+        self.controller_indices = _grow(self.controller_indices, n)
+        for c in self.controllers:
+            c.extend(n, in_place=True)
+        return self
+
+    def select_batch_elements(self, idx: Tensor, in_place: bool = True):
+        if not in_place:
+            return self.copy().select_batch_elements(idx, in_place=True)
+        super().select_batch_elements(idx, in_place=True)
+        self.controller_indices = self.controller_indices[idx]
+        for c in self.controllers:
+            c.select_batch_elements(idx, in_place=True)
+        return self
+
+
 class ReplayController(NPCController):
     """NPCs that replay a log: npc_states BxNpxTx4, npc_present_masks BxNpxT; the log wraps around at its end
     (behavior/replay.py:46-107)."""
