@@ -51,3 +51,16 @@ extern "C" int tds_host_draw_triangle_inside(uint8_t* img, int W, int H, const i
     });
     return 1;
 }
+
+// stateless row rule (tds_raster_rows_at.h): rows evaluated from the set-up alone, here bottom-up and every row twice
+#include "tds_raster_rows_at.h"
+extern "C" void tds_host_draw_triangle_rows_at(uint8_t* img, int W, int H, const int32_t* p) {
+    tds::RowTri t;
+    tds::row_tri_setup(W, H, p[0], p[1], p[2], p[3], p[4], p[5], t, [](int dy) { return tds::row_rcp(dy); });
+    for (int pass = 0; pass < 2; pass++)
+        for (int y = t.yhi; y >= t.ylo; y--)
+            tds::row_tri_at(t, W, y, [&](int lo, int hi) {
+                if (lo < 0 || hi >= W || lo > hi) { img[0] = 99; return; }
+                for (int x = lo; x <= hi; x++) img[y * W + x] = 1;
+            });
+}

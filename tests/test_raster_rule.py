@@ -88,6 +88,19 @@ def test_kernel_rule_row_runs_match_cv2(host_rule, res):
         assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
 
 
+@pytest.mark.parametrize("res", [8, 64, 256, 448])
+def test_stateless_row_rule_matches_cv2(host_rule, res):
+    """tds_raster_rows_at.h: the intervals of a row from the set-up alone, rows taken bottom-up and twice (the building
+    block for spreading the rows of a batch of faces over the lanes of a warp; not used by the kernels yet)."""
+    rng = np.random.default_rng(res + 11)
+    for pts in _triangles(rng, res, 6000, max_abs=8000):
+        m = np.zeros((res, res), np.uint8)
+        host_rule.tds_host_draw_triangle_rows_at(m.ctypes.data_as(ctypes.c_void_p), res, res,
+                                                 pts.ctypes.data_as(ctypes.c_void_p))
+        assert m.max() <= 1, pts.tolist()
+        assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
+
+
 @pytest.mark.parametrize("res,small", [(8, 1), (64, 1), (128, 1), (64, 0), (256, 0), (448, 0)])
 def test_kernel_rule_inside_fast_path_matches_cv2(host_rule, res, small):
     """Triangles with all vertices inside the image: one interval per row (tds_raster_rows.h, FastTri)."""
