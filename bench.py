@@ -108,6 +108,56 @@ def cpu_port_throughput(sample_envs, repeats=1, seed=1):
     return sample_envs * AGENTS / min(times), procs, times
 
 
+def reference_python_throughput(steps=5, warmup=1, agents=20):
+    """The UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.sh) through its own Simulator API on
+    BASELINE config 1: one environment, 20 vehicles, bicycle model, 64x64 birdviews with the cv2 renderer,
+    step -> render_egocentric -> compute_collision (discs) -> compute_offroad, on the host cores torch uses.
+    A bounded sample: `steps` timed steps of the 100 the config names.  None when the install is not there."""
+    try:
+        from oracle.ref_harness import import_reference, reference_available
+        if not reference_available():
+            return None
+        import torch
+        import_reference()
+        from torchdrivesim.simulator import Simulator, TorchDriveConfig
+        from torchdrivesim.rendering import CV2RendererConfig
+        from torchdrivesim.kinematic import KinematicBicycle
+        from torchdrivesim.map import find_map_config
+        from torchdrivesim.utils import Resolution
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+    B, A = 1, agents
+    state, size, lr, actions = synth_inputs(B, A, 1, warmup + steps)
+    cfgm = find_map_config(MAP)
+    km = KinematicBicycle(left_handed=True)
+    km.set_params(lr=torch.tensor(lr))
+    km.set_state(torch.tensor(state))
+    cfg = TorchDriveConfig(left_handed_coordinates=True, renderer=CV2RendererConfig(left_handed_coordinates=True))
+    sim = Simulator(cfg=cfg, road_mesh=cfgm.road_mesh.expand(B), kinematic_model=km, agent_size=torch.tensor(size),
+                    initial_present_mask=torch.ones(B, A, dtype=torch.bool))
+    res = Resolution(RES, RES)
+    parts = {"step": 0.0, "render": 0.0, "collision": 0.0, "offroad": 0.0}
+    t_all = 0.0
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        sim.step(torch.tensor(actions[i]))
+        t1 = time.perf_counter()
+        sim.render_egocentric(res=res, fov=FOV)
+        t2 = time.perf_counter()
+        sim.compute_collision()
+        t3 = time.perf_counter()
+        sim.compute_offroad()
+        t4 = time.perf_counter()
+        if i >= warmup:
+            t_all += t4 - t0
+            for k, d in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                parts[k] += d
+    return {"value": B * A * steps / t_all, "unit": "agent-env-steps/s", "cores": int(torch.get_num_threads()), "kind": "reference",
+            "sample": f"config 1: {MAP}, 1 environment x {A} vehicles, bicycle, {RES}x{RES} cv2 renderer, discs collisions + offroad; "
+                      f"{steps} timed steps of 100 through the unmodified reference Simulator (baseline/_ref)",
+            "seconds_per_step": t_all / steps, "seconds_per_step_by_part": {k: v / steps for k, v in parts.items()}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,7 +184,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "agent-env-steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "agent-env-steps/s", "cores": procs, "kind": "port", "sample": sample,
+                         "reference_python": reference_python_throughput()},
         "e2e": {"value": value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -302,15 +353,17 @@ def run_ours(args):
     # images out to pinned host memory every step
     h_act = torch.tensor(actions).pin_memory()
     h_img = torch.empty(B, A, 3, RES, RES, dtype=torch.float32).pin_memory()
+    h_img_u8 = torch.empty(B, A, 3, RES, RES, dtype=torch.uint8).pin_memory()
+    h_img_rank = torch.empty(B, A, RES, RES, dtype=torch.uint8).pin_memory()
     h_state = torch.empty(B, A, 4).pin_memory()
     h_coll = torch.empty(B, A).pin_memory()
     h_off = torch.empty(B, A).pin_memory()
 
     def e2e_step(i, to_host_images):
-        if to_host_images:
+        if to_host_images is not False:
             a = h_act[i].to(dev, non_blocking=True)
             sim.step(a)
-            sim.render_egocentric_to_host(h_img, chunk_envs=128)
+            sim.render_egocentric_to_host(to_host_images, chunk_envs=128)
             h_coll.copy_(sim.compute_collision(), non_blocking=True)
             h_off.copy_(sim.compute_offroad(), non_blocking=True)
             h_state.copy_(sim.get_state(), non_blocking=True)
@@ -320,9 +373,11 @@ def run_ours(args):
             h_off.copy_(off, non_blocking=True)
             h_state.copy_(runner.state, non_blocking=True)
 
-    e2e = {"host_images": float("nan"), "device_images": float("nan")}
-    for name, to_host in (() if args.kernels_only else (("host_images", True), ("device_images", False))):
-        if to_host:
+    e2e = {"host_images": float("nan"), "device_images": float("nan"), "host_images_uint8": float("nan"),
+           "host_images_rank": float("nan")}
+    legs = (("host_images", h_img), ("host_images_uint8", h_img_u8), ("host_images_rank", h_img_rank), ("device_images", False))
+    for name, to_host in (() if args.kernels_only else legs):
+        if to_host is not False:
             sim.set_state(state0.clone())
         else:
             runner.set_state(state0)
@@ -341,6 +396,46 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e[name] = world * B * A * K / (float(tt.item()) * 1e-3)
     small_out = (h_state.numel() + h_coll.numel() + h_off.numel()) * 4
+
+    # ---- the ceiling of the e2e legs: a bare device -> pinned host copy of one step's float32 images, all ranks at
+    # once (PCIe per GPU; the host's root complexes and memory when 8 GPUs copy together)
+    pcie = None
+    if not args.kernels_only:
+        for _ in range(2):
+            h_img.copy_(images, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            h_img.copy_(images, non_blocking=True)
+        c1.record()
+        barrier()
+        tc = torch.tensor([c0.elapsed_time(c1) / 3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        pcie_ms = float(tc.item())
+        pcie = {"d2h_gbs_per_gpu": h_img.numel() * 4 / pcie_ms / 1e6, "d2h_gbs_aggregate": world * h_img.numel() * 4 / pcie_ms / 1e6,
+                "ms_per_step_of_images": pcie_ms,
+                "e2e_ceiling": world * B * A / (pcie_ms * 1e-3),
+                "note": "bare pinned D2H copy of one step's float32 images (3.2 GB per GPU), all ranks concurrently, max over ranks; "
+                        "e2e_ceiling = agent-env-steps/s if a step cost nothing but that copy"}
+
+    # ---- BASELINE configs 3-5 at the shard one GPU of the 8-GPU job holds (rank 0 only, after the headline loop)
+    configs = None
+    if rank == 0 and not args.kernels_only and not os.environ.get("TDS_BENCH_NO_CONFIGS"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_configs", os.path.join(ROOT, "profiles", "bench_configs.py"))
+        bc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bc)
+        del images, h_img, h_img_u8, h_img_rank
+        runner = None
+        torch.cuda.empty_cache()
+        try:
+            configs = bc.run(("3", "4", "5"), dev)
+        except Exception as e:      # noqa: BLE001
+            configs = {"error": repr(e)[:300]}
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -365,8 +460,15 @@ def run_ours(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e["host_images"], "unit": "agent-env-steps/s", "h2d_bytes_per_step": int(h_act[0].numel() * 4),
-                    "d2h_bytes_per_step": int(h_img.numel() * 4 + small_out),
+                    "d2h_bytes_per_step": int(B * A * 3 * RES * RES * 4 + small_out),
                     "note": "public API, pinned host buffers; images delivered to host every step (PCIe-bound)"},
+            "e2e_uint8": {"value": e2e["host_images_uint8"], "unit": "agent-env-steps/s", "h2d_bytes_per_step": int(h_act[0].numel() * 4),
+                          "d2h_bytes_per_step": int(B * A * 3 * RES * RES + small_out),
+                          "note": "same, images delivered as uint8 RGB (the pixel values are integers in [0,255]: identical after a cast)"},
+            "e2e_rank": {"value": e2e["host_images_rank"], "unit": "agent-env-steps/s", "h2d_bytes_per_step": int(h_act[0].numel() * 4),
+                         "d2h_bytes_per_step": int(B * A * RES * RES + small_out),
+                         "note": "same, images delivered as one byte per pixel (draw rank; colour table from tds_raster_rank_table)"},
+            "pcie": pcie, "configs": configs,
             "e2e_device_images": {"value": e2e["device_images"], "unit": "agent-env-steps/s",
                                   "h2d_bytes_per_step": int(h_act[0].numel() * 4), "d2h_bytes_per_step": int(small_out),
                                   "note": "same, images stay in HBM for a GPU consumer (the reference API returns device tensors)"},
@@ -377,7 +479,8 @@ def run_ours(args):
                          "step_frac_of_hbm_roofline": value / world * BYTES_PER_AGENT_STEP / 1e9 / peak},
             "cpu_baseline": {"value": cpu_val, "unit": "agent-env-steps/s", "cores": cpu_procs, "kind": "port",
                              "sample": f"{max(8, min(os.cpu_count() or 1, 128))} environments x {AGENTS} agents, one step, "
-                                       f"oracle (C + numpy port of the reference path), one process per core"},
+                                       f"oracle (C + numpy port of the reference path), one process per core",
+                             "reference_python": None if args.kernels_only else reference_python_throughput()},
             "infraction_metrics": {"collision_sum": float(metrics[0]), "offroad_sum": float(metrics[1]),
                                    "colliding_agent_steps": float(metrics[2]), "offroad_agent_steps": float(metrics[3])},
         }

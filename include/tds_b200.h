@@ -160,6 +160,28 @@ int tds_infraction_metrics(const float* d_collision, const float* d_offroad, con
                            double* d_acc, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Glue of the per-step path and of differentiable rollouts: what the reference does with eager torch ops between its
+ * hot functions, as single launches.
+ * tds_agent_boxes:  d_state [n,4] (x, y, psi, v), d_size [n,2] (length, width) -> d_box [n,5] (x, y, length, width, psi),
+ *                   the box layout of compute_collision (simulator.py:1161-1170); d_cam_sc [n,2] = (sin psi, cos psi),
+ *                   the egocentric camera orientation of render_egocentric (simulator.py:961, 1017).  Either output
+ *                   may be NULL.
+ * tds_rollout_loss: d_acc[0..2] (float64, accumulated) += sum of d_collision [n], sum of d_offroad [n],
+ *                   sum over agents of |xy - target|^2 (d_state [n,4], d_target_xy [n,2]); any input may be NULL.
+ *                   One launch, fixed reduction order.
+ * tds_rollout_grad: d loss / d state of one step of a rollout whose loss is  w_c sum collision + w_o sum offroad +
+ *                   (w_t / 2) sum |xy - target|^2 :   d_grad_state [n,4] = d_grad_next (gradient arriving from the next
+ *                   kinematic step, NULL: 0) + w_o d_grad_offroad (tds_offroad_bwd, [n,4]) + w_c (d_grad_box_ego +
+ *                   d_grad_box_all)[x, y, psi] (tds_collision_allpairs_bwd, [n,5] each) + w_t (xy - target).
+ * ---------------------------------------------------------------------------------------- */
+int tds_agent_boxes(const float* d_state, const float* d_size, int64_t n, float* d_box, float* d_cam_sc, void* stream);
+int tds_rollout_loss(const float* d_collision, const float* d_offroad, const float* d_state, const float* d_target_xy,
+                     int64_t n, double* d_acc, void* stream);
+int tds_rollout_grad(const float* d_grad_next, const float* d_grad_offroad, const float* d_grad_box_ego,
+                     const float* d_grad_box_all, const float* d_state, const float* d_target_xy, float w_offroad,
+                     float w_collision, float w_target, int64_t n, float* d_grad_state, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Non-visual observations.  Replaces Simulator.get_all_agents_relative (simulator.py:748-781) with
  * utils.relative (utils.py:71-79): for every origin agent i < A and every agent j < N of the same environment
  *   out = ( R(-psi_i) (xy_j - xy_i),  normalize_angle(psi_j - psi_i),  length_j, width_j, present_j ).
@@ -206,6 +228,8 @@ typedef struct {
     float raster_cell, offroad_cell;
     float min_x, min_y, max_x, max_y;
     int64_t device_bytes;
+    int32_t raster_strips;   /* six-vertex strip records (four faces each), counted once per cell they are binned in */
+    int32_t reserved;
 } tds_map_info_t;
 int tds_map_info(const tds_map_t* map, tds_map_info_t* out);
 
@@ -265,6 +289,34 @@ int tds_raster_birdview(const tds_map_t* const* maps, int32_t n_maps, const int3
                         const float* d_cam_tris, const int32_t* d_cam_tri_class, int32_t Tc,
                         const tds_palette_t* palette, float scale, int32_t res,
                         float* d_out, void* d_workspace, void* stream);
+
+/* Same raster with per-camera agent colours and a choice of the image format.
+ * d_agent_class [B,Nc,N] uint8 or NULL: palette class of the RECTANGLE of agent n as camera c sees it, instead of the
+ * class of its type - generate(custom_agent_colors=...), mesh.py:1092-1099 (the host layer gives every distinct
+ * colour a palette class with the draw rank of the agent's type; the direction triangle keeps its class).
+ * Image formats (the pixel values are integers in [0,255] in the reference too,
+ * rendering/cv2.py:50-67, so the narrow formats lose nothing; they exist for consumers behind PCIe):
+ *   TDS_IMAGE_F32  d_out float32 [B,Nc,3,res,res]  - the reference's dtype and layout (tds_raster_birdview)
+ *   TDS_IMAGE_U8   d_out uint8   [B,Nc,3,res,res]  - the same values as bytes (4x fewer bytes)
+ *   TDS_IMAGE_RANK d_out uint8   [B,Nc,res,res]    - per pixel the draw rank of the top-most class, 0 = background,
+ *                  k >= 1 = the k-th entry of tds_raster_rank_table (12x fewer bytes) */
+#define TDS_IMAGE_F32 0
+#define TDS_IMAGE_U8 1
+#define TDS_IMAGE_RANK 2
+int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_maps, const int32_t* d_env_map,
+                            int32_t B, int32_t Nc, int32_t N,
+                            const float* d_cam_xy, const float* d_cam_sc,
+                            const float* d_agent_state, const float* d_agent_size, const int32_t* d_agent_type,
+                            const uint8_t* d_present, int32_t present_per_camera,
+                            const float* d_tl_corners, const int32_t* d_tl_state, int32_t L,
+                            const float* d_rect_corners, const int32_t* d_rect_class, int32_t R,
+                            const float* d_cam_tris, const int32_t* d_cam_tri_class, int32_t Tc,
+                            const tds_palette_t* palette, float scale, int32_t res,
+                            const uint8_t* d_agent_class, int32_t image_format, void* d_out, void* d_workspace,
+                            void* stream);
+/* Host helper for TDS_IMAGE_RANK: h_rgb[k][0..2] = colour of draw rank k (k = 0: background, black), h_class[k] = palette
+ * class of rank k (-1 for k = 0); returns the number of ranks including the background, <= TDS_MAX_CLASSES + 1. */
+int32_t tds_raster_rank_table(const tds_palette_t* palette, uint8_t h_rgb[][3], int32_t* h_class);
 
 /* Measurement hook: when both are non-NULL cudaEvent_t handles, the next tds_raster_birdview calls on
  * this thread record `start` / `stop` on their stream immediately around the raster kernel launch

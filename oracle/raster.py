@@ -120,7 +120,8 @@ def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_
                 tl_allowed_states: Sequence[str] = ("red", "yellow", "green"),
                 static_controls: Optional[Dict[str, np.ndarray]] = None,
                 levels: Dict[str, float] = None, colors: Dict[str, Tuple[int, int, int]] = None,
-                waypoints: Optional[np.ndarray] = None, waypoints_mask: Optional[np.ndarray] = None) -> Scene:
+                waypoints: Optional[np.ndarray] = None, waypoints_mask: Optional[np.ndarray] = None,
+                agent_colors: Optional[np.ndarray] = None) -> Scene:
     """Restates generate() for one environment and one rendering mask.
 
     static_face_cat: per static face category NAME (the category of its first vertex, cv2.py:58).
@@ -130,6 +131,9 @@ def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_
     waypoints [M,2] (+ mask [M]) are those of ONE camera (mesh.py:1120-1145): a disc per waypoint, translated (the
     pose has psi = 0, so the rotation is the identity); the faces of a masked waypoint collapse onto vertex 0 of the
     camera's waypoint mesh, the centre of its first waypoint.
+    agent_colors [N,3] in [0,1] are the custom colours of ONE camera (mesh.py:1092-1099): they replace the colour of
+    the four rectangle vertices of every agent (the degenerate face of an absent agent is at actor vertex 0, so it
+    takes agent 0's custom colour); the level stays that of the agent's type, the direction triangle keeps its colour.
     """
     levels = DEFAULT_LEVELS if levels is None else levels
     colors = DEFAULT_COLORS if colors is None else colors
@@ -137,6 +141,7 @@ def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_
     verts = [np.asarray(static_verts, f32).reshape(-1, 2)]
     faces = [np.asarray(static_faces, np.int32).reshape(-1, 3)]
     cats = list(static_face_cat)
+    custom_rgb = {}                       # face index -> quantized colour (rendering/cv2.py:50)
     nv = verts[0].shape[0]
     if agent_state is not None and len(agent_state) > 0:
         n = len(agent_state)
@@ -145,13 +150,22 @@ def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_
         present = np.ones(n, bool) if present is None else np.asarray(present, bool)
         av = agent_world_verts(agent_state, agent_size).reshape(n * 7, 2)
         verts.append(av)
+        qcol = None
+        if agent_colors is not None:
+            qcol = np.floor(np.asarray(agent_colors, f32) * f32(1.0 - 1e-3) * f32(256)).clip(0, 255).astype(np.uint8)
         for k in range(n):
             b = nv + 7 * k
             if present[k]:
                 faces.append(np.array([[b + 0, b + 1, b + 3], [b + 1, b + 3, b + 2], [b + 4, b + 5, b + 6]], np.int32))
+                if qcol is not None:
+                    custom_rgb[len(cats)] = qcol[k]
+                    custom_rgb[len(cats) + 1] = qcol[k]
                 cats += [agent_type_names[agent_types[k]]] * 2 + ["direction"]
             else:
                 faces.append(np.full((3, 3), nv, np.int32))
+                if qcol is not None:
+                    for i in range(3):
+                        custom_rgb[len(cats) + i] = qcol[0]
                 cats += [agent_type_names[agent_types[0]]] * 3
         nv += n * 7
     for name, corners in (static_controls or {}).items():
@@ -183,6 +197,8 @@ def build_scene(static_verts: np.ndarray, static_faces: np.ndarray, static_face_
     lut = {c: quantize_color(colors[c]) for c in set(cats)}
     face_rank = np.array([ranks[c] for c in cats], np.uint8)
     face_rgb = np.stack([lut[c] for c in cats]).astype(np.uint8) if cats else np.zeros((0, 3), np.uint8)
+    for i, c in custom_rgb.items():
+        face_rgb[i] = c
     return Scene(verts=np.ascontiguousarray(verts), faces=np.ascontiguousarray(faces),
                  face_rank=face_rank, face_rgb=np.ascontiguousarray(face_rgb))
 

@@ -1,9 +1,10 @@
-"""Import the UNMODIFIED reference (/root/reference) in the build container.
+"""Import the UNMODIFIED reference: /root/reference in the build container, or its offline install under
+baseline/_ref (baseline/install_ref.sh; git-ignored, travels to the GPU box with the repository snapshot).
 
-TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (to generate the
-committed golden vectors) and by the optional `needs_reference` tests.  Nothing
-on the product path, in `-m gpu` tests, smoke() or bench.py may import this:
-/root/reference does not exist on the GPU box.
+TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (to generate the committed golden vectors), by
+the `needs_reference` tests (the drop-in seam behind the real reference Simulator, on the CPU here and on the
+B200 with the real kernels) and by bench.py's reference arm / `cpu_baseline.reference_python` leg.  Nothing on
+the product path imports this.
 
 The three stub modules follow SURVEY.md App. D: omegaconf, shapely.geometry and
 lanelet2.core are absent from the image and are only touched off the hot path.
@@ -12,7 +13,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("TDS_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    for cand in (os.environ.get("TDS_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "torchdrivesim", "resources", "maps")):
+            return cand
+    return os.environ.get("TDS_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

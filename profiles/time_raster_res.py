@@ -24,14 +24,18 @@ out = torch.empty(B, A, 3, RES, RES, device=dev)
 for _ in range(3):
     sim.render_egocentric(out=out, res=res, fov=FOV)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+lib = tds._lib.load()
 n = 5
-e0.record()
-for _ in range(n):
-    sim.render_egocentric(out=out, res=res, fov=FOV)
-e1.record()
+evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+for a, b in evs:
+    a.record(); b.record()
 torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / n
+for a, b in evs:
+    lib.tds_raster_set_timing_events(a.cuda_event, b.cuda_event)
+    sim.render_egocentric(out=out, res=res, fov=FOV)
+lib.tds_raster_set_timing_events(None, None)
+torch.cuda.synchronize()
+ms = sum(a.elapsed_time(b) for a, b in evs) / n
 gb = B * A * 12 * RES * RES / 1e9
-print(f"res {RES} B {B} A {A} fov {FOV}: render {ms:.3f} ms, {gb:.2f} GB out, {gb / ms * 1e3:.0f} GB/s "
+print(f"res {RES} B {B} A {A} fov {FOV}: raster kernel {ms:.3f} ms, {gb:.2f} GB out, {gb / ms * 1e3:.0f} GB/s "
       f"({100 * gb / ms * 1e3 / 6545.3:.1f} % of measured HBM), {B * A / ms * 1e3 / 1e6:.2f} M cameras/s")

@@ -37,6 +37,24 @@ extern "C" void tds_host_draw_triangle_rows(uint8_t* img, int W, int H, const in
         });
 }
 
+// the same rule spread over four cooperating workers - three outline edges + a fourth of the fill rows each (what the
+// kernel runs, one worker per lane, for faces that cross the image border).  The host plays the workers in turn: the
+// fill set-up of worker 3 is computed first and handed to the others through `share`.
+extern "C" void tds_host_draw_triangle_by_parts(uint8_t* img, int W, int H, const int32_t* p) {
+    auto rcp = [](int dy) { return tds::row_rcp(dy); };
+    auto emit = [&](int y, int lo, int hi) {
+        if (lo < 0 || hi >= W || lo > hi || y < 0 || y >= H) { img[0] = 99; return; }      // contract violation: flagged
+        for (int x = lo; x <= hi; x++) img[y * W + x] = 1;
+    };
+    int held[10], n = 0, k = 0;
+    // pass 1: worker 3 records what it shares; pass 2..4: workers 0..2 receive it
+    tds::row_tri_part(W, H, p[0], p[1], p[2], p[3], p[4], p[5], 3, rcp, emit, [&](int v) { held[n++] = v; return v; });
+    for (int part = 2; part >= 0; part--) {
+        k = 0;
+        tds::row_tri_part(W, H, p[0], p[1], p[2], p[3], p[4], p[5], part, rcp, emit, [&](int) { return held[k++]; });
+    }
+}
+
 // fast path of the bitplane kernel: all vertices inside the image, one interval per row.
 // small != 0 uses the reciprocal-table slopes (images up to 128 pixels).
 extern "C" int tds_host_draw_triangle_inside(uint8_t* img, int W, int H, const int32_t* p, int small) {

@@ -199,6 +199,46 @@ def golden_waypoints():
     print("waypoints: image", img.shape, "goal-coloured px", int((img[:, :, 0] == np.floor(goal[0] / 255 * 256)).sum()))
 
 
+def golden_custom_colors():
+    """generate(custom_agent_colors=...) (mesh.py:1092-1099) and add_static_meshes (mesh.py:870-883): every agent is
+    given a colour per camera; a strip of extra static 'map_boundary' triangles is appended to the background."""
+    from torchdrivesim.mesh import BaseMesh, rendering_mesh
+    gen = torch.Generator().manual_seed(808)
+    B, A, res, fov = 2, 6, 64, 35.0
+    types = (torch.arange(A) % 3 == 2).long().expand(B, A).clone()
+    names = ["vehicle", "pedestrian"]
+    present = torch.ones(B, A, dtype=torch.bool)
+    present[0, 0] = False          # absent agent 0: the degenerate face takes ITS custom colour
+    present[1, 4] = False
+    sim, cfgm = make_sim("carla_Town01", B, A, gen, types=types, type_names=names, present=present)
+    st = sim.get_state().clone()
+    # agents side by side, 7 m apart (no overlaps: rectangles of equal level are drawn in an undefined order)
+    offs = torch.stack([7.0 * (torch.arange(A) - A // 2).float(), 3.0 * (torch.arange(A) % 2).float()], -1)
+    st[:, :, :2] = st[:, :1, :2] + offs[None]
+    sim.set_state(st)
+    palette = torch.tensor([[1.0, 0.0, 0.0], [0.2, 0.9, 0.3], [0.5, 0.5, 0.5], [0.9, 0.8, 0.1]])
+    pick = torch.randint(0, 4, (B, A, A), generator=gen)
+    colors = palette[pick]                                                  # [B,Nc,A,3] in [0,1]
+    # a fan of extra static triangles around the first agent
+    c = st[:, 0, :2]
+    ang = torch.linspace(0, 2 * np.pi, 7)[:-1]
+    ring = torch.stack([torch.cos(ang), torch.sin(ang)], -1) * 9.0
+    verts = torch.cat([c[:, None], c[:, None] + ring[None]], 1)             # [B,7,2]
+    faces = torch.tensor([[0, 1, 2], [0, 3, 4], [0, 5, 6]])[None].expand(B, -1, -1)
+    extra = rendering_mesh(BaseMesh(verts=verts, faces=faces), "map_boundary")
+    sim.birdview_mesh_generator.add_static_meshes([extra])
+    img = sim.render_egocentric(res=Resolution(res, res), fov=fov, custom_agent_colors=colors)
+    assert float((img - img.round()).abs().max()) == 0.0
+    tl = sim.traffic_controls["traffic_light"]
+    np.savez_compressed(os.path.join(HERE, "render_custom.npz"), map="carla_Town01", state=st.numpy(),
+                        size=sim.get_agent_size().numpy(), present=present.numpy(), types=types.numpy(),
+                        type_names=np.array(names), tl_state=tl.state.numpy(), tl_corners=tl.corners.numpy(),
+                        colors=colors.numpy(), extra_verts=verts.numpy(), extra_faces=faces.numpy(), res=res, fov=fov,
+                        image=img.numpy().astype(np.uint8))
+    print("custom colours: image", img.shape, "red px", int(((img[:, :, 0] == 255) & (img[:, :, 1] == 0)).sum()),
+          "boundary px", int(((img[:, :, 0] == 255) & (img[:, :, 1] == 255) & (img[:, :, 2] == 0)).sum()))
+
+
 def golden_relative():
     """Non-visual observations (simulator.py:730-781): get_all_agents_absolute / get_all_agents_relative."""
     gen = torch.Generator().manual_seed(707)
@@ -412,6 +452,6 @@ def golden_traffic():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals", "noise", "mesh_formats", "light_schedule"]
+    which = sys.argv[1:] or ["kinematic", "collision", "offroad", "render", "traffic", "waypoints", "relative", "npc", "goals", "noise", "mesh_formats", "light_schedule", "custom_colors"]
     for w in which:
         globals()["golden_" + w]()

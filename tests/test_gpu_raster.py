@@ -225,3 +225,140 @@ def test_goal_waypoints_golden_and_oracle():
     ora = util.oracle_render_batch(m, state, size, types, np.ones((B, A), bool), ["vehicle"], None, None,
                                    state[..., :2].copy(), cam_sc, 128, 60.0, waypoints=wp, waypoints_mask=mask)
     assert sum(int((img[b, c] != o).any(0).sum()) for (b, c), o in ora.items()) == 0
+
+
+def _sim(mapname, state, size, present, types=None, names=None, town=None):
+    import torchdrivesim_b200 as tds
+    dev = torch.device("cuda:0")
+    B, A = state.shape[:2]
+    town = town or tds.StaticMap.from_npz(util.map_path(mapname))
+    km = tds.KinematicBicycle(left_handed=True)
+    km.set_params(lr=torch.full((B, A), util.VEH[2], device=dev))
+    km.set_state(torch.as_tensor(state, device=dev))
+    return tds.Simulator(town, km, torch.as_tensor(size, device=dev), torch.as_tensor(present, device=dev),
+                         tds.TorchDriveConfig(left_handed_coordinates=True),
+                         agent_types=None if types is None else torch.as_tensor(types, device=dev), agent_type_names=names)
+
+
+def test_uint8_and_rank_images_equal_the_float_image():
+    """The lossless narrow formats: uint8 RGB == the float32 image cast, palette[rank image] == the uint8 image, through
+    render_egocentric(dtype=...) and through the chunked pinned-host path, at a warp-per-camera and a CTA-per-camera size."""
+    import torchdrivesim_b200 as tds
+    rng = np.random.default_rng(12)
+    m = util.load_map_np("carla_Town02")
+    for res, fov, B, A in ((64, 35.0, 5, 6), (128, 50.0, 3, 5), (100, 40.0, 2, 4)):
+        state, size, types, present = util.random_scene(m, B, A, rng, ped_every=3, absent_p=0.2)
+        sim = _sim("carla_Town02", state, size, present, types, ["vehicle", "pedestrian"])
+        R = tds.Resolution(res, res)
+        f32 = sim.render_egocentric(res=R, fov=fov)
+        u8 = sim.render_egocentric(res=R, fov=fov, dtype=torch.uint8)
+        rk = sim.render_egocentric(res=R, fov=fov, dtype='rank')
+        assert u8.dtype == torch.uint8 and u8.shape == f32.shape and rk.shape == (B, A, res, res)
+        assert torch.equal(u8, f32.to(torch.uint8)) and float(f32.max()) > 0
+        cam = sim.get_state()
+        scene = sim._scene(cam[..., :2], None, None, None, None)
+        rgb, cls = sim.renderer.rank_table(scene)
+        assert torch.equal(rgb.to(rk.device)[rk.long()].permute(0, 1, 4, 2, 3), u8)
+        assert int(rk.max()) < rgb.shape[0] and int(cls[0]) == -1
+        for dt, shape in ((torch.float32, f32.shape), (torch.uint8, f32.shape), (torch.uint8, rk.shape)):
+            host = torch.empty(shape, dtype=dt).pin_memory()
+            sim.render_egocentric_to_host(host, chunk_envs=2, res=R, fov=fov)
+            torch.cuda.synchronize()
+            want = f32 if dt == torch.float32 else (u8 if len(shape) == 5 else rk)
+            assert torch.equal(host, want.cpu())
+
+
+def test_custom_agent_colours_and_static_meshes_golden():
+    """generate(custom_agent_colors=...) and add_static_meshes against images of the unmodified reference
+    (tests/golden/render_custom.npz), and the same frame without the custom colours against the oracle."""
+    import torchdrivesim_b200 as tds
+    dev = torch.device("cuda:0")
+    g = util.golden("render_custom")
+    st, B, A = g["state"], g["state"].shape[0], g["state"].shape[1]
+    names = [str(s) for s in g["type_names"]]
+    res, fov = int(g["res"]), float(g["fov"])
+    imgs = []
+    for b in range(B):          # the extra static mesh differs per environment: one map (set) per environment
+        sim = _sim(str(g["map"]), st[b:b + 1], g["size"][b:b + 1], g["present"][b:b + 1], g["types"][b:b + 1], names)
+        tl = tds.TrafficLightControl(pos=torch.zeros(1, g["tl_corners"].shape[1], 5, device=dev))
+        tl.corners = torch.as_tensor(g["tl_corners"][b:b + 1], device=dev)
+        tl.set_state(torch.as_tensor(g["tl_state"][b:b + 1], device=dev))
+        sim.traffic_controls = {"traffic_light": tl}
+        sim.birdview_mesh_generator.initialize_traffic_controls_mesh(sim.traffic_controls)
+        m0 = util.load_map_np(str(g["map"]))
+        extra = tds.StaticMap(g["extra_verts"][b], g["extra_faces"][b], ["map_boundary"],
+                              np.zeros(len(g["extra_verts"][b]), np.int64))
+        sim.birdview_mesh_generator.add_static_meshes([extra])
+        img = sim.render_egocentric(res=tds.Resolution(res, res), fov=fov,
+                                    custom_agent_colors=torch.as_tensor(g["colors"][b:b + 1], device=dev))
+        torch.cuda.synchronize()
+        imgs.append(img.cpu().numpy())
+        ref = g["image"][b:b + 1].astype(np.float32)
+        assert int((imgs[-1] != ref).any(2).sum()) == 0, f"environment {b}"
+        assert ((ref[:, :, 0] == 255) & (ref[:, :, 1] == 255) & (ref[:, :, 2] == 0)).sum() > 100     # the extra mesh is there
+    # too many distinct colours for the palette: a clear error, not a wrong image
+    sim = _sim(str(g["map"]), st[:1], g["size"][:1], g["present"][:1], g["types"][:1], names)
+    many = torch.rand(1, A, A, 3, device=dev)
+    with pytest.raises(tds._lib.TdsError):
+        sim.render_egocentric(custom_agent_colors=many)
+
+
+def test_dense_scene_unlisted_dynamic_branch():
+    """BASELINE config 4 density: more than kCullCap = 128 dynamic primitives reach one view quad, so the kernel walks
+    ALL agents instead of its per-camera list (20 % of them absent, which that branch must skip itself); 256x256."""
+    rng = np.random.default_rng(44)
+    m = util.load_map_np("carla_Town01")
+    B, A = 2, 260
+    state, size, types, present = util.random_scene(m, B, A, rng, spread=9.0, ped_every=5, absent_p=0.2)
+    present[:, 0] = [True, False]
+    cams = [(b, c) for b in range(B) for c in range(8)]
+    # cameras on the 8 agents nearest to the middle of the crowd
+    near = np.argsort(np.abs(state[..., :2] - np.median(state[..., :2], axis=1, keepdims=True)).max(-1), axis=1)[:, :8]
+    cam_xy = np.take_along_axis(state[..., :2], near[..., None], 1).copy()
+    cam_sc = _sincos_torch(np.take_along_axis(state[..., 2], near, 1))
+    # how many agents does a camera see?  (35 m view: everything within ~17 m)
+    d = np.abs(state[:, None, :, :2] - cam_xy[:, :, None, :]).max(-1)
+    assert ((d < 15.0) & present[:, None, :]).sum(-1).min() > 130
+    names = ["vehicle", "pedestrian"]
+    for res, fov in ((256, 35.0), (64, 35.0)):
+        img = _gpu_render(["carla_Town01"], None, state, size, types, present, names, None, None, cam_xy, cam_sc, res, fov)
+        ora = util.oracle_render_batch(m, state, size, types, present, names, None, None, cam_xy, cam_sc, res, fov, cams=cams)
+        bad = sum(int((img[b, c] != o).any(0).sum()) for (b, c), o in ora.items())
+        assert bad == 0, f"res {res}: {bad} mismatching pixels over {len(ora)} cameras"
+
+
+def test_extreme_zoom_huge_coordinates():
+    """fov <= 1 m at 448x448 (and 0.25 m at 64x64): road triangles and lane-marking strips project to coordinates
+    beyond +-8000 pixels, the 64-bit rule of draw_huge - on the device, for single faces and for strips."""
+    rng = np.random.default_rng(9)
+    m = util.load_map_np("carla_Town01")
+    B, A = 2, 3
+    state, size, types, present = util.random_scene(m, B, A, rng, spread=1.0)
+    # put cameras right on lane-marking vertices and road vertices
+    lane = m["verts"][m["vert_category"] != m["categories"].index("road")]
+    state[0, :, :2] = lane[rng.integers(0, lane.shape[0], A)] + rng.normal(0, 0.05, (A, 2))
+    cam_xy, cam_sc = state[..., :2].copy(), _sincos_torch(state[..., 2])
+    for res, fov in ((448, 1.0), (64, 0.25), (256, 0.6)):
+        img = _gpu_render(["carla_Town01"], None, state, size, types, present, ["vehicle"], None, None, cam_xy, cam_sc, res, fov)
+        ora = util.oracle_render_batch(m, state, size, types, present, ["vehicle"], None, None, cam_xy, cam_sc, res, fov)
+        bad = sum(int((img[b, c] != o).any(0).sum()) for (b, c), o in ora.items())
+        assert bad == 0, f"res {res} fov {fov}: {bad} mismatching pixels"
+        assert img.max() > 0
+
+
+def test_strip_stage_equals_face_by_face_walk(monkeypatch):
+    """Stage 1S (six-vertex strips, vertices plotted at once) against the same records walked face by face
+    (TDS_RASTER_STRIPS=0): identical images on thousands of cameras at several tile sizes and zooms."""
+    import bench
+    rng = np.random.default_rng(31)
+    for mapname, res, fov, B, A in (("carla_Town01", 64, 35.0, 24, 64), ("carla_Town10HD", 64, 20.0, 8, 32),
+                                    ("carla_Town02", 128, 80.0, 6, 16), ("carla_Town01", 256, 35.0, 2, 16),
+                                    ("carla_Town02", 48, 10.0, 8, 16), ("carla_Town01", 96, 120.0, 4, 16)):
+        m = util.load_map_np(mapname)
+        state, size, types, present = util.random_scene(m, B, A, rng, spread=30.0)
+        cam_xy, cam_sc = state[..., :2].copy(), _sincos_torch(state[..., 2])
+        monkeypatch.setenv("TDS_RASTER_STRIPS", "1")
+        a = _gpu_render([mapname], None, state, size, types, present, ["vehicle"], None, None, cam_xy, cam_sc, res, fov)
+        monkeypatch.setenv("TDS_RASTER_STRIPS", "0")
+        b = _gpu_render([mapname], None, state, size, types, present, ["vehicle"], None, None, cam_xy, cam_sc, res, fov)
+        assert a.max() > 0 and np.array_equal(a, b), f"{mapname} {res} {fov}: {(a != b).any(2).sum()} pixels differ"

@@ -98,12 +98,73 @@ def test_generator_rejects_unsupported_inputs():
     per_cam = st[:, None].repeat(1, 3, 1, 1)                      # materialised per-camera states
     with pytest.raises(tds._lib.TdsError):
         gen.generate(3, agent_state=per_cam, present_mask=None)
-    with pytest.raises(NotImplementedError):
-        gen.generate(1, agent_state=st[:, None], custom_agent_colors=torch.zeros(4, 1, 6, 3))
+    with pytest.raises(tds._lib.TdsError):
+        gen.generate(1, agent_state=st[:, None], custom_agent_colors=torch.zeros(4, 2, 6, 3))   # colours per camera: [B,Nc,N,3]
     with pytest.raises(tds._lib.TdsError):
         gen.generate(1, agent_state=st[:, None], waypoints=torch.zeros(4, 2, 2, 2))          # Nc mismatch
     big = gen.expand(2)
     assert big.agent_size.shape[0] == 8 and big.world_center.shape[0] == 8
+
+
+def test_custom_agent_colours_become_palette_classes():
+    """generate(custom_agent_colors=...) (mesh.py:1092-1099): every distinct (agent type, quantized colour) pair is a
+    class of the scene's palette at the level of the agent's type; too many distinct colours raise."""
+    from torchdrivesim_b200.palette import class_names, class_id
+    sim = _sim(lights=False)
+    gen = sim.birdview_mesh_generator
+    st = sim.get_state()
+    B, N = st.shape[0], st.shape[1]
+    col = torch.zeros(B, 1, N, 3)
+    col[..., 0] = 1.0                    # red everywhere ...
+    col[0, 0, 1] = torch.tensor([0.2, 0.9, 0.3])
+    scene = gen.generate(1, agent_state=st[:, None], custom_agent_colors=col)
+    base = len(class_names())
+    assert scene.agent_class.dtype == torch.uint8 and tuple(scene.agent_class.shape) == (B, 1, N)
+    assert sorted(set(scene.agent_class.flatten().tolist())) == [base, base + 1]
+    assert sorted(c for _, c in scene.custom_classes) == [(51, 230, 76), (255, 0, 0)]
+    pal = scene.palette(sim.renderer.color_map, sim.renderer.rendering_levels)
+    assert pal.n_classes == base + 2 and pal.rank[base] == pal.rank[class_id("vehicle")] and pal.active[base + 1] == 1
+    big = _sim(B=4, A=6, lights=False)          # 24 distinct colours do not fit 32 classes
+    with pytest.raises(tds._lib.TdsError):
+        big.birdview_mesh_generator.generate(1, agent_state=big.get_state()[:, None], custom_agent_colors=torch.rand(4, 1, 6, 3))
+
+
+def test_add_static_meshes_extends_every_map():
+    sim = _sim(lights=False)
+    gen = sim.birdview_mesh_generator
+    nf = gen.mapset.maps[0].faces.shape[0]
+    extra = tds.StaticMap(np.array([[0, 0], [1, 0], [0, 1]], np.float32), np.array([[0, 1, 2]], np.int32), ["map_boundary"],
+                          np.zeros(3, np.int64))
+    gen.add_static_meshes([extra])
+    m = gen.mapset.maps[0]
+    assert m.faces.shape[0] == nf + 1 and m.face_category_names[-1] == "map_boundary" and int(m.faces[-1].min()) == m.verts.shape[0] - 3
+    assert "map_boundary" in gen.mapset.static_categories()
+
+
+def test_mesh_pickle_loader_never_runs_a_nested_pickle(tmp_path):
+    """StaticMap.from_mesh_pickle: a payload that smuggles a forbidden global through the legacy
+    torch.storage._load_from_bytes hook is rejected instead of being unpickled a second time without restrictions."""
+    import io
+    import pickle
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("__import__('os').getpid()",))
+
+    inner = io.BytesIO()
+    pickle.dump(Evil(), inner)          # what torch.load(weights_only=False) would happily execute
+
+    class Smuggle:
+        def __reduce__(self):
+            import torch.storage
+            return (torch.storage._load_from_bytes, (inner.getvalue(),))
+
+    p = tmp_path / "evil.pkl"
+    with open(p, "wb") as f:
+        pickle.dump({"verts": Smuggle()}, f)
+    with pytest.raises(Exception) as e:
+        tds.StaticMap.from_mesh_pickle(str(p))
+    assert "eval" in str(e.value) or "Unsupported" in str(e.value) or "weights" in str(e.value).lower() or "not allowed" in str(e.value)
 
 
 def test_waypoint_triangles_follow_the_reference_layout():

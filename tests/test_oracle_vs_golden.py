@@ -89,6 +89,27 @@ def test_render_waypoints_pixel_exact():
     assert len(ora) == B * A
 
 
+def test_render_custom_colours_and_static_meshes_pixel_exact():
+    """generate(custom_agent_colors=...) (mesh.py:1092-1099) + add_static_meshes (mesh.py:870-883) against the
+    unmodified reference: per-camera agent colours, the degenerate face of an absent agent 0, extra static faces."""
+    g = util.golden("render_custom")
+    m0 = util.load_map_np(str(g["map"]))
+    st = g["state"]
+    B, A = st.shape[:2]
+    cam_sc = torch.stack([torch.sin(torch.tensor(st[..., 2])), torch.cos(torch.tensor(st[..., 2]))], -1).numpy()
+    names = [str(s) for s in g["type_names"]]
+    n = 0
+    for b in range(B):
+        m = util.with_extra_static(m0, g["extra_verts"][b], g["extra_faces"][b], "map_boundary")
+        ora = util.oracle_render_batch(m, st, g["size"], g["types"], g["present"], names, g["tl_corners"], g["tl_state"],
+                                       st[..., :2], cam_sc, int(g["res"]), float(g["fov"]), cams=[(b, c) for c in range(A)],
+                                       agent_colors=g["colors"])
+        for (bb, c), img in ora.items():
+            assert np.array_equal(img, g["image"][bb, c].astype(np.float32)), f"camera {(bb, c)}"
+            n += 1
+    assert n == B * A
+
+
 def test_category_ranks_follow_levels():
     r = R.category_ranks()
     assert r["road"] < r["right_lane"] < r["left_lane"] < r["traffic_light_green"] < r["traffic_light_red"] \

@@ -88,6 +88,19 @@ def test_kernel_rule_row_runs_match_cv2(host_rule, res):
         assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
 
 
+@pytest.mark.parametrize("res", [8, 64, 100, 256, 448])
+def test_kernel_rule_by_parts_matches_cv2(host_rule, res):
+    """row_tri_part (tds_raster_rows.h): the runs of each outline edge and the fill spans as four independent parts -
+    the form the kernel runs, one part per lane, for the faces that cross the image border."""
+    rng = np.random.default_rng(res + 17)
+    for pts in _triangles(rng, res, 8000, max_abs=8000):
+        m = np.zeros((res, res), np.uint8)
+        host_rule.tds_host_draw_triangle_by_parts(m.ctypes.data_as(ctypes.c_void_p), res, res,
+                                                  pts.ctypes.data_as(ctypes.c_void_p))
+        assert m.max() <= 1, pts.tolist()
+        assert np.array_equal(m > 0, _cv2_mask(pts, res)), pts.tolist()
+
+
 @pytest.mark.parametrize("res", [8, 64, 256, 448])
 def test_stateless_row_rule_matches_cv2(host_rule, res):
     """tds_raster_rows_at.h: the intervals of a row from the set-up alone, rows taken bottom-up and twice (the building

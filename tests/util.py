@@ -56,7 +56,7 @@ def tl_tensors(m, B, rng):
 
 
 def oracle_render_batch(m, state, size, types, present, type_names, tl_corners, tl_state, cam_xy, cam_sc, res, fov,
-                        cams=None, waypoints=None, waypoints_mask=None):
+                        cams=None, waypoints=None, waypoints_mask=None, agent_colors=None):
     """Oracle images for the cameras in `cams` (list of (b, c)); present [B,N] or [B,Nc,N]."""
     from oracle import raster as R
     out = {}
@@ -67,7 +67,21 @@ def oracle_render_batch(m, state, size, types, present, type_names, tl_corners, 
                            tl_corners=None if tl_corners is None else tl_corners[b],
                            tl_state=None if tl_state is None else tl_state[b],
                            waypoints=None if waypoints is None else waypoints[b, c],
-                           waypoints_mask=None if waypoints_mask is None else waypoints_mask[b, c])
+                           waypoints_mask=None if waypoints_mask is None else waypoints_mask[b, c],
+                           agent_colors=None if agent_colors is None else agent_colors[b, c])
         img, _ = R.render_camera(sc, cam_xy[b, c], cam_sc[b, c], res, fov)
         out[(b, c)] = img
+    return out
+
+
+def with_extra_static(m, extra_verts, extra_faces, category):
+    """Map dict `m` + extra static triangles of one category appended behind the background (add_static_meshes)."""
+    nv = m["verts"].shape[0]
+    cats = list(m["categories"]) + ([category] if category not in m["categories"] else [])
+    out = dict(m)
+    out["verts"] = np.concatenate([m["verts"][:, :2], np.asarray(extra_verts, np.float32)])
+    out["faces"] = np.concatenate([m["faces"], np.asarray(extra_faces, np.int32) + nv]).astype(np.int32)
+    out["face_cat"] = list(m["face_cat"]) + [category] * len(extra_faces)
+    out["categories"] = cats
+    out["vert_category"] = np.concatenate([m["vert_category"], np.full(len(extra_verts), cats.index(category))])
     return out

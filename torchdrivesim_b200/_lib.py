@@ -23,6 +23,9 @@ MODEL_SIMPLE = 3
 MODEL_ORIENTED = 4
 METRIC_DISCS = 0
 METRIC_IOU = 1
+IMAGE_F32 = 0
+IMAGE_U8 = 1
+IMAGE_RANK = 2
 
 
 class TdsError(RuntimeError):
@@ -46,7 +49,7 @@ class MapInfo(ctypes.Structure):
                 ("raster_records", c_int32), ("offroad_gx", c_int32), ("offroad_gy", c_int32),
                 ("offroad_entries", c_int32), ("raster_cell", c_float), ("offroad_cell", c_float),
                 ("min_x", c_float), ("min_y", c_float), ("max_x", c_float), ("max_y", c_float),
-                ("device_bytes", c_int64)]
+                ("device_bytes", c_int64), ("raster_strips", c_int32), ("reserved", c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/tds_b200.h declares
@@ -70,6 +73,10 @@ SIGNATURES = {
     "tds_waypoint_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "tds_waypoint_gather": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tds_infraction_metrics": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "tds_agent_boxes": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "tds_rollout_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "tds_rollout_grad": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                   c_int64, c_void_p, c_void_p]),
     "tds_agents_relative": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "tds_sensing_noise": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "tds_sensing_occlusion": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
@@ -82,6 +89,12 @@ SIGNATURES = {
                                   c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tds_raster_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "tds_raster_set_timing_events": (None, [c_void_p, c_void_p]),
+    "tds_raster_birdview_fmt": (c_int32, [POINTER(c_void_p), c_int32, c_void_p, c_int32, c_int32, c_int32,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                          c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32,
+                                          c_void_p, c_void_p, c_int32,
+                                          POINTER(Palette), c_float, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "tds_raster_rank_table": (c_int32, [POINTER(Palette), c_void_p, c_void_p]),
     "tds_raster_birdview": (c_int32, [POINTER(c_void_p), c_int32, c_void_p, c_int32, c_int32, c_int32,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                       c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32,

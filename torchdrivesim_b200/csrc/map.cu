@@ -96,10 +96,71 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
         cy = std::min(std::max(cy, 0), d.rgy - 1);
         return cy * d.rgx + cx;
     };
+    // ---- strips of four faces over six vertices (see tds_map.cuh); the other faces become face records
+    std::vector<uint8_t> in_strip((size_t)nf, 0);
+    struct Strip { int v[6]; int cls; };
+    std::vector<Strip> strips;
+    auto finite_v = [&](int v) { return std::isfinite(h_verts[2 * v]) && std::isfinite(h_verts[2 * v + 1]); };
+    for (int f = 0; f + 3 < nf;) {
+        const int32_t* q = h_faces + 3 * (size_t)f;
+        bool ok = h_face_class[f] == h_face_class[f + 1] && h_face_class[f] == h_face_class[f + 2] &&
+                  h_face_class[f] == h_face_class[f + 3];
+        for (int k = 0; ok && k < 3; k++) ok = q[3 * (k + 1)] == q[3 * k + 1] && q[3 * (k + 1) + 1] == q[3 * k + 2];
+        if (ok) {
+            Strip s;
+            s.v[0] = q[0]; s.v[1] = q[1]; s.v[2] = q[2]; s.v[3] = q[5]; s.v[4] = q[8]; s.v[5] = q[11];
+            s.cls = h_face_class[f];
+            for (int k = 0; ok && k < 6; k++) ok = finite_v(s.v[k]);
+            if (ok) {
+                strips.push_back(s);
+                for (int k = 0; k < 4; k++) in_strip[f + k] = 1;
+                f += 4;
+                continue;
+            }
+        }
+        f++;
+    }
+    const bool dedupe_ok = d.rgx <= 8191 && d.rgy <= 8191;
+    struct SRec { int key; int strip; uint32_t meta; };
+    std::vector<SRec> srecs;
+    srecs.reserve(strips.size() * 2);
+    for (size_t s = 0; s < strips.size(); s++) {
+        int cell[6];
+        for (int k = 0; k < 6; k++) cell[k] = rcell_of(h_verts[2 * strips[s].v[k]], h_verts[2 * strips[s].v[k] + 1]);
+        for (int k = 0; k < 6; k++) {
+            bool seen = false;
+            for (int j = 0; j < k; j++) seen |= cell[j] == cell[k];
+            if (seen) continue;
+            uint32_t meta = (uint32_t)strips[s].cls;
+            if (dedupe_ok && k > 0) meta |= 32u | ((uint32_t)(cell[0] % d.rgx) << 6) | ((uint32_t)(cell[0] / d.rgx) << 19);
+            srecs.push_back({cell[k], (int)s, meta});
+        }
+    }
+    std::stable_sort(srecs.begin(), srecs.end(), [&](const SRec& a, const SRec& b) {
+        if (a.key != b.key) return a.key < b.key;
+        return strips[a.strip].cls < strips[b.strip].cls;
+    });
+    std::vector<int32_t> scell((size_t)nc + 1, 0);
+    for (const SRec& r : srecs) scell[r.key + 1]++;
+    for (size_t i = 0; i + 1 < scell.size(); i++) scell[i + 1] += scell[i];
+    const size_t sblocks = (srecs.size() + 31) / 32;
+    std::vector<float> srecdata(sblocks * 96 * 4, 0.f);
+    std::vector<uint32_t> smeta(std::max<size_t>(srecs.size(), 1), 0u);
+    for (size_t i = 0; i < srecs.size(); i++) {
+        const Strip& s = strips[srecs[i].strip];
+        float* base = &srecdata[(i >> 5) * 96 * 4 + (i & 31) * 4];
+        for (int k = 0; k < 6; k++) {
+            float* p = base + (k >> 1) * 32 * 4;
+            p[k & 1] = h_verts[2 * s.v[k]];
+            p[2 + (k & 1)] = h_verts[2 * s.v[k] + 1];
+        }
+        smeta[i] = srecs[i].meta;
+    }
     struct Rec { int key; int face; int own; };
     std::vector<Rec> recs;
     recs.reserve((size_t)nf * 2);
     for (int f = 0; f < nf; f++) {
+        if (in_strip[f]) continue;
         int cell[3];
         for (int k = 0; k < 3; k++) cell[k] = rcell_of(h_verts[2 * h_faces[3 * f + k]], h_verts[2 * h_faces[3 * f + k] + 1]);
         for (int k = 0; k < 3; k++) {
@@ -184,7 +245,8 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     }
     if (!(upload(recdata, &m->allocations[0], bytes) && upload(rcell, &m->allocations[1], bytes) &&
           upload(tri, &m->allocations[2], bytes) && upload(ocell, &m->allocations[3], bytes) &&
-          upload(orec, &m->allocations[4], bytes))) {
+          upload(orec, &m->allocations[4], bytes) && upload(srecdata, &m->allocations[5], bytes) &&
+          upload(smeta, &m->allocations[6], bytes) && upload(scell, &m->allocations[7], bytes))) {
         fail(TDS_ERR_CUDA, "map_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         tds_map_destroy(m);
         return nullptr;
@@ -194,8 +256,11 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     d.tri = (const float*)m->allocations[2];
     d.ocell = (const int32_t*)m->allocations[3];
     d.orec = (const float4*)m->allocations[4];
+    d.srec = (const float4*)m->allocations[5];
+    d.smeta = (const uint32_t*)m->allocations[6];
+    d.scell = (const int32_t*)m->allocations[7];
     m->info.n_verts = nv; m->info.n_faces = nf;
-    m->info.raster_gx = d.rgx; m->info.raster_gy = d.rgy; m->info.raster_records = (int32_t)recs.size();
+    m->info.raster_gx = d.rgx; m->info.raster_gy = d.rgy; m->info.raster_records = (int32_t)recs.size(); m->info.raster_strips = (int32_t)srecs.size();
     m->info.offroad_gx = d.ogx; m->info.offroad_gy = d.ogy;
     m->info.raster_cell = raster_cell; m->info.offroad_cell = offroad_cell;
     m->info.min_x = minx; m->info.min_y = miny; m->info.max_x = maxx; m->info.max_y = maxy;

@@ -56,4 +56,8 @@ __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {
                  : "memory");
 }
 
+__device__ __forceinline__ void st_cs_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 }  // namespace tds

@@ -14,6 +14,16 @@ struct MapDev {
     //   in this cell.  Records are sorted by cell (row-major), so one grid row is one contiguous range.
     const float4* rec;
     const int32_t* rcell;           // [rgx * rgy + 1] CSR offsets into rec (in records)
+    // ---- strips: four consecutive faces (a,b,c), (b,c,d), (c,d,e), (d,e,f) of one class - what the reference's
+    // line_segments_to_mesh (lanelet2.py:253-283) emits for every lane-marking segment - are kept as ONE record of
+    // six vertices instead of four face records, binned by the cell of each of the six vertices.  Vertex data in
+    // blocks of 32 strips, structure of arrays: block b = 3 x 32 float4, strip j of the block at float4 index
+    // b * 96 + p * 32 + j, p = 0: (x0, x1, y0, y1), p = 1: (x2, x3, y2, y3), p = 2: (x4, x5, y4, y5).
+    // smeta = class | secondary << 5 | primary cell column << 6 | primary cell row << 19: a copy outside the cell of
+    // vertex 0 (secondary) is skipped when the camera also scans that primary cell.
+    const float4* srec;
+    const uint32_t* smeta;
+    const int32_t* scell;           // [rgx * rgy + 1] CSR offsets into srec / smeta (in strips)
     float rx0, ry0, rcs, rinv;
     int32_t rgx, rgy, n_slots;
     int32_t slot_of_class[TDS_MAX_CLASSES];   // -1: the map has no face of that class
@@ -35,7 +45,7 @@ struct MapSetDev {
 struct tds_map {
     tds::MapDev dev;
     tds_map_info_t info;
-    void* allocations[5];
+    void* allocations[8];
     int device;
 };
 

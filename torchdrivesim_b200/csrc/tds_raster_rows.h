@@ -118,9 +118,9 @@ TDS_HD void row_fill_setup(int W, int H, int x0, int y0, int x1, int y1, int x2,
     const int yhi = (by - 1) < (H - 1) ? (by - 1) : (H - 1);
     if (ylo > yhi) return;
     f.fylo = ylo; f.fyhi = yhi;
-    f.dTB = edge_dx<int>(tx, ty, bx, by);
-    f.dTM = my > ty ? edge_dx<int>(tx, ty, mx, my) : 0;
-    f.dMB = by > my ? edge_dx<int>(mx, my, bx, by) : 0;
+    f.dTB = edge_dx32(tx, ty, bx, by);
+    f.dTM = my > ty ? edge_dx32(tx, ty, mx, my) : 0;
+    f.dMB = by > my ? edge_dx32(mx, my, bx, by) : 0;
     f.xT = tx << 16;
     f.xM = mx << 16;
     f.xa = (tx << 16) + (ylo - ty) * f.dTB;
@@ -169,6 +169,49 @@ TDS_HD void row_tri_step(RowTri& t, int W, int y, Emit&& emit) {
     for (int k = 0; k < 3; k++)
         if (y >= t.e[k].ylo && y <= t.e[k].yhi) { row_edge_step(t.e[k], y, lo, hi); emit(lo, hi); }
     if (y >= t.f.fylo && y <= t.f.fyhi && row_fill_step(t.f, W, y, lo, hi)) emit(lo, hi);
+}
+
+// The same pixel set spread over FOUR cooperating workers (the raster kernel: four lanes per face that crosses the
+// image border; a third of the code of row_tri_setup + row_tri_step).  Worker `part` = 0, 1, 2
+// walks the runs of the outline edge v2->v0, v0->v1, v1->v2 in its rows; worker 3 sets the fill up and hands it to all
+// four through share(value) -> the value held by worker 3 (a shuffle on the GPU, the identity on the host, where one
+// caller plays the four workers in turn); then every worker takes each fourth fill row, evaluated from the set-up
+// alone.  emit(y, lo, hi) per interval: the intervals of a row arrive from different workers; a bit-per-pixel target
+// ORs them, so the order does not matter.
+template <class RcpFn, class Emit, class Share>
+TDS_HD void row_tri_part(int W, int H, int x0, int y0, int x1, int y1, int x2, int y2, int part, RcpFn&& rcp_of, Emit&& emit,
+                         Share&& share) {
+    RowFill f;
+    f.fylo = 1; f.fyhi = 0; f.my = 0; f.ty = 0; f.xa = 0; f.dTB = 0; f.xT = 0; f.dTM = 0; f.xM = 0; f.dMB = 0;
+    if (part < 3) {
+        const int ax = part == 0 ? x2 : (part == 1 ? x0 : x1), ay = part == 0 ? y2 : (part == 1 ? y0 : y1);
+        const int bx = part == 0 ? x0 : (part == 1 ? x1 : x2), by = part == 0 ? y0 : (part == 1 ? y1 : y2);
+        RowEdge e;
+        row_edge_setup(W, H, ax, ay, bx, by, e, rcp_of);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int y = e.ylo; y <= e.yhi; y++) {
+            int lo, hi;
+            row_edge_step(e, y, lo, hi);
+            emit(y, lo, hi);
+        }
+    } else {
+        row_fill_setup(W, H, x0, y0, x1, y1, x2, y2, f);
+    }
+    // the fill: rows fylo + part, fylo + part + 4, ... (row_fill_at: the span of a row from the set-up alone)
+    f.fylo = share(f.fylo); f.fyhi = share(f.fyhi); f.my = share(f.my); f.ty = share(f.ty);
+    f.xa = share(f.xa); f.dTB = share(f.dTB); f.xT = share(f.xT); f.dTM = share(f.dTM); f.xM = share(f.xM); f.dMB = share(f.dMB);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int y = f.fylo + part; y <= f.fyhi; y += 4) {
+        const int xb = y < f.my ? f.xT + (y - f.ty) * f.dTM : f.xM + (y - f.my) * f.dMB;
+        const int xa = f.xa + (y - f.fylo) * f.dTB;
+        const int xl = xa < xb ? xa : xb, xr = xa < xb ? xb : xa;
+        const int c1 = (xl + 32768) >> 16, c2 = (xr + 32768) >> 16;
+        if (c2 >= 0 && c1 < W) emit(y, c1 < 0 ? 0 : c1, c2 >= W ? W - 1 : c2);
+    }
 }
 
 

@@ -104,14 +104,24 @@ class StaticMap:
             def __setstate__(self, state):
                 self.__dict__.update(state)
 
+        import io
+
         allowed = {("collections", "OrderedDict"), ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"),
-                   ("torch.storage", "_load_from_bytes"), ("torch", "Size"), ("numpy", "ndarray"), ("numpy", "dtype"),
+                   ("torch", "Size"), ("numpy", "ndarray"), ("numpy", "dtype"),
                    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct")}
+
+        def _storage_from_bytes(b):
+            # torch.storage._load_from_bytes is torch.load(..., weights_only=False), i.e. a second, UNRESTRICTED
+            # unpickler fed with bytes from the file: never resolve it.  The legacy storage payload is re-read with
+            # the weights-only loader, which admits tensors / storages and nothing else.
+            return torch.load(io.BytesIO(b), weights_only=True)
 
         class _Unpickler(pickle.Unpickler):
             def find_class(self, module, name):
                 if module.startswith("torchdrivesim."):
                     return _Bag
+                if (module, name) == ("torch.storage", "_load_from_bytes"):
+                    return _storage_from_bytes
                 if (module, name) in allowed or (module == "torch" and (name.endswith("Storage") or name in
                                                                          ("float32", "float64", "int64", "int32", "bool", "uint8"))):
                     return super().find_class(module, name)
@@ -123,6 +133,28 @@ class StaticMap:
             if not hasattr(mesh, attr):
                 raise _lib.TdsError(f"{path} does not hold a BirdviewMesh (no `{attr}`)")
         return cls.from_birdview_mesh(mesh, batch_index=batch_index, name=os.path.basename(path), **kw)
+
+    def with_extra_meshes(self, meshes, batch_index: int = 0) -> "StaticMap":
+        """A new map = this one followed by more static meshes (BirdviewRGBMeshGenerator.add_static_meshes,
+        mesh.py:870-883: they are concatenated behind the background mesh).  `meshes`: StaticMap objects or reference
+        BirdviewMesh-like objects (verts [B,V,2+], faces [B,F,3], categories, vert_category [B,V])."""
+        verts, faces, cats, vcat = [self.verts], [self.faces], list(self.categories), [self.vert_category]
+        nv = self.verts.shape[0]
+        for m in meshes:
+            if not isinstance(m, StaticMap):
+                m = StaticMap.from_birdview_mesh(m, batch_index=min(batch_index, m.verts.shape[0] - 1))
+            remap = np.zeros(max(len(m.categories), 1), np.int64)
+            for i, c in enumerate(m.categories):
+                if c not in cats:
+                    cats.append(c)
+                remap[i] = cats.index(c)
+            verts.append(m.verts)
+            faces.append(m.faces + nv)
+            vcat.append(remap[m.vert_category])
+            nv += m.verts.shape[0]
+        return StaticMap(np.concatenate(verts), np.concatenate(faces), cats, np.concatenate(vcat), name=self.name,
+                         left_handed=self.left_handed, stoplines=self.stoplines, stopline_types=self.stopline_types,
+                         raster_cell=self.raster_cell, offroad_cell=self.offroad_cell)
 
     # ---- queries ------------------------------------------------------------------------------
     @property

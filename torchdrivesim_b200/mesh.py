@@ -37,6 +37,8 @@ class BirdviewScene:
     workspace: Optional[Tensor] = None
     cam_tris: Optional[Tensor] = None          # [B,Nc,Tc,3,2] triangles of one camera each (waypoint discs)
     cam_tri_class: Optional[Tensor] = None     # [B,Nc,Tc] int32 class ids (< 0: skipped)
+    agent_class: Optional[Tensor] = None       # [B,Nc,N] uint8: class of each agent's rectangle per camera (custom colours)
+    custom_classes: Optional[list] = None      # [(agent type name, (r, g, b))] behind the ids of agent_class
 
     def slice(self, b0: int, b1: int) -> "BirdviewScene":
         """Environments [b0, b1) of the scene (views, no copies) - used to render in chunks."""
@@ -45,7 +47,8 @@ class BirdviewScene:
         return BirdviewScene(ms, cut(self.agent_state), cut(self.agent_size), cut(self.agent_type), cut(self.present),
                              self.agent_type_names, self.render_agent_direction, cut(self.tl_corners), cut(self.tl_state),
                              self.tl_allowed_states, cut(self.rect_corners), cut(self.rect_class), self.rect_categories,
-                             b1 - b0, self.workspace, cut(self.cam_tris), cut(self.cam_tri_class))
+                             b1 - b0, self.workspace, cut(self.cam_tris), cut(self.cam_tri_class), cut(self.agent_class),
+                             self.custom_classes)
 
     def palette(self, color_map, rendering_levels) -> "_lib.Palette":
         active = list(self.mapset.static_categories())
@@ -59,7 +62,7 @@ class BirdviewScene:
         if self.cam_tris is not None:
             active.append("goal_waypoint")
         return build_palette(color_map, rendering_levels, active, self.agent_type_names,
-                             self.render_agent_direction, self.tl_allowed_states)
+                             self.render_agent_direction, self.tl_allowed_states, custom=self.custom_classes)
 
 
 def _as_mapset(mesh) -> MapSet:
@@ -140,7 +143,16 @@ class B200BirdviewMeshGenerator:
             self.tl_corners, self.tl_allowed_states = None, []
 
     def add_static_meshes(self, meshes) -> None:
-        raise NotImplementedError("extra static meshes: build them into the StaticMap instead")
+        """Includes additional static elements in the background (mesh.py:870-883).  `meshes`: StaticMap objects or
+        reference BirdviewMesh objects whose categories have a colour and a rendering level; batch element b of a
+        mesh goes to map b of the map set (a mesh of batch size 1 goes to all of them).  The grids of the extended
+        maps are rebuilt on first use."""
+        meshes = list(meshes)
+        if not meshes:
+            return
+        self.mapset = MapSet([m.with_extra_meshes(meshes, batch_index=i) for i, m in enumerate(self.mapset.maps)],
+                             self.mapset.env_map)
+        self.background_mesh = self.mapset
 
     def generate(self, num_cameras: int, agent_state: Optional[Tensor] = None, present_mask: Optional[Tensor] = None,
                  traffic_lights=None, waypoints: Optional[Tensor] = None,
@@ -148,8 +160,6 @@ class B200BirdviewMeshGenerator:
                  custom_agent_colors: Optional[Tensor] = None) -> BirdviewScene:
         """Same arguments as the reference's generate (mesh.py:1053-1075): agent_state [B,Nc,N,4] (one
         copy per camera; must be the broadcast of a [B,N,4] tensor), present_mask [B,Nc,N]."""
-        if custom_agent_colors is not None:
-            raise NotImplementedError("custom agent colours are not part of the B200 hot path yet")
         state = size = types = present = None
         if agent_state is not None and self.agent_size is not None:
             if agent_state.dim() == 4:
@@ -175,6 +185,8 @@ class B200BirdviewMeshGenerator:
                               tl_corners=tl_corners, tl_state=tl_state, tl_allowed_states=self.tl_allowed_states,
                               rect_corners=self.rect_corners, rect_class=self.rect_class,
                               rect_categories=self.rect_categories, batch_size=B, workspace=self._workspace)
+        if custom_agent_colors is not None and state is not None:
+            scene.agent_class, scene.custom_classes = self._custom_agent_classes(num_cameras, custom_agent_colors, types, state)
         if waypoints is not None and waypoints.shape[-2] > 0:
             scene.cam_tris, scene.cam_tri_class = self._waypoint_triangles(num_cameras, waypoints, waypoints_rendering_mask)
         if state is not None:
@@ -184,6 +196,31 @@ class B200BirdviewMeshGenerator:
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=state.device)
             scene.workspace = self._workspace
         return scene
+
+    # ---- custom agent colours (mesh.py:1092-1099, rendering/cv2.py:50) ----------------------------------
+    def _custom_agent_classes(self, num_cameras: int, colors: Tensor, types: Optional[Tensor], state: Tensor):
+        """colors [B,Nc,N,3] in [0,1] -> (uint8 class per camera and agent, [(type name, rgb)] of those classes).
+        The reference paints the rectangle of agent n in camera c with floor(color * (1 - 1e-3) * 256) at the level of
+        the agent's type; every distinct (type, colour) pair becomes a class of this scene's palette.  Finding the
+        distinct pairs synchronises with the host (torch.unique) - the price of arbitrary colours in a class-based
+        raster; where rectangles of EQUAL level overlap, the reference's order is undefined (unstable argsort)."""
+        from .palette import class_names
+        B, N = state.shape[0], state.shape[1]
+        if tuple(colors.shape) != (B, num_cameras, N, 3):
+            raise _lib.TdsError("custom_agent_colors must be [B,Nc,N,3]")
+        q = (colors.detach().to(torch.float32) * (1.0 - 1e-3) * 256).floor().clamp(0, 255).to(torch.int64)
+        ty = torch.zeros(B, N, dtype=torch.int64, device=q.device) if types is None else types.to(q.device).to(torch.int64)
+        key = (ty[:, None, :] << 24) | (q[..., 0] << 16) | (q[..., 1] << 8) | q[..., 2]
+        uniq, inv = torch.unique(key, return_inverse=True)
+        base = len(class_names())
+        if base + uniq.numel() > _lib.MAX_CLASSES:
+            raise _lib.TdsError(f"{uniq.numel()} distinct custom agent colours: at most {_lib.MAX_CLASSES - base} fit the palette")
+        custom = []
+        for k in uniq.tolist():
+            t = k >> 24
+            name = self.agent_type_names[t] if t < len(self.agent_type_names) else self.agent_type_names[0]
+            custom.append((name, ((k >> 16) & 255, (k >> 8) & 255, k & 255)))
+        return (base + inv).to(torch.uint8).contiguous(), custom
 
     # ---- goal waypoints (mesh.py:885-909, 1120-1145, 1243-1271) -------------------------------------------
     waypoint_radius = 2.0

@@ -143,6 +143,46 @@ def collision_allpairs(ego_box: torch.Tensor, all_box: torch.Tensor, mask: torch
     return _AllPairs.apply(ego_box, all_box, mask, metric, ego_is_prefix)
 
 
+class _AgentBoxes(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, size):
+        lib = _lib.load()
+        s = _lib.as_f32(state)
+        z = _lib.as_f32(size[..., :2])
+        n = s[..., 0].numel()
+        box = torch.empty(s.shape[:-1] + (5,), dtype=torch.float32, device=s.device)
+        _lib.check(lib.tds_agent_boxes(_lib.ptr(s), _lib.ptr(z), n, _lib.ptr(box), None, _lib.stream_ptr(s.device)))
+        ctx.meta = (state.shape, size.shape)
+        return box
+
+    @staticmethod
+    def backward(ctx, g):
+        sshape, zshape = ctx.meta
+        gs = torch.cat([g[..., 0:2], g[..., 4:5], torch.zeros_like(g[..., 0:1])], dim=-1)
+        gz = g[..., 2:4]
+        if zshape[-1] > 2:
+            gz = torch.cat([gz, torch.zeros(gz.shape[:-1] + (zshape[-1] - 2,), dtype=gz.dtype, device=gz.device)], dim=-1)
+        return gs.reshape(sshape), gz.reshape(zshape)
+
+
+def agent_boxes(state: torch.Tensor, size: torch.Tensor) -> torch.Tensor:
+    """state [...,4] (x, y, psi, v), size [...,2+] (length, width) -> boxes [...,5] (x, y, length, width, psi): the layout of
+    compute_collision (simulator.py:1161-1170) in one launch instead of a torch.cat; differentiable."""
+    if state.shape[-1] != 4 or size.shape[-1] < 2 or state.shape[:-1] != size.shape[:-1]:
+        raise _lib.TdsError("agent_boxes: expected state [...,4] and size [...,2]")
+    return _AgentBoxes.apply(state, size)
+
+
+def heading_sincos(state: torch.Tensor) -> torch.Tensor:
+    """state [...,4] -> [...,2] = (sin psi, cos psi) evaluated like every other heading of the path (float64, rounded):
+    the egocentric camera orientation of render_egocentric (simulator.py:961, 1017).  Not differentiable."""
+    lib = _lib.load()
+    s = _lib.as_f32(state)
+    out = torch.empty(s.shape[:-1] + (2,), dtype=torch.float32, device=s.device)
+    _lib.check(lib.tds_agent_boxes(_lib.ptr(s), None, s[..., 0].numel(), None, _lib.ptr(out), _lib.stream_ptr(s.device)))
+    return out
+
+
 # ------------------------------------------------------------------------------------ traffic lights
 def traffic_light_violation(agent_box: torch.Tensor, tl_corners: torch.Tensor, tl_state: torch.Tensor, red_state: int,
                             rear_factor: float = 0.1, present: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -296,10 +336,13 @@ def raster_birdview(mapset: MapSet, palette: "_lib.Palette", cam_xy: torch.Tenso
                     rect_corners: Optional[torch.Tensor], rect_class: Optional[torch.Tensor],
                     res: int, fov: float, out: Optional[torch.Tensor] = None,
                     workspace: Optional[torch.Tensor] = None, cam_tris: Optional[torch.Tensor] = None,
-                    cam_tri_class: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    cam_tri_class: Optional[torch.Tensor] = None, image_format: int = _lib.IMAGE_F32,
+                    agent_class: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cam_xy, cam_sc [B,Nc,2] -> images [B,Nc,3,res,res] float32 in [0,255] (not differentiable, like
     the cv2 backend).  present is [B,N] or [B,Nc,N]; cam_tris [B,Nc,Tc,3,2] + cam_tri_class [B,Nc,Tc] are
-    triangles seen by one camera each (waypoint discs)."""
+    triangles seen by one camera each (waypoint discs).  image_format: IMAGE_F32 (the reference's dtype),
+    IMAGE_U8 (the same values as uint8 [B,Nc,3,res,res]) or IMAGE_RANK (uint8 [B,Nc,res,res] draw ranks, see
+    `raster_rank_table`).  agent_class [B,Nc,N] uint8: palette class of each agent's rectangle per camera (custom colours)."""
     lib = _lib.load()
     dev = cam_xy.device
     cxy, csc = _lib.as_f32(cam_xy), _lib.as_f32(cam_sc)
@@ -321,10 +364,14 @@ def raster_birdview(mapset: MapSet, palette: "_lib.Palette", cam_xy: torch.Tenso
     tls = None if L == 0 else _lib.as_i32(tl_state)
     rc = None if R == 0 else _lib.as_f32(rect_corners)
     rcl = None if R == 0 else _lib.as_i32(rect_class)
+    if image_format not in (_lib.IMAGE_F32, _lib.IMAGE_U8, _lib.IMAGE_RANK):
+        raise _lib.TdsError(f"raster: unknown image format {image_format}")
+    oshape = (B, Nc, res, res) if image_format == _lib.IMAGE_RANK else (B, Nc, 3, res, res)
+    odtype = torch.float32 if image_format == _lib.IMAGE_F32 else torch.uint8
     if out is None:
-        out = torch.empty(B, Nc, 3, res, res, dtype=torch.float32, device=dev)
-    elif tuple(out.shape) != (B, Nc, 3, res, res) or out.dtype != torch.float32 or not out.is_contiguous():
-        raise _lib.TdsError("raster: `out` must be a contiguous float32 [B,Nc,3,res,res] tensor")
+        out = torch.empty(oshape, dtype=odtype, device=dev)
+    elif tuple(out.shape) != oshape or out.dtype != odtype or not out.is_contiguous():
+        raise _lib.TdsError(f"raster: `out` must be a contiguous {odtype} {list(oshape)} tensor")
     need = lib.tds_raster_workspace_bytes(B, N, L, R)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -334,11 +381,28 @@ def raster_birdview(mapset: MapSet, palette: "_lib.Palette", cam_xy: torch.Tenso
         if tuple(cam_tris.shape) != (B, Nc, Tc, 3, 2) or cam_tri_class is None or tuple(cam_tri_class.shape) != (B, Nc, Tc):
             raise _lib.TdsError("raster: cam_tris must be [B,Nc,Tc,3,2] and cam_tri_class [B,Nc,Tc]")
         ctr, ccl = _lib.as_f32(cam_tris), _lib.as_i32(cam_tri_class)
+    acl = None
+    if agent_class is not None and N > 0:
+        if tuple(agent_class.shape) != (B, Nc, N) or agent_class.dtype != torch.uint8:
+            raise _lib.TdsError("raster: agent_class must be uint8 [B,Nc,N]")
+        acl = agent_class.contiguous()
     handles, n_maps = mapset.handles(dev)
     env_map = mapset.env_map_on(dev)
-    _lib.check(lib.tds_raster_birdview(handles, n_maps, _lib.ptr(env_map), B, Nc, N, _lib.ptr(cxy), _lib.ptr(csc),
-                                       _lib.ptr(ast), _lib.ptr(asz), _lib.ptr(aty), _lib.ptr(pr), per_cam,
-                                       _lib.ptr(tlc), _lib.ptr(tls), L, _lib.ptr(rc), _lib.ptr(rcl), R,
-                                       _lib.ptr(ctr), _lib.ptr(ccl), Tc, ctypes.byref(palette), float(2.0 / fov), int(res), _lib.ptr(out),
-                                       _lib.ptr(workspace), _lib.stream_ptr(dev)))
+    _lib.check(lib.tds_raster_birdview_fmt(handles, n_maps, _lib.ptr(env_map), B, Nc, N, _lib.ptr(cxy), _lib.ptr(csc),
+                                           _lib.ptr(ast), _lib.ptr(asz), _lib.ptr(aty), _lib.ptr(pr), per_cam,
+                                           _lib.ptr(tlc), _lib.ptr(tls), L, _lib.ptr(rc), _lib.ptr(rcl), R,
+                                           _lib.ptr(ctr), _lib.ptr(ccl), Tc, ctypes.byref(palette), float(2.0 / fov), int(res),
+                                           _lib.ptr(acl), int(image_format), _lib.ptr(out), _lib.ptr(workspace),
+                                           _lib.stream_ptr(dev)))
     return out
+
+
+def raster_rank_table(palette: "_lib.Palette"):
+    """(rgb uint8 [K+1,3], class ids int32 [K+1]) of the draw ranks an IMAGE_RANK image holds: row 0 is the
+    background, row k the k-th class in draw order.  rgb[rank_image.long()] is the IMAGE_U8 picture (channels last)."""
+    lib = _lib.load()
+    rgb = (ctypes.c_uint8 * (3 * (_lib.MAX_CLASSES + 1)))()
+    cls = (ctypes.c_int32 * (_lib.MAX_CLASSES + 1))()
+    n = lib.tds_raster_rank_table(ctypes.byref(palette), rgb, cls)
+    return (torch.tensor(list(rgb), dtype=torch.uint8).reshape(-1, 3)[:n].clone(),
+            torch.tensor(list(cls), dtype=torch.int32)[:n].clone())

@@ -62,8 +62,11 @@ def quantize_color(rgb: Iterable[float]) -> Tuple[int, int, int]:
 
 def build_palette(color_map: Dict[str, Color], rendering_levels: Dict[str, float], active: Iterable[str],
                   agent_type_names: Optional[List[str]] = None, direction: bool = True,
-                  tl_states: Optional[List[str]] = None) -> "_lib.Palette":
-    """Fills the C-ABI palette for the categories in `active`."""
+                  tl_states: Optional[List[str]] = None,
+                  custom: Optional[List[Tuple[str, Color]]] = None) -> "_lib.Palette":
+    """Fills the C-ABI palette for the categories in `active`.  `custom` = [(category, (r, g, b))]: extra classes of this
+    palette only, drawn at the level of `category` with the given, already quantized, colour (custom agent colours);
+    they take the class ids len(class_names()), len(class_names()) + 1, ..."""
     active = list(dict.fromkeys(active))
     for name in active:
         class_id(name)
@@ -87,6 +90,16 @@ def build_palette(color_map: Dict[str, Color], rendering_levels: Dict[str, float
         if t >= _lib.MAX_AGENT_TYPES:
             raise _lib.TdsError(f"at most {_lib.MAX_AGENT_TYPES} agent types are supported")
         pal.agent_type_class[t] = class_id(n)
+    for k, (cat, rgb) in enumerate(custom or []):
+        i = len(names) + k
+        if i >= _lib.MAX_CLASSES:
+            raise _lib.TdsError(f"too many distinct custom agent colours: {len(custom)} + {len(names)} categories > {_lib.MAX_CLASSES}")
+        if cat not in rank:
+            raise _lib.TdsError(f"category '{cat}' needs a rendering level")
+        pal.n_classes = i + 1
+        pal.active[i] = 1
+        pal.rank[i] = rank[cat]
+        pal.rgb[i][0], pal.rgb[i][1], pal.rgb[i][2] = int(rgb[0]), int(rgb[1]), int(rgb[2])
     pal.direction_class = class_id("direction") if direction else -1
     for s in range(_lib.MAX_TL_STATES):
         pal.tl_state_class[s] = -1

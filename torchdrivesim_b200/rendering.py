@@ -64,7 +64,9 @@ class B200Renderer(BirdviewRenderer):
     image is not differentiable."""
 
     def render_frame(self, scene, camera_xy: Tensor, camera_sc: Tensor, res: Optional[Resolution] = None,
-                     fov: Optional[float] = None, out: Optional[Tensor] = None) -> Tensor:
+                     fov: Optional[float] = None, out: Optional[Tensor] = None, dtype=None) -> Tensor:
+        """dtype: None / torch.float32 = the reference's image ([.,3,H,W] float32 in [0,255]); torch.uint8 = the same
+        values as bytes; 'rank' = uint8 [.,H,W] draw ranks (index into `rank_table(scene)`), the most compact form."""
         from .mesh import BirdviewScene
         if not isinstance(scene, BirdviewScene):
             raise _lib.TdsError("B200Renderer renders BirdviewScene objects made by B200BirdviewMeshGenerator.generate; "
@@ -79,13 +81,31 @@ class B200Renderer(BirdviewRenderer):
         if B != scene.batch_size:
             raise _lib.TdsError(f"camera batch {B} does not match the scene batch {scene.batch_size}")
         palette = scene.palette(self.color_map, self.rendering_levels)
+        fmt = image_format_of(dtype)
+        tail = (res.height, res.width) if fmt == _lib.IMAGE_RANK else (3, res.height, res.width)
         if out is not None:
-            out = out.view(B, Nc, 3, res.height, res.width)
+            out = out.view((B, Nc) + tail)
         img = ops.raster_birdview(scene.mapset, palette, camera_xy, camera_sc, scene.agent_state, scene.agent_size,
                                   scene.agent_type, scene.present, scene.tl_corners, scene.tl_state,
                                   scene.rect_corners, scene.rect_class, res.height, fov_m, out=out,
-                                  workspace=scene.workspace, cam_tris=scene.cam_tris, cam_tri_class=scene.cam_tri_class)
-        return img.reshape(B * Nc, 3, res.height, res.width)
+                                  workspace=scene.workspace, cam_tris=scene.cam_tris, cam_tri_class=scene.cam_tri_class,
+                                  image_format=fmt, agent_class=scene.agent_class)
+        return img.reshape((B * Nc,) + tail)
+
+    def rank_table(self, scene):
+        """(rgb uint8 [K+1,3], class ids [K+1]) for images rendered with dtype='rank' from this scene."""
+        return ops.raster_rank_table(scene.palette(self.color_map, self.rendering_levels))
+
+
+def image_format_of(dtype) -> int:
+    import torch
+    if dtype is None or dtype == torch.float32:
+        return _lib.IMAGE_F32
+    if dtype == torch.uint8:
+        return _lib.IMAGE_U8
+    if dtype == 'rank':
+        return _lib.IMAGE_RANK
+    raise _lib.TdsError(f"unsupported image dtype {dtype}: use torch.float32, torch.uint8 or 'rank'")
 
 
 def renderer_from_config(cfg: RendererConfig, *args, **kwargs) -> BirdviewRenderer:

@@ -9,7 +9,9 @@ tensor conventions:
 
     npc_controller.advance_npcs :854 (+ :54-124, behavior/replay.py:46-107) -> one replay / spawn / despawn launch
 
-Waypoint goal bookkeeping, observation noise and lanelet-based losses are out of scope.
+    waypoint_goals.step     :860-861 (+ goals.py:159-217) -> one launch; observation noise: observation_noise.py
+
+The lanelet-based wrong-way loss, the IAI / heuristic behaviour models and the map-from-log noise are out of scope.
 """
 import copy as _copy
 from dataclasses import dataclass, field
@@ -257,14 +259,9 @@ class Simulator:
     def fit_action(self, future_state: Tensor, current_state: Optional[Tensor] = None) -> Tensor:
         return self.kinematic_model.fit_action(future_state=future_state, current_state=current_state)
 
-    def render(self, camera_xy: Tensor, camera_psi: Tensor, res: Optional[Resolution] = None,
-               rendering_mask: Optional[Tensor] = None, fov: Optional[float] = None, out: Optional[Tensor] = None,
-               waypoints: Optional[Tensor] = None, waypoints_rendering_mask: Optional[Tensor] = None) -> Tensor:
-        """camera_xy BxNx2, camera_psi BxNx1 -> BxNx3xHxW (simulator.py:920-992); waypoints BxNxMx2 and their
-        BxNxM mask draw goal-waypoint discs for the camera they belong to."""
-        camera_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
-        if camera_xy.dim() == 2:
-            camera_xy, camera_sc = camera_xy.unsqueeze(1), camera_sc.unsqueeze(1)
+    def _scene(self, camera_xy: Tensor, rendering_mask: Optional[Tensor], waypoints: Optional[Tensor],
+               waypoints_rendering_mask: Optional[Tensor], custom_agent_colors: Optional[Tensor]):
+        """The scene descriptor `render` hands to the renderer (simulator.py:961-990)."""
         n_cameras = camera_xy.shape[-2]
         present = self.get_all_agent_present_mask()
         if rendering_mask is not None:
@@ -272,18 +269,28 @@ class Simulator:
         else:
             present = present.unsqueeze(-2).expand(-1, n_cameras, -1)
         tl = self.traffic_controls.get('traffic_light') if self.traffic_controls is not None else None
-        scene = self.birdview_mesh_generator.generate(
+        return self.birdview_mesh_generator.generate(
             n_cameras, agent_state=self.get_all_agent_state().detach()[:, None].expand(-1, n_cameras, -1, -1),
             present_mask=present, traffic_lights=tl, waypoints=waypoints,
-            waypoints_rendering_mask=waypoints_rendering_mask)
-        img = self.renderer.render_frame(scene, camera_xy, camera_sc, res=res, fov=fov, out=out)
+            waypoints_rendering_mask=waypoints_rendering_mask, custom_agent_colors=custom_agent_colors)
+
+    def render(self, camera_xy: Tensor, camera_psi: Tensor, res: Optional[Resolution] = None,
+               rendering_mask: Optional[Tensor] = None, fov: Optional[float] = None, out: Optional[Tensor] = None,
+               waypoints: Optional[Tensor] = None, waypoints_rendering_mask: Optional[Tensor] = None,
+               custom_agent_colors: Optional[Tensor] = None, dtype=None) -> Tensor:
+        """camera_xy BxNx2, camera_psi BxNx1 -> BxNx3xHxW (simulator.py:920-992); waypoints BxNxMx2 and their
+        BxNxM mask draw goal-waypoint discs for the camera they belong to; custom_agent_colors BxNxAllx3 in [0,1]
+        is the colour of each agent in each camera.  dtype: torch.float32 (default, the reference's image),
+        torch.uint8 (the same values, 4x fewer bytes) or 'rank' (BxNxHxW draw ranks, see `renderer.rank_table`)."""
+        camera_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
+        if camera_xy.dim() == 2:
+            camera_xy, camera_sc = camera_xy.unsqueeze(1), camera_sc.unsqueeze(1)
+        n_cameras = camera_xy.shape[-2]
+        scene = self._scene(camera_xy, rendering_mask, waypoints, waypoints_rendering_mask, custom_agent_colors)
+        img = self.renderer.render_frame(scene, camera_xy, camera_sc, res=res, fov=fov, out=out, dtype=dtype)
         return img.reshape((self.batch_size, n_cameras) + img.shape[1:])
 
-    def render_egocentric(self, ego_rotate: bool = True, res: Optional[Resolution] = None, fov: Optional[float] = None,
-                          visibility_matrix: Optional[Tensor] = None, out: Optional[Tensor] = None,
-                          n_subsequent_waypoints: int = 1) -> Tensor:
-        """One camera per agent -> BxAx3xHxW (simulator.py:994-1033); with waypoint goals every agent sees the discs of
-        its next `n_subsequent_waypoints` collections."""
+    def _egocentric_cameras(self, ego_rotate: bool, visibility_matrix: Optional[Tensor], n_subsequent_waypoints: int):
         state = self.get_state().detach()
         camera_xy, camera_psi = state[..., :2], state[..., 2:3]
         if not ego_rotate:
@@ -295,39 +302,59 @@ class Simulator:
         waypoints = waypoints_mask = None
         if self.waypoint_goals is not None:
             waypoints, waypoints_mask = self.waypoint_goals.get_waypoints_and_masks(count=n_subsequent_waypoints)
+        return camera_xy, camera_psi, rendering_mask, waypoints, waypoints_mask
+
+    def render_egocentric(self, ego_rotate: bool = True, res: Optional[Resolution] = None, fov: Optional[float] = None,
+                          visibility_matrix: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                          n_subsequent_waypoints: int = 1, custom_agent_colors: Optional[Tensor] = None,
+                          dtype=None) -> Tensor:
+        """One camera per agent -> BxAx3xHxW (simulator.py:994-1033); with waypoint goals every agent sees the discs of
+        its next `n_subsequent_waypoints` collections; custom_agent_colors BxAxAllx3: the colours agents see each
+        other as."""
+        camera_xy, camera_psi, rendering_mask, waypoints, waypoints_mask = self._egocentric_cameras(
+            ego_rotate, visibility_matrix, n_subsequent_waypoints)
         return self.render(camera_xy, camera_psi, rendering_mask=rendering_mask, res=res, fov=fov, out=out,
-                           waypoints=waypoints, waypoints_rendering_mask=waypoints_mask)
+                           waypoints=waypoints, waypoints_rendering_mask=waypoints_mask,
+                           custom_agent_colors=custom_agent_colors, dtype=dtype)
 
     def render_egocentric_to_host(self, host_out: Tensor, chunk_envs: int = 128, res: Optional[Resolution] = None,
-                                  fov: Optional[float] = None) -> Tensor:
-        """Egocentric birdviews delivered into a PINNED host tensor [B,A,3,H,W]: environments are rendered
-        in chunks into two device buffers while the previous chunk is copied out on a side stream, so the
-        PCIe transfer overlaps the raster kernel.  Returns `host_out` (valid after the returned stream
-        work is synchronised by the caller, e.g. torch.cuda.synchronize())."""
+                                  fov: Optional[float] = None, ego_rotate: bool = True,
+                                  visibility_matrix: Optional[Tensor] = None, n_subsequent_waypoints: int = 1,
+                                  custom_agent_colors: Optional[Tensor] = None) -> Tensor:
+        """`render_egocentric` delivered into a PINNED host tensor: [B,A,3,H,W] float32 (the reference's image),
+        [B,A,3,H,W] uint8 (the same values as bytes: the pixels are integers in [0,255], rendering/cv2.py:50, so
+        nothing is lost and a PCIe-bound consumer gets 4x the frames) or [B,A,H,W] uint8 with dtype 'rank' semantics
+        when `host_out` has no channel dimension.  Environments are rendered in chunks into two device buffers while
+        the previous chunk is copied out on a side stream, so the transfer overlaps the raster kernel.  Returns
+        `host_out` (valid once the current stream is synchronised)."""
         res = self.renderer.res if res is None else res
-        state = self.get_state().detach()
-        dev = state.device
-        B, A = state.shape[0], state.shape[1]
-        if tuple(host_out.shape) != (B, A, 3, res.height, res.width) or not host_out.is_pinned():
-            raise _lib.TdsError("host_out must be a pinned float32 tensor of shape [B,A,3,H,W]")
-        cam_xy = state[..., :2].contiguous()
-        cam_sc = torch.cat([torch.sin(state[..., 2:3]), torch.cos(state[..., 2:3])], dim=-1)
-        present = self.get_all_agent_present_mask()
-        tl = self.traffic_controls.get('traffic_light') if self.traffic_controls is not None else None
-        scene = self.birdview_mesh_generator.generate(A, agent_state=state[:, None].expand(-1, A, -1, -1),
-                                                      present_mask=present.unsqueeze(-2).expand(-1, A, -1), traffic_lights=tl)
+        camera_xy, camera_psi, rendering_mask, waypoints, waypoints_mask = self._egocentric_cameras(
+            ego_rotate, visibility_matrix, n_subsequent_waypoints)
+        dev = camera_xy.device
+        B, A = camera_xy.shape[0], camera_xy.shape[1]
+        rank = host_out.dim() == 4
+        tail = (res.height, res.width) if rank else (3, res.height, res.width)
+        if tuple(host_out.shape) != (B, A) + tail or not host_out.is_pinned() or \
+                host_out.dtype not in ((torch.uint8,) if rank else (torch.float32, torch.uint8)):
+            raise _lib.TdsError("host_out must be a pinned tensor: float32 / uint8 [B,A,3,H,W] or uint8 [B,A,H,W] (draw ranks)")
+        dtype = 'rank' if rank else host_out.dtype
+        cam_xy = camera_xy.contiguous()
+        cam_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
+        scene = self._scene(cam_xy, rendering_mask, waypoints, waypoints_mask, custom_agent_colors)
         chunk = max(1, min(chunk_envs, B))
-        if getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, A, 3, res.height, res.width):
-            self._h2d_bufs = [torch.empty(chunk, A, 3, res.height, res.width, dtype=torch.float32, device=dev) for _ in range(2)]
+        key = ((chunk, A) + tail, host_out.dtype)
+        if getattr(self, "_h2d_key", None) != key:
+            self._h2d_bufs = [torch.empty(key[0], dtype=host_out.dtype, device=dev) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._buf_free = [None, None]
+            self._h2d_key = key
         main = torch.cuda.current_stream(dev)
         for i, b0 in enumerate(range(0, B, chunk)):
             b1 = min(b0 + chunk, B)
             buf = self._h2d_bufs[i % 2][: b1 - b0]
             if self._buf_free[i % 2] is not None:
                 main.wait_event(self._buf_free[i % 2])          # the previous copy out of this buffer is done
-            self.renderer.render_frame(scene.slice(b0, b1), cam_xy[b0:b1], cam_sc[b0:b1], res=res, fov=fov, out=buf)
+            self.renderer.render_frame(scene.slice(b0, b1), cam_xy[b0:b1], cam_sc[b0:b1], res=res, fov=fov, out=buf, dtype=dtype)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(self._copy_stream):
