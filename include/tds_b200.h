@@ -163,8 +163,8 @@ int tds_infraction_metrics(const float* d_collision, const float* d_offroad, con
  * Glue of the per-step path and of differentiable rollouts: what the reference does with eager torch ops between its
  * hot functions, as single launches.
  * tds_agent_boxes:  d_state [n,4] (x, y, psi, v), d_size [n,2] (length, width) -> d_box [n,5] (x, y, length, width, psi),
- *                   the box layout of compute_collision (simulator.py:1161-1170); d_cam_sc [n,2] = (sin psi, cos psi),
- *                   the egocentric camera orientation of render_egocentric (simulator.py:961, 1017).  Either output
+ *                   the box layout of compute_collision (simulator.py:1161-1170); d_cam_sc [n,2] = (sin psi, cos psi) and
+ *                   d_xy [n,2] = (x, y), the egocentric cameras of render_egocentric (simulator.py:961, 1017).  Any output
  *                   may be NULL.
  * tds_rollout_loss: d_acc[0..2] (float64, accumulated) += sum of d_collision [n], sum of d_offroad [n],
  *                   sum over agents of |xy - target|^2 (d_state [n,4], d_target_xy [n,2]); any input may be NULL.
@@ -174,7 +174,8 @@ int tds_infraction_metrics(const float* d_collision, const float* d_offroad, con
  *                   kinematic step, NULL: 0) + w_o d_grad_offroad (tds_offroad_bwd, [n,4]) + w_c (d_grad_box_ego +
  *                   d_grad_box_all)[x, y, psi] (tds_collision_allpairs_bwd, [n,5] each) + w_t (xy - target).
  * ---------------------------------------------------------------------------------------- */
-int tds_agent_boxes(const float* d_state, const float* d_size, int64_t n, float* d_box, float* d_cam_sc, void* stream);
+int tds_agent_boxes(const float* d_state, const float* d_size, int64_t n, float* d_box, float* d_cam_sc, float* d_xy,
+                    void* stream);
 int tds_rollout_loss(const float* d_collision, const float* d_offroad, const float* d_state, const float* d_target_xy,
                      int64_t n, double* d_acc, void* stream);
 int tds_rollout_grad(const float* d_grad_next, const float* d_grad_offroad, const float* d_grad_box_ego,
@@ -264,8 +265,9 @@ typedef struct {
     int32_t tl_state_class[TDS_MAX_TL_STATES];      /* class of traffic-light state index s */
 } tds_palette_t;
 
-/* bytes of the per-step scratch buffer (world-space dynamic triangles of every environment + the work
- * counter of the persistent raster grid); always > 0 */
+/* bytes of the per-step scratch buffer (world-space dynamic triangles of every environment, the work counters of the
+ * persistent raster grid and a list of up to B * N cameras for its second pass); always > 0.  Calls with more than
+ * B * N cameras allocate library-owned scratch on first use, which cannot happen inside a CUDA graph capture. */
 int64_t tds_raster_workspace_bytes(int32_t B, int32_t N, int32_t L, int32_t R);
 
 /* Renders Nc cameras per environment.

@@ -8,7 +8,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _make(B, A, seed, lights, npcs=0):
+def _make(B, A, seed, lights, npcs=0, goals=False):
     import torchdrivesim_b200 as tds
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(seed)
@@ -30,17 +30,23 @@ def _make(B, A, seed, lights, npcs=0):
                                     torch.tensor(rng.uniform(size=(B, npcs, 8)) > 0.5, device=dev))
         ctrl = tds.ReplayController(torch.full((B, npcs, 2), 2.0, device=dev), torch.tensor(log, dtype=torch.float32, device=dev),
                                     torch.tensor(rng.uniform(size=(B, npcs, 4)) > 0.4, device=dev), spawn_controller=spawn)
+    wg = None
+    if goals:
+        # three collections of two waypoints per agent, the first ones within reach of the first steps
+        wp = state[:, :, None, None, :2] + rng.normal(0, 1.5, (B, A, 3, 2, 2)) + np.arange(3)[None, None, :, None, None] * 2.0
+        wg = tds.WaypointGoal(torch.tensor(wp, dtype=torch.float32, device=dev), torch.tensor(rng.uniform(size=(B, A, 3, 2)) > 0.2, device=dev))
     sim = tds.Simulator(town, km, torch.tensor(size, device=dev), torch.tensor(present, device=dev),
-                        tds.TorchDriveConfig(left_handed_coordinates=True), traffic_controls=tc, npc_controller=ctrl)
+                        tds.TorchDriveConfig(left_handed_coordinates=True), traffic_controls=tc, npc_controller=ctrl,
+                        waypoint_goals=wg)
     acts = torch.tensor(rng.uniform(-1, 1, (5, B, A, 2)).astype(np.float32), device=dev)
     return sim, acts
 
 
-@pytest.mark.parametrize("lights,npcs", [(False, 0), (True, 0), (True, 3)])
-def test_graph_replay_equals_eager(lights, npcs):
+@pytest.mark.parametrize("lights,npcs,goals", [(False, 0, False), (True, 0, False), (True, 3, False), (True, 2, True)])
+def test_graph_replay_equals_eager(lights, npcs, goals):
     import torchdrivesim_b200 as tds
-    eager, acts = _make(6, 5, 3, lights, npcs)
-    graphed_sim, _ = _make(6, 5, 3, lights, npcs)
+    eager, acts = _make(6, 5, 3, lights, npcs, goals)
+    graphed_sim, _ = _make(6, 5, 3, lights, npcs, goals)
     runner = tds.GraphedHotPath(graphed_sim)
     for t in range(acts.shape[0]):
         eager.step(acts[t])
@@ -50,7 +56,12 @@ def test_graph_replay_equals_eager(lights, npcs):
         assert torch.equal(runner.state, eager.get_state()), f"state differs at step {t}"
         assert torch.equal(img_g, img_e), f"image differs at step {t}"
         assert torch.equal(coll_g, coll_e) and torch.equal(off_g, off_e)
+        if goals:       # the goals advance inside the graph (simulator.py:860-861) and the discs follow
+            assert torch.equal(graphed_sim.waypoint_goals.state, eager.waypoint_goals.state), f"goal state differs at step {t}"
+            assert torch.equal(graphed_sim.waypoint_goals.mask, eager.waypoint_goals.mask)
         if npcs:
             assert torch.equal(graphed_sim.get_npc_state(), eager.get_npc_state())
             assert torch.equal(graphed_sim.get_npc_present_mask(), eager.get_npc_present_mask())
     assert graphed_sim.internal_time == eager.internal_time == acts.shape[0]
+    if goals:
+        assert int(eager.waypoint_goals.state.max()) > 0 and (img_e[:, :, 0] == 139).any()      # goals were reached; discs are drawn

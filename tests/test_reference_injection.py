@@ -55,7 +55,7 @@ def test_injected_objects_reproduce_the_stock_reference(monkeypatch):
         return OK.bicycle_step(st, act, lr_, params.dt, True)
 
     def fake_raster(mapset, palette, cam_xy, cam_sc, agent_state, agent_size, agent_type, present_, tl_corners, tl_state,
-                    rect_corners, rect_class, res, fov, out=None, workspace=None, cam_tris=None, cam_tri_class=None):
+                    rect_corners, rect_class, res, fov, out=None, workspace=None, cam_tris=None, cam_tri_class=None, **kw):
         assert cam_xy.shape == (B, A, 2) and agent_state.shape == (B, A, 4) and present_.shape == (B, A)
         assert tl_corners.shape == (B, 24, 4, 2) and tl_state.shape == (B, 24)
         imgs = util.oracle_render_batch(m, agent_state.numpy(), agent_size.numpy(), agent_type.numpy(), present_.numpy(),

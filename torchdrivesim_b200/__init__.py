@@ -21,7 +21,7 @@ from .simulator import CollisionMetric, Simulator, TorchDriveConfig  # noqa: F40
 from .graph import GraphedHotPath  # noqa: F401
 from .rollout import FusedRollout  # noqa: F401
 from . import distributed, ops  # noqa: F401
-from .traffic_lights import TrafficLightController, TrafficLightStateMachine  # noqa: F401
+from .traffic_lights import TrafficLightController, unroll_controller  # noqa: F401
 from .traffic_controls import BaseTrafficControl, StopSignControl, TrafficLightControl, YieldControl  # noqa: F401
 
 __version__ = "0.1.0"

@@ -157,39 +157,60 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
         smeta[i] = srecs[i].meta;
     }
     struct Rec { int key; int face; int own; };
-    std::vector<Rec> recs;
-    recs.reserve((size_t)nf * 2);
-    for (int f = 0; f < nf; f++) {
-        if (in_strip[f]) continue;
-        int cell[3];
-        for (int k = 0; k < 3; k++) cell[k] = rcell_of(h_verts[2 * h_faces[3 * f + k]], h_verts[2 * h_faces[3 * f + k] + 1]);
-        for (int k = 0; k < 3; k++) {
-            bool seen = false;
-            for (int j = 0; j < k; j++) seen |= cell[j] == cell[k];
-            if (seen) continue;
-            int own = 0;
-            for (int j = 0; j < 3; j++) own |= (cell[j] == cell[k]) << j;
-            recs.push_back({cell[k], f, own});
+    auto build_face_records = [&](bool all, std::vector<int32_t>& cells, std::vector<float>& data) {
+        std::vector<Rec> recs;
+        recs.reserve((size_t)nf * 2);
+        for (int f = 0; f < nf; f++) {
+            if (!all && in_strip[f]) continue;
+            int cell[3];
+            for (int k = 0; k < 3; k++) cell[k] = rcell_of(h_verts[2 * h_faces[3 * f + k]], h_verts[2 * h_faces[3 * f + k] + 1]);
+            for (int k = 0; k < 3; k++) {
+                bool seen = false;
+                for (int j = 0; j < k; j++) seen |= cell[j] == cell[k];
+                if (seen) continue;
+                int own = 0;
+                for (int j = 0; j < 3; j++) own |= (cell[j] == cell[k]) << j;
+                recs.push_back({cell[k], f, own});
+            }
         }
-    }
-    // cell-major (all classes of a cell together: the kernel makes ONE pass over the candidates and keeps
-    // painter's order in per-class bitplanes); inside a cell by class, then by face
-    std::stable_sort(recs.begin(), recs.end(), [&](const Rec& a, const Rec& b) {
-        if (a.key != b.key) return a.key < b.key;
-        return h_face_class[a.face] < h_face_class[b.face];
-    });
-    std::vector<int32_t> rcell((size_t)nc + 1, 0);
-    for (const Rec& r : recs) rcell[r.key + 1]++;
-    for (size_t i = 0; i + 1 < rcell.size(); i++) rcell[i + 1] += rcell[i];
-    std::vector<float> recdata(recs.size() * 8, 0.f);
-    for (size_t i = 0; i < recs.size(); i++) {
-        const int f = recs[i].face;
-        for (int k = 0; k < 3; k++) {
-            recdata[8 * i + 2 * k] = h_verts[2 * h_faces[3 * f + k]];
-            recdata[8 * i + 2 * k + 1] = h_verts[2 * h_faces[3 * f + k] + 1];
+        // cell-major (all classes of a cell together: the kernel makes ONE pass over the candidates and keeps
+        // painter's order in per-class bitplanes); inside a cell by class, then by face
+        std::stable_sort(recs.begin(), recs.end(), [&](const Rec& a, const Rec& b) {
+            if (a.key != b.key) return a.key < b.key;
+            return h_face_class[a.face] < h_face_class[b.face];
+        });
+        cells.assign((size_t)nc + 1, 0);
+        for (const Rec& r : recs) cells[r.key + 1]++;
+        for (size_t i = 0; i + 1 < cells.size(); i++) cells[i + 1] += cells[i];
+        data.assign(recs.size() * 8, 0.f);
+        for (size_t i = 0; i < recs.size(); i++) {
+            const int f = recs[i].face;
+            for (int k = 0; k < 3; k++) {
+                data[8 * i + 2 * k] = h_verts[2 * h_faces[3 * f + k]];
+                data[8 * i + 2 * k + 1] = h_verts[2 * h_faces[3 * f + k] + 1];
+            }
+            const int meta = recs[i].own | ((int)h_face_class[f] << 8);
+            memcpy(&data[8 * i + 6], &meta, sizeof(int));
         }
-        const int meta = recs[i].own | ((int)h_face_class[f] << 8);
-        memcpy(&recdata[8 * i + 6], &meta, sizeof(int));
+        return (int32_t)recs.size();
+    };
+    std::vector<int32_t> rcell, rcell_all;
+    std::vector<float> recdata, recdata_all;
+    const int32_t n_recs = build_face_records(false, rcell, recdata);
+    if (strips.empty()) { rcell_all = rcell; recdata_all = recdata; }
+    else build_face_records(true, rcell_all, recdata_all);
+    // median length of the long side of a strip (vertex 0 -> vertex 1): the host side decides from it whether a
+    // strip is a handful of pixels at the requested zoom
+    d.strip_len = 0.f;
+    if (!strips.empty()) {
+        std::vector<float> len(strips.size());
+        for (size_t i = 0; i < strips.size(); i++) {
+            const float dx = h_verts[2 * strips[i].v[1]] - h_verts[2 * strips[i].v[0]];
+            const float dy = h_verts[2 * strips[i].v[1] + 1] - h_verts[2 * strips[i].v[0] + 1];
+            len[i] = std::sqrt(dx * dx + dy * dy);
+        }
+        std::nth_element(len.begin(), len.begin() + len.size() / 2, len.end());
+        d.strip_len = len[len.size() / 2];
     }
     // ---------------- offroad grid (bounding-box binning)
     d.ocs = offroad_cell;
@@ -246,7 +267,8 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     if (!(upload(recdata, &m->allocations[0], bytes) && upload(rcell, &m->allocations[1], bytes) &&
           upload(tri, &m->allocations[2], bytes) && upload(ocell, &m->allocations[3], bytes) &&
           upload(orec, &m->allocations[4], bytes) && upload(srecdata, &m->allocations[5], bytes) &&
-          upload(smeta, &m->allocations[6], bytes) && upload(scell, &m->allocations[7], bytes))) {
+          upload(smeta, &m->allocations[6], bytes) && upload(scell, &m->allocations[7], bytes) &&
+          upload(recdata_all, &m->allocations[8], bytes) && upload(rcell_all, &m->allocations[9], bytes))) {
         fail(TDS_ERR_CUDA, "map_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         tds_map_destroy(m);
         return nullptr;
@@ -259,8 +281,10 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     d.srec = (const float4*)m->allocations[5];
     d.smeta = (const uint32_t*)m->allocations[6];
     d.scell = (const int32_t*)m->allocations[7];
+    d.rec_all = (const float4*)m->allocations[8];
+    d.rcell_all = (const int32_t*)m->allocations[9];
     m->info.n_verts = nv; m->info.n_faces = nf;
-    m->info.raster_gx = d.rgx; m->info.raster_gy = d.rgy; m->info.raster_records = (int32_t)recs.size(); m->info.raster_strips = (int32_t)srecs.size();
+    m->info.raster_gx = d.rgx; m->info.raster_gy = d.rgy; m->info.raster_records = n_recs; m->info.raster_strips = (int32_t)srecs.size();
     m->info.offroad_gx = d.ogx; m->info.offroad_gy = d.ogy;
     m->info.raster_cell = raster_cell; m->info.offroad_cell = offroad_cell;
     m->info.min_x = minx; m->info.min_y = miny; m->info.max_x = maxx; m->info.max_y = maxy;

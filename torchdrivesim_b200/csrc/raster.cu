@@ -91,7 +91,8 @@ extern "C" void tds_raster_set_timing_events(void* start_event, void* stop_event
 
 extern "C" int64_t tds_raster_workspace_bytes(int32_t B, int32_t N, int32_t L, int32_t R) {
     if (B < 0 || N < 0 || L < 0 || R < 0) return -1;
-    return (int64_t)B * ws_env_bytes(3 * N + 2 * L + 2 * R) + 16;
+    // per-environment primitives | 32 bytes of work counters | the redo list of the LEAN kernels for up to B * N cameras
+    return (int64_t)B * ws_env_bytes(3 * N + 2 * L + 2 * R) + 32 + (int64_t)B * N * 4;
 }
 
 static void make_palette_dev(const tds_palette_t* palette, int N, int L, int R, PaletteDev& pal) {
@@ -120,8 +121,8 @@ static void make_palette_dev(const tds_palette_t* palette, int N, int L, int R, 
     if (R > 0) pal.dyn_mask = 0xffffffffu;     // extra rectangles carry arbitrary classes
 }
 
-// Library-owned scratch per (device, stream): the work counters of the persistent grids and the list of cameras a LEAN
-// kernel hands to the general one (up to one entry per camera).  Grown with cudaMalloc when a call has more cameras
+// Library-owned scratch per (device, stream) for calls with more cameras than agents (free cameras of Simulator.render):
+// the work counters of the persistent grids and the list of cameras a LEAN kernel hands to the general one.  Grown with cudaMalloc when a call has more cameras
 // than any before it on that stream - which cannot happen inside a CUDA graph capture: call once before capturing.
 static int raster_scratch(int64_t ncam, cudaStream_t st, int32_t** out) {
     struct Entry { int dev; cudaStream_t st; int32_t* ptr; int64_t cap; };
@@ -221,21 +222,30 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
     a.cam_tris = d_cam_tris; a.cam_cls = d_cam_tri_class; a.Tc = Tc;
     // Stage 1S plots every in-image vertex of a strip without asking whether its face is kept: that needs the image
     // (truncated coordinates in [0, res), i.e. pixel coordinates in (-1, res)) to lie inside the inner decision
-    // radius of the 1.05x view quad, r_in = 0.525 res - band >= res / 2 + 1 (make_camera).  Tiles of 44 pixels and
-    // more qualify at any zoom the band allows; below, strips are walked as four single faces.
+    // radius of the 1.05x view quad, r_in = 0.525 res - band >= res / 2 + 1 (make_camera): tiles of 44 pixels and
+    // more qualify at any zoom the band allows.  And it only pays while a typical strip is a handful of pixels - most
+    // strips are then finished by plotting their six vertices; at closer zoom every face of a strip is classified on
+    // its own anyway and the camera walks the plain face records of ALL faces instead (rec_all).
     {
         const float half = (float)res / 2.0f, band = 0.01f + 0.002f * (scale * half);
-        a.strip_mode = (0.525f * (float)res - band >= half + 1.001f) ? 1 : 0;
-        if (const char* e = getenv("TDS_RASTER_STRIPS")) a.strip_mode = a.strip_mode && atoi(e) != 0;
+        // measured (Town01, 35 m): 64x64 (0.9 px) 2.37 -> 2.11 ms with strips; 128x128 (1.8 px) 3.08 -> 3.33 ms; 256x256 2.04 -> 2.55 ms
+        float strip_px = 0.f;
+        for (int i = 0; i < n_maps; i++) strip_px = std::max(strip_px, set.m[i].strip_len * scale * half);
+        a.strip_mode = (0.525f * (float)res - band >= half + 1.001f && strip_px > 0.f && strip_px <= 1.4f) ? 1 : 0;
+        if (const char* e = getenv("TDS_RASTER_STRIPS"))
+            a.strip_mode = (atoi(e) != 0 && 0.525f * (float)res - band >= half + 1.001f) ? 1 : 0;
     }
     const int K = pal.n_classes;
     TDS_REQUIRE(K <= 31, "raster: at most 31 active classes (got %d)", K);
     // The LEAN kernels hold the common case only (see raster_kernel.cuh); whatever they cannot finish exactly they put
     // on a list, and the general kernel of the same shape renders those cameras again right behind them.
-    bool lean = a.strip_mode && Tc == 0 && a.agent_cls == nullptr && K <= 7;
+    bool lean = Tc == 0 && a.agent_cls == nullptr;
     if (const char* e = getenv("TDS_RASTER_LEAN")) lean = lean && atoi(e) != 0;
-    int32_t* scratch = nullptr;
-    if (int e = raster_scratch(ncam, st, &scratch)) return e;
+    // counters + redo list: the tail of the caller's workspace holds B * N cameras (one per agent, the egocentric case);
+    // more cameras than that take library-owned scratch memory
+    int32_t* scratch = reinterpret_cast<int32_t*>((uint8_t*)d_workspace + (int64_t)B * ws_env_bytes(T));
+    if (ncam > (int64_t)B * N)
+        if (int e = raster_scratch(ncam, st, &scratch)) return e;
     TDS_CUDA_OK(cudaMemsetAsync(scratch, 0, 8 * sizeof(int32_t), st));
     a.next_cam = scratch;              // work counter of the first launch
     a.redo = scratch + 4;              // [0] = count, [4 ..] = cameras

@@ -5,9 +5,9 @@ namespace tds_raster {
 
 template <int RES, int NS, bool SMALL>
 static int pick(const LaunchCfg& c, bool f32, bool lean) {
-    if (NS == 3 && lean) {
-        return f32 ? launch_variant(raster_kernel<128, RES, NS, SMALL, 0, true, NS == 3>, c, 1, 128, false)
-                   : launch_variant(raster_kernel<128, RES, NS, SMALL, 0, false, NS == 3>, c, 1, 128, false);
+    if (lean) {
+        return f32 ? launch_variant(raster_kernel<128, RES, NS, SMALL, 0, true, true>, c, 1, 128, false)
+                   : launch_variant(raster_kernel<128, RES, NS, SMALL, 0, false, true>, c, 1, 128, false);
     }
     return f32 ? launch_variant(raster_kernel<128, RES, NS, SMALL, 0, true, false>, c, 1, 128, false)
                : launch_variant(raster_kernel<128, RES, NS, SMALL, 0, false, false>, c, 1, 128, false);
@@ -20,8 +20,8 @@ int launch_g128(const LaunchCfg& c, bool f32, bool lean) {
         if (c.res == 256) return pick<256, 3, false>(c, f32, lean);
         return small ? pick<0, 3, true>(c, f32, lean) : pick<0, 3, false>(c, f32, lean);
     }
-    if (c.res == 128) return pick<128, 5, true>(c, f32, false);
-    return small ? pick<0, 5, true>(c, f32, false) : pick<0, 5, false>(c, f32, false);
+    if (c.res == 128) return pick<128, 5, true>(c, f32, lean);
+    return small ? pick<0, 5, true>(c, f32, lean) : pick<0, 5, false>(c, f32, lean);
 }
 
 }  // namespace tds_raster

@@ -6,9 +6,9 @@ namespace tds_raster {
 
 template <int G, int NS, bool SMALL>
 static int pick(const LaunchCfg& c, bool f32, bool lean) {
-    if (NS == 3 && lean) {
-        return f32 ? launch_variant(raster_kernel<G, 0, NS, SMALL, 0, true, NS == 3>, c, 1, G, false)
-                   : launch_variant(raster_kernel<G, 0, NS, SMALL, 0, false, NS == 3>, c, 1, G, false);
+    if (lean) {
+        return f32 ? launch_variant(raster_kernel<G, 0, NS, SMALL, 0, true, true>, c, 1, G, false)
+                   : launch_variant(raster_kernel<G, 0, NS, SMALL, 0, false, true>, c, 1, G, false);
     }
     return f32 ? launch_variant(raster_kernel<G, 0, NS, SMALL, 0, true, false>, c, 1, G, false)
                : launch_variant(raster_kernel<G, 0, NS, SMALL, 0, false, false>, c, 1, G, false);
@@ -20,8 +20,8 @@ int launch_g256(const LaunchCfg& c, int G, bool f32, bool lean) {
         if (G == 256) return small ? pick<256, 3, true>(c, f32, lean) : pick<256, 3, false>(c, f32, lean);
         return pick<512, 3, false>(c, f32, lean);
     }
-    if (G == 256) return small ? pick<256, 5, true>(c, f32, false) : pick<256, 5, false>(c, f32, false);
-    return pick<512, 5, false>(c, f32, false);
+    if (G == 256) return small ? pick<256, 5, true>(c, f32, lean) : pick<256, 5, false>(c, f32, lean);
+    return pick<512, 5, false>(c, f32, lean);
 }
 
 }  // namespace tds_raster

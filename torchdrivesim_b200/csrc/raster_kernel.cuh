@@ -290,7 +290,7 @@ struct RasterArgs {
     const float* cam_tris;     // [B*Nc][Tc][6] world-space triangles of each camera (waypoint discs), or NULL
     const int32_t* cam_cls;    // [B*Nc][Tc] their classes (< 0: skipped)
     int32_t Tc;
-    int32_t strip_mode;        // 1: strips take stage 1S; 0 (tiles below ~44 pixels): they are expanded to faces
+    int32_t strip_mode;        // 1: strips take stage 1S, the face segments hold the other faces; 0: the face segments hold all faces
     int32_t out_format;        // TDS_IMAGE_F32 / TDS_IMAGE_U8 / TDS_IMAGE_RANK
     const uint8_t* agent_cls;  // [B*Nc][N] class of each agent's rectangle as this camera sees it (custom colours), or NULL
     int32_t* redo;             // [0] = number of cameras in redo[4..]: LEAN kernels list the cameras they cannot finish
@@ -370,7 +370,7 @@ __device__ __forceinline__ void project2(const Camera& cam, uint64_t X, uint64_t
 #endif
 // NS = bits of the per-pixel draw rank (0 = background): 3 for up to 7 active classes, 5 for up to 31
 // KS = planes reserved per camera in static shared memory (64x64 warp-per-camera variants), 0 = dynamic shared memory
-// F32: float32 image (else uint8 RGB / draw ranks, a.out_format).  LEAN: the common case only - strips through stage 1S, no
+// F32: float32 image (else uint8 RGB / draw ranks, a.out_format).  LEAN: the common case only - no
 // per-camera triangles, no per-camera agent classes, and cameras that meet coordinates beyond +-8000 pixels are handed
 // to the general kernel through a.redo: code that is never executed still costs instruction-cache reach
 template <int G, int RES, int NS, bool SMALL, int KS_, bool F32, bool LEAN>
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         // runs with full warps.  Strips that need more than their vertices wait in a queue of their own until 8 of
         // them make a full warp of faces (4 lanes per strip).  The last iterations (seg > 2 nrows) only drain the queues.
         const int seg_dyn = 2 * nrows;
-        const int strip_rows = (LEAN || a.strip_mode) ? nrows : 0;      // segments below this one take stage 1S
+        const int strip_rows = nrows;                  // segments below this one take stage 1S (empty without strip mode)
         bool redo = false;                             // LEAN: something this kernel leaves to the general one
         int seg = -1, j0 = 0, seg_start = 0, seg_count = 0;
         int nq0 = 0, nq1 = 0, nq2 = 0;                 // fill levels of this warp's queues (uniform over the warp)
@@ -547,11 +547,12 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                     seg++;
                     j0 = 0;
                     if (seg < seg_dyn) {
+                        // without strip mode the strip segments are empty and the face segments hold EVERY face
                         const bool strips = seg < nrows;
-                        const int32_t* cell = (strips ? map.scell : map.rcell) + (r0 + (strips ? seg : seg - nrows)) * map.rgx;
+                        const int32_t* cell = (strips ? map.scell : (a.strip_mode ? map.rcell : map.rcell_all)) +
+                                              (r0 + (strips ? seg : seg - nrows)) * map.rgx;
                         seg_start = __ldg(cell + gc0);
-                        seg_count = __ldg(cell + gc1 + 1) - seg_start;
-                        if (!LEAN && strips && !a.strip_mode) seg_count *= 4;        // walked as 4 faces per strip
+                        seg_count = (strips && !a.strip_mode) ? 0 : __ldg(cell + gc1 + 1) - seg_start;
                     } else {
                         seg_start = 0;
                         seg_count = seg == seg_dyn ? dyn_count : 0;
@@ -679,20 +680,8 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                     // ================= stage 1F: one face per thread
                     float x0, y0, x1, y1, x2, y2;
                     int own = 7, cls;
-                    if (!LEAN && seg < nrows) {
-                        // strips walked face by face (tiles too small for stage 1S): face f of strip s = vertices f, f+1, f+2
-                        const int idx = seg_start + (jj >> 2), f = jj & 3;
-                        const float* fp = reinterpret_cast<const float*>(map.srec + (int64_t)(idx >> 5) * 96 + (idx & 31));
-                        const uint32_t meta = __ldg(map.smeta + idx);
-                        const int pc = (int)((meta >> 6) & 8191u), pr = (int)(meta >> 19);
-                        const bool dup = (meta & 32u) && pc >= gc0 && pc <= gc1 && pr >= r0 && pr < r0 + nrows;
-                        cls = dup ? 255 : (int)(meta & 31u);
-                        const int k0 = f, k1 = f + 1, k2 = f + 2;
-                        x0 = __ldg(fp + (k0 >> 1) * 128 + (k0 & 1)); y0 = __ldg(fp + (k0 >> 1) * 128 + 2 + (k0 & 1));
-                        x1 = __ldg(fp + (k1 >> 1) * 128 + (k1 & 1)); y1 = __ldg(fp + (k1 >> 1) * 128 + 2 + (k1 & 1));
-                        x2 = __ldg(fp + (k2 >> 1) * 128 + (k2 & 1)); y2 = __ldg(fp + (k2 >> 1) * 128 + 2 + (k2 & 1));
-                    } else if (seg < seg_dyn) {
-                        const float4* rp = map.rec + 2 * (int64_t)(seg_start + jj);
+                    if (seg < seg_dyn) {
+                        const float4* rp = (a.strip_mode ? map.rec : map.rec_all) + 2 * (int64_t)(seg_start + jj);
                         const float4 v01 = __ldg(rp);
                         const float4 v2o = __ldg(rp + 1);
                         x0 = v01.x; y0 = v01.y; x1 = v01.z; y1 = v01.w; x2 = v2o.x; y2 = v2o.y;

@@ -2,7 +2,7 @@
 // with eager torch ops between its hot functions, as single launches of our own.
 //
 //   tds_agent_boxes      state (x, y, psi, v) + size (l, w) -> collision boxes (x, y, l, w, psi)        simulator.py:1161-1170
-//                        (+ the (sin, cos) of every heading for the egocentric cameras,                    simulator.py:961, 1017)
+//                        (+ the position and the (sin, cos) of the heading of every agent = its egocentric camera,   simulator.py:961, 1017)
 //   tds_rollout_loss     acc += [sum collision, sum offroad, sum |xy - target|^2] of one step             imitation_learning.py:279-335
 //   tds_rollout_grad     d loss / d state of one step: the gradient that arrives from the next kinematic step
 //                        + offroad backward + collision backward (scattered from box layout) + the target term
@@ -16,12 +16,12 @@
 namespace {
 
 __global__ void __launch_bounds__(256) agent_boxes_kernel(const float4* __restrict__ state, const float2* __restrict__ size, int64_t n,
-                                                          float* __restrict__ box, float2* __restrict__ cam_sc) {
+                                                          float* __restrict__ box, float2* __restrict__ cam_sc, float2* __restrict__ xy) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 s = state[i];
-    const float2 z = size[i];
     if (box) {
+        const float2 z = size[i];
         float* o = box + 5 * i;
         o[0] = s.x; o[1] = s.y; o[2] = z.x; o[3] = z.y; o[4] = s.z;
     }
@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) agent_boxes_kernel(const float4* __restri
         tds::sincos_cr(s.z, sn, cs);
         cam_sc[i] = make_float2(sn, cs);
     }
+    if (xy) xy[i] = make_float2(s.x, s.y);
 }
 
 // ONE CTA, fixed reduction order (reproducible sums), like tds_infraction_metrics
@@ -95,12 +96,14 @@ __global__ void __launch_bounds__(256) rollout_grad_kernel(const float4* __restr
 
 }  // namespace
 
-extern "C" int tds_agent_boxes(const float* d_state, const float* d_size, int64_t n, float* d_box, float* d_cam_sc, void* stream) {
+extern "C" int tds_agent_boxes(const float* d_state, const float* d_size, int64_t n, float* d_box, float* d_cam_sc, float* d_xy,
+                               void* stream) {
     TDS_REQUIRE(n >= 0, "agent_boxes: negative n");
     if (n == 0) return TDS_OK;
-    TDS_REQUIRE(d_state && (d_box == nullptr || d_size) && (d_box || d_cam_sc), "agent_boxes: null pointer");
+    TDS_REQUIRE(d_state && (d_box == nullptr || d_size) && (d_box || d_cam_sc || d_xy), "agent_boxes: null pointer");
     agent_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(d_state), reinterpret_cast<const float2*>(d_size), n, d_box, reinterpret_cast<float2*>(d_cam_sc));
+        reinterpret_cast<const float4*>(d_state), reinterpret_cast<const float2*>(d_size), n, d_box, reinterpret_cast<float2*>(d_cam_sc),
+        reinterpret_cast<float2*>(d_xy));
     TDS_LAUNCH_OK();
     return TDS_OK;
 }

@@ -24,6 +24,12 @@ struct MapDev {
     const float4* srec;
     const uint32_t* smeta;
     const int32_t* scell;           // [rgx * rgy + 1] CSR offsets into srec / smeta (in strips)
+    // rec / rcell hold the faces that are NOT part of a strip; rec_all / rcell_all hold every face in the same record
+    // format: what a camera walks when strips do not pay (large tiles / close zoom, where no strip is a handful of
+    // pixels and every face of a strip would have to be classified on its own anyway).
+    const float4* rec_all;
+    const int32_t* rcell_all;
+    float strip_len;                // median length (metres) of the long side of the strips, 0 without strips
     float rx0, ry0, rcs, rinv;
     int32_t rgx, rgy, n_slots;
     int32_t slot_of_class[TDS_MAX_CLASSES];   // -1: the map has no face of that class
@@ -45,7 +51,7 @@ struct MapSetDev {
 struct tds_map {
     tds::MapDev dev;
     tds_map_info_t info;
-    void* allocations[8];
+    void* allocations[10];
     int device;
 };
 

@@ -49,19 +49,29 @@ class WaypointGoal:
         """Both of the above from one launch."""
         return self._gather(count)
 
-    def step(self, agent_states: Tensor, time: int = 0, threshold: float = 2.0) -> None:
-        """goals.py:159-172.  `mask` and `state` are replaced by updated copies, as in the reference."""
+    def step(self, agent_states: Tensor, time: int = 0, threshold: float = 2.0, in_place: bool = False) -> None:
+        """goals.py:159-172.  `mask` and `state` are replaced by updated copies, as in the reference; with `in_place`
+        the existing tensors are updated instead (they must be a contiguous bool / uint8 mask and a contiguous int64
+        state): what a CUDA graph needs, which reads and writes fixed buffers (GraphedHotPath)."""
         lib = _lib.load()
         st = _lib.as_f32(agent_states)
         B, A, N, M = self.waypoints.shape[:4]
         if st.dim() != 3 or st.shape[0] != B or st.shape[1] != A or st.shape[-1] != 4:
             raise _lib.TdsError("agent_states must be [B,A,4] with the batch and agent counts of the waypoints")
-        mask = _lib.as_u8(self.mask).clone()
-        state = self.state.to(torch.int64).contiguous().clone()
+        if in_place:
+            if self.mask.dtype not in (torch.bool, torch.uint8) or not self.mask.is_contiguous() or \
+                    self.state.dtype != torch.int64 or not self.state.is_contiguous():
+                raise _lib.TdsError("WaypointGoal.step(in_place=True) needs a contiguous bool mask and a contiguous int64 state")
+            mask = self.mask.view(torch.uint8) if self.mask.dtype == torch.bool else self.mask
+            state = self.state
+        else:
+            mask = _lib.as_u8(self.mask).clone()
+            state = self.state.to(torch.int64).contiguous().clone()
         _lib.check(lib.tds_waypoint_step(_lib.ptr(st), _lib.ptr(_lib.as_f32(self.waypoints)), _lib.ptr(mask), _lib.ptr(state),
                                          B * A, N, M, float(threshold), _lib.stream_ptr(st.device)))
-        self.mask = mask.view(torch.bool)
-        self.state = state
+        if not in_place:
+            self.mask = mask.view(torch.bool)
+            self.state = state
 
     # ---- batch plumbing (goals.py:107-157) -------------------------------------------------------
     def copy(self):

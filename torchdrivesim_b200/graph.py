@@ -5,7 +5,12 @@ offroad) into a CUDA graph over static buffers and replays it with new actions. 
 our kernels plus a dozen tiny torch kernels; replaying a graph removes the eager-mode launch gaps between
 them (the reference has no equivalent: it is eager PyTorch + a Python loop per triangle).
 
-Inference-only (no autograd tape is recorded); use the eager `Simulator` methods for differentiable rollouts.
+Inference-only (no autograd tape is recorded); differentiable rollouts have their own graph (`FusedRollout`).
+
+A graph reads and writes FIXED buffers.  Everything the step reads is therefore moved into buffers this class owns
+(traffic-control states, NPC states, waypoint-goal masks and states) and refreshed in place; tensors the caller swaps
+into the simulator afterwards (`update_present_mask`, a new `waypoint_goals.mask`) are invisible to the graph - update
+`sim.present_mask` / the goal buffers in place (`.copy_`) instead.
 """
 from typing import Optional, Tuple
 
@@ -45,6 +50,12 @@ class GraphedHotPath:
             self._npc_state = sim.npc_controller.npc_state.detach().to(torch.float32).clone()
             self._npc_present = sim.npc_controller.npc_present_mask.detach().clone()
             sim.npc_controller.npc_state, sim.npc_controller.npc_present_mask = self._npc_state, self._npc_present
+        # ... and the waypoint goals: their step (simulator.py:860-861) is part of the graph and updates these in place
+        self._goals = sim.waypoint_goals
+        if self._goals is not None:
+            self._goals.mask = self._goals.mask.to(torch.bool).contiguous().clone()
+            self._goals.state = self._goals.state.to(torch.int64).contiguous().clone()
+            self._goal_saved = (self._goals.mask.clone(), self._goals.state.clone())
         sim.kinematic_model.set_state(self.state)
         # warm up on a side stream (allocator, lazily built map handles), then capture
         s = torch.cuda.Stream(device=dev)
@@ -55,11 +66,17 @@ class GraphedHotPath:
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        self.state.copy_(saved)
+        self._restore(saved)
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self._body()
+        self._restore(saved)
+
+    def _restore(self, saved: Tensor) -> None:
         self.state.copy_(saved)
+        if self._goals is not None:
+            self._goals.mask.copy_(self._goal_saved[0])
+            self._goals.state.copy_(self._goal_saved[1])
 
     def _body(self) -> None:
         sim = self.sim
@@ -67,6 +84,8 @@ class GraphedHotPath:
         sim.kinematic_model.step(self.action)        # Simulator.step minus the host-side control / NPC stepping
         self.state.copy_(sim.get_state())           # the graph chains steps through this static buffer
         sim.kinematic_model.set_state(self.state)
+        if self._goals is not None:
+            self._goals.step(self.state, sim.internal_time, threshold=sim.cfg.waypoint_removal_threshold, in_place=True)
         if self._render:
             sim.render_egocentric(res=self._res, fov=self._fov, out=self.images)
         self.collision.copy_(sim.compute_collision())

@@ -240,8 +240,12 @@ class B200BirdviewMeshGenerator:
             for _ in range(n - 1):
                 verts.append(torch.matmul(rot, verts[-1].unsqueeze(-1)).squeeze(-1))
             faces = torch.tensor([[0, k, k + 1] for k in range(1, n)] + [[0, n, 1]], dtype=torch.long)
-            self._disc_cache = (key, torch.cat(verts, 0), faces)
-        return self._disc_cache[1].to(device), self._disc_cache[2].to(device)
+            self._disc_cache = (key, torch.cat(verts, 0), faces, {})
+        # one copy per device, made on first use (a host -> device copy cannot be part of a CUDA graph capture)
+        on_dev = self._disc_cache[3]
+        if str(device) not in on_dev:
+            on_dev[str(device)] = (self._disc_cache[1].to(device), self._disc_cache[2].to(device))
+        return on_dev[str(device)]
 
     def _waypoint_triangles(self, num_cameras: int, waypoints: Tensor, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
         """waypoints [B,Nc,M,2] (+ mask [B,Nc,M]) -> world-space triangles [B,Nc,M*n,3,2] and their class ids.  A disc

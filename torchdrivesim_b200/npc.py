@@ -214,7 +214,11 @@ class ReplayController(NPCController):
 
 
 def _advance(ctrl: NPCController, spawn: SpawnController, replay: bool) -> None:
-    """One launch: replay gather (optional), despawn outside the exit boundary, spawn (tds_npc_advance)."""
+    """One launch: replay gather (optional), despawn outside the exit boundary, spawn (tds_npc_advance).
+    Two deliberate differences from the reference: the NPC states are float32 (the kernel's arithmetic type; a float64
+    log is narrowed), and the spawn / despawn edits land on `ctrl` itself - the reference's SpawnController writes to
+    `simulator.npc_controller` (simulator.py:71-85), which is the same object except inside a CompoundNPCController,
+    where its edits are overwritten by the gather that follows anyway."""
     lib = _lib.load()
     state = _lib.as_f32(ctrl.npc_state)
     if state.dim() != 3 or state.shape[-1] != 4:

@@ -151,7 +151,7 @@ class _AgentBoxes(torch.autograd.Function):
         z = _lib.as_f32(size[..., :2])
         n = s[..., 0].numel()
         box = torch.empty(s.shape[:-1] + (5,), dtype=torch.float32, device=s.device)
-        _lib.check(lib.tds_agent_boxes(_lib.ptr(s), _lib.ptr(z), n, _lib.ptr(box), None, _lib.stream_ptr(s.device)))
+        _lib.check(lib.tds_agent_boxes(_lib.ptr(s), _lib.ptr(z), n, _lib.ptr(box), None, None, _lib.stream_ptr(s.device)))
         ctx.meta = (state.shape, size.shape)
         return box
 
@@ -173,14 +173,20 @@ def agent_boxes(state: torch.Tensor, size: torch.Tensor) -> torch.Tensor:
     return _AgentBoxes.apply(state, size)
 
 
-def heading_sincos(state: torch.Tensor) -> torch.Tensor:
-    """state [...,4] -> [...,2] = (sin psi, cos psi) evaluated like every other heading of the path (float64, rounded):
-    the egocentric camera orientation of render_egocentric (simulator.py:961, 1017).  Not differentiable."""
+def egocentric_cameras(state: torch.Tensor):
+    """state [...,4] -> (xy [...,2] contiguous, (sin psi, cos psi) [...,2]): the camera of every agent in one launch, the
+    heading evaluated like every other heading of the path (float64, rounded) - render_egocentric, simulator.py:961,
+    1017.  Not differentiable."""
     lib = _lib.load()
     s = _lib.as_f32(state)
-    out = torch.empty(s.shape[:-1] + (2,), dtype=torch.float32, device=s.device)
-    _lib.check(lib.tds_agent_boxes(_lib.ptr(s), None, s[..., 0].numel(), None, _lib.ptr(out), _lib.stream_ptr(s.device)))
-    return out
+    xy = torch.empty(s.shape[:-1] + (2,), dtype=torch.float32, device=s.device)
+    sc = torch.empty_like(xy)
+    _lib.check(lib.tds_agent_boxes(_lib.ptr(s), None, s[..., 0].numel(), None, _lib.ptr(sc), _lib.ptr(xy), _lib.stream_ptr(s.device)))
+    return xy, sc
+
+
+def heading_sincos(state: torch.Tensor) -> torch.Tensor:
+    return egocentric_cameras(state)[1]
 
 
 # ------------------------------------------------------------------------------------ traffic lights

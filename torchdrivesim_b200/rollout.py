@@ -98,7 +98,7 @@ class FusedRollout:
             s0, s1 = self.state[t], self.state[t + 1]
             _lib.check(lib.tds_kinematic_step_fwd(p(s0), p(self.actions[t]), 2, p(self.lr), p(self.model), self.uniform_model, n,
                                                   ctypes.byref(self.params), p(s1), st))
-            _lib.check(lib.tds_agent_boxes(p(s1), p(self.size), n, p(self.box[t]), None, st))
+            _lib.check(lib.tds_agent_boxes(p(s1), p(self.size), n, p(self.box[t]), None, None, st))
             _lib.check(lib.tds_collision_allpairs_fwd(p(self.box[t]), p(self.box[t]), p(self.present), B, A, A, self.metric, 1,
                                                       p(self.collision), p(self.argmax[t]), st))
             _lib.check(lib.tds_offroad_fwd(self.handles, self.n_maps, p(self.env_map), p(s1), p(self.size), p(self.present), B, A,

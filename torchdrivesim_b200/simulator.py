@@ -277,12 +277,13 @@ class Simulator:
     def render(self, camera_xy: Tensor, camera_psi: Tensor, res: Optional[Resolution] = None,
                rendering_mask: Optional[Tensor] = None, fov: Optional[float] = None, out: Optional[Tensor] = None,
                waypoints: Optional[Tensor] = None, waypoints_rendering_mask: Optional[Tensor] = None,
-               custom_agent_colors: Optional[Tensor] = None, dtype=None) -> Tensor:
+               custom_agent_colors: Optional[Tensor] = None, dtype=None, camera_sc: Optional[Tensor] = None) -> Tensor:
         """camera_xy BxNx2, camera_psi BxNx1 -> BxNx3xHxW (simulator.py:920-992); waypoints BxNxMx2 and their
         BxNxM mask draw goal-waypoint discs for the camera they belong to; custom_agent_colors BxNxAllx3 in [0,1]
         is the colour of each agent in each camera.  dtype: torch.float32 (default, the reference's image),
         torch.uint8 (the same values, 4x fewer bytes) or 'rank' (BxNxHxW draw ranks, see `renderer.rank_table`)."""
-        camera_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
+        if camera_sc is None:           # (sin, cos) of the camera orientation; the egocentric path hands it in
+            camera_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
         if camera_xy.dim() == 2:
             camera_xy, camera_sc = camera_xy.unsqueeze(1), camera_sc.unsqueeze(1)
         n_cameras = camera_xy.shape[-2]
@@ -291,10 +292,14 @@ class Simulator:
         return img.reshape((self.batch_size, n_cameras) + img.shape[1:])
 
     def _egocentric_cameras(self, ego_rotate: bool, visibility_matrix: Optional[Tensor], n_subsequent_waypoints: int):
+        """Camera position, orientation and (sin, cos) of every controlled agent: one launch of ours instead of the
+        slice + sin + cos + cat of simulator.py:1008-1017 (the heading is evaluated like every other heading of the path)."""
         state = self.get_state().detach()
-        camera_xy, camera_psi = state[..., :2], state[..., 2:3]
+        camera_psi = state[..., 2:3]
+        camera_xy, camera_sc = ops.egocentric_cameras(state)
         if not ego_rotate:
             camera_psi = torch.ones_like(camera_psi) * (math.pi / 2)
+            camera_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
         rendering_mask = visibility_matrix
         if self.cfg.single_agent_rendering:
             rendering_mask = torch.eye(self.agent_count, dtype=torch.bool, device=state.device).unsqueeze(0).expand(
@@ -302,7 +307,7 @@ class Simulator:
         waypoints = waypoints_mask = None
         if self.waypoint_goals is not None:
             waypoints, waypoints_mask = self.waypoint_goals.get_waypoints_and_masks(count=n_subsequent_waypoints)
-        return camera_xy, camera_psi, rendering_mask, waypoints, waypoints_mask
+        return camera_xy, camera_psi, camera_sc, rendering_mask, waypoints, waypoints_mask
 
     def render_egocentric(self, ego_rotate: bool = True, res: Optional[Resolution] = None, fov: Optional[float] = None,
                           visibility_matrix: Optional[Tensor] = None, out: Optional[Tensor] = None,
@@ -311,11 +316,11 @@ class Simulator:
         """One camera per agent -> BxAx3xHxW (simulator.py:994-1033); with waypoint goals every agent sees the discs of
         its next `n_subsequent_waypoints` collections; custom_agent_colors BxAxAllx3: the colours agents see each
         other as."""
-        camera_xy, camera_psi, rendering_mask, waypoints, waypoints_mask = self._egocentric_cameras(
+        camera_xy, camera_psi, camera_sc, rendering_mask, waypoints, waypoints_mask = self._egocentric_cameras(
             ego_rotate, visibility_matrix, n_subsequent_waypoints)
         return self.render(camera_xy, camera_psi, rendering_mask=rendering_mask, res=res, fov=fov, out=out,
                            waypoints=waypoints, waypoints_rendering_mask=waypoints_mask,
-                           custom_agent_colors=custom_agent_colors, dtype=dtype)
+                           custom_agent_colors=custom_agent_colors, dtype=dtype, camera_sc=camera_sc)
 
     def render_egocentric_to_host(self, host_out: Tensor, chunk_envs: int = 128, res: Optional[Resolution] = None,
                                   fov: Optional[float] = None, ego_rotate: bool = True,
@@ -328,7 +333,7 @@ class Simulator:
         the previous chunk is copied out on a side stream, so the transfer overlaps the raster kernel.  Returns
         `host_out` (valid once the current stream is synchronised)."""
         res = self.renderer.res if res is None else res
-        camera_xy, camera_psi, rendering_mask, waypoints, waypoints_mask = self._egocentric_cameras(
+        camera_xy, camera_psi, cam_sc, rendering_mask, waypoints, waypoints_mask = self._egocentric_cameras(
             ego_rotate, visibility_matrix, n_subsequent_waypoints)
         dev = camera_xy.device
         B, A = camera_xy.shape[0], camera_xy.shape[1]
@@ -339,7 +344,6 @@ class Simulator:
             raise _lib.TdsError("host_out must be a pinned tensor: float32 / uint8 [B,A,3,H,W] or uint8 [B,A,H,W] (draw ranks)")
         dtype = 'rank' if rank else host_out.dtype
         cam_xy = camera_xy.contiguous()
-        cam_sc = torch.cat([torch.sin(camera_psi), torch.cos(camera_psi)], dim=-1)
         scene = self._scene(cam_xy, rendering_mask, waypoints, waypoints_mask, custom_agent_colors)
         chunk = max(1, min(chunk_envs, B))
         key = ((chunk, A) + tail, host_out.dtype)
@@ -403,24 +407,23 @@ class Simulator:
 
     def compute_traffic_lights_violations(self) -> Tensor:
         """simulator.py:1046-1062: which agents run a red light (TrafficLightControl.compute_violation) times the
-        present mask; boolean BxA."""
+        present mask: BxA in the dtype of the state, 1.0 = violation (`violation * present.to(state.dtype)` there)."""
         state = self.get_state()
         tl = self.traffic_controls.get('traffic_light') if self.traffic_controls is not None else None
         if tl is None:
-            return torch.zeros(state.shape[0], state.shape[1], dtype=torch.bool, device=state.device)
-        box = torch.cat([state[..., :2], self.get_agent_size()[..., :2], state[..., 2:3]], dim=-1)
+            return torch.zeros(state.shape[0], state.shape[1], dtype=state.dtype, device=state.device)
+        box = ops.agent_boxes(state.detach(), self.get_agent_size()[..., :2])
         return ops.traffic_light_violation(box, tl.corners, tl.state, tl.allowed_states.index('red'),
-                                           tl.violation_rear_factor, present=self.get_present_mask())
+                                           tl.violation_rear_factor, present=self.get_present_mask()).to(state.dtype)
 
     def compute_collision(self) -> Tensor:
         """simulator.py:1161-1194 for the `discs` and `iou` metrics, all agents in one launch."""
         state, size = self.get_state(), self.get_agent_size()[..., :2]
-        box = torch.cat([state[..., :2], size, state[..., 2:3]], dim=-1)
-        if box.shape[-2] == 0:
-            return torch.zeros_like(box[..., 0])
+        if state.shape[-2] == 0:
+            return torch.zeros_like(state[..., 0])
+        box = ops.agent_boxes(state, size)
         metric = _lib.METRIC_IOU if self.cfg.collision_metric == CollisionMetric.iou else _lib.METRIC_DISCS
         all_box = box
         if self.npc_count > 0:
-            all_state, all_size = self.get_all_agent_state(), self.get_all_agent_size()[..., :2]
-            all_box = torch.cat([all_state[..., :2], all_size, all_state[..., 2:3]], dim=-1)
+            all_box = ops.agent_boxes(self.get_all_agent_state(), self.get_all_agent_size()[..., :2])
         return ops.collision_allpairs(box, all_box, self.get_all_agent_present_mask(), metric, ego_is_prefix=True)

@@ -1,14 +1,18 @@
-"""Traffic-light schedules: the finite state machines of the reference (torchdrivesim/traffic_lights.py:27-300) that
-cycle groups of lights through timed states, read from `{map}_traffic_light_controller.json`.
+"""Traffic-light schedules as tables.
 
-The reference ticks these Python objects on the host every step and rebuilds a state tensor from a dict.  Here the
-schedule is unrolled ONCE on the host (`TrafficLightController.unroll`) into the `replay_states` tensor of a
-`TrafficLightControl`, so that stepping the lights during a rollout is the device-side gather of
-`BaseTrafficControl.step` - no host work, no synchronisation, capturable in a CUDA graph.
-Same tick arithmetic as the reference (Python floats), so the unrolled states equal what `tick(dt)` produces.
+The reference drives the lights of a map with one Python state machine per group of lights
+(torchdrivesim/traffic_lights.py:27-300, read from `{map}_traffic_light_controller.json`), ticked on the host every
+step, and rebuilds the state tensor of `TrafficLightControl` from a dict afterwards.  Here a schedule is three arrays
+per map - duration and successor of every (group, phase) and the phase each light shows - advanced in one pass over the groups, and normally not advanced during a rollout at all: `unroll` tabulates the states of the next T steps
+once, and that table is the `replay_states` of a `TrafficLightControl`, stepped by a device-side gather
+(`BaseTrafficControl.step`): no host work per step, no synchronisation, capturable in a CUDA graph.
+
+The countdown arithmetic is the reference's (Python floats: `remaining -= dt` accumulates its rounding exactly as
+there), so the tabulated states equal what its `tick(dt)` produces, tick for tick (tests/golden/light_schedule.npz).
+`unroll_controller` tabulates any object with the reference's interface (`tick(dt)`, `current_state_with_name`), e.g.
+the reference's own `TrafficLightController`.
 """
 import json
-from dataclasses import dataclass
 from typing import Dict, List, Sequence, Tuple
 
 import torch
@@ -16,100 +20,96 @@ import torch
 LIGHT_STATES = ("none", "green", "yellow", "red")            # TrafficLightState, traffic_lights.py:16-20
 
 
-@dataclass
-class TrafficLightGroupState:
-    actor_states: Dict[str, str]        # actor id -> state name
-    sequence_number: int
-    duration: float                     # seconds
-    next_state: int
-
-
-class TrafficLightStateMachine:
-    """One group of lights (traffic_lights.py:37-157)."""
-
-    def __init__(self, group_states: List[TrafficLightGroupState]):
-        self._states = group_states
-        self.set_to(0, group_states[0].duration)       # the reference starts from a RANDOM state (reset); call set_to
-
-    def set_to(self, state_index: int, time_remaining: float) -> None:
-        state = min(max(int(state_index), 0), len(self._states) - 1)
-        self._current_state = self._states[state]
-        self._duration = self._current_state.duration
-        self._time_remaining = time_remaining if time_remaining <= self._duration else self._duration
-
-    def tick(self, dt: float) -> None:
-        self._time_remaining -= dt
-        while self._time_remaining <= 0:
-            next_state = self._current_state.next_state
-            next_duration = self._states[next_state].duration
-            if self._time_remaining == 0:
-                self.set_to(next_state, next_duration)
-                break
-            elif self._time_remaining + next_duration > 0:
-                self._time_remaining += next_duration
-                self.set_to(next_state, self._time_remaining)
-                break
-            else:
-                self._time_remaining += next_duration
-                self._current_state = self._states[next_state]
-
-    @property
-    def states(self) -> List[TrafficLightGroupState]:
-        return self._states
-
-    @property
-    def current_state(self) -> TrafficLightGroupState:
-        return self._current_state
-
-    @property
-    def time_remaining(self) -> float:
-        return self._time_remaining
+def unroll_controller(controller, traffic_light_ids: Sequence[int], dt: float, steps: int,
+                      allowed_states: Sequence[str] = ("red", "yellow", "green")) -> torch.Tensor:
+    """[L, steps] int64: the state index of every light before tick 0, 1, ..., steps-1 of `controller` (which is
+    advanced by steps - 1 ticks).  Works on this module's `TrafficLightController` and on the reference's."""
+    allowed = list(allowed_states)
+    cols = []
+    for t in range(steps):
+        names = controller.current_state_with_name
+        cols.append(torch.tensor([allowed.index(names[str(i)]) for i in traffic_light_ids]))
+        if t + 1 < steps:
+            controller.tick(dt)
+    return torch.stack(cols, dim=-1)
 
 
 class TrafficLightController:
-    """All groups of a map (traffic_lights.py:159-292)."""
+    """The schedule of one map: G groups, group g cycling through its phases.
 
-    def __init__(self, traffic_fsms: List[TrafficLightStateMachine]):
-        self.traffic_fsms = traffic_fsms
+    duration[g][p], successor[g][p]  seconds and next phase of phase p of group g (traffic_lights.py:27-35);
+    lights[g][p]                     {light id: state name} shown during that phase;
+    phase[g], remaining[g]           the running state: current phase and seconds left in it.
+    """
+
+    def __init__(self, duration: List[List[float]], successor: List[List[int]], lights: List[List[Dict[str, str]]],
+                 sequence_number: List[List[int]] = None):
+        self.duration = [list(map(float, d)) for d in duration]
+        self.successor = [list(map(int, s)) for s in successor]
+        self.lights = lights
+        self.sequence_number = sequence_number or [list(range(len(d))) for d in duration]
+        # the reference starts every group from a RANDOM phase (reset); here: phase 0 with its full duration; use set_to
+        self.phase = [0 for _ in self.duration]
+        self.remaining = [d[0] for d in self.duration]
 
     @classmethod
     def from_json(cls, json_file_path: str) -> "TrafficLightController":
+        """[[{"actor_states": {id: name}, "state": k, "duration": s, "next_state": j}, ...] per group] (traffic_lights.py:181-205)."""
         with open(json_file_path, "rb") as f:
-            items = json.load(f)
+            groups = json.load(f)
         try:
-            return cls([TrafficLightStateMachine([
-                TrafficLightGroupState(actor_states={k: str(v) for k, v in gs["actor_states"].items()},
-                                       sequence_number=int(gs["state"]), duration=float(gs["duration"]),
-                                       next_state=int(gs["next_state"])) for gs in sm]) for sm in items])
+            return cls(duration=[[float(p["duration"]) for p in g] for g in groups],
+                       successor=[[int(p["next_state"]) for p in g] for g in groups],
+                       lights=[[{str(k): str(v) for k, v in p["actor_states"].items()} for p in g] for g in groups],
+                       sequence_number=[[int(p["state"]) for p in g] for g in groups])
         except KeyError as e:
             raise ValueError(f"KeyError: {e} in {json_file_path}")
 
+    # ---- the countdown (traffic_lights.py:107-135), all groups ------------------------------------------------
+    def _enter(self, g: int, phase: int, remaining: float) -> None:
+        phase = min(max(int(phase), 0), len(self.duration[g]) - 1)
+        self.phase[g] = phase
+        self.remaining[g] = min(remaining, self.duration[g][phase])
+
     def tick(self, dt: float) -> None:
-        for fsm in self.traffic_fsms:
-            fsm.tick(dt)
+        for g in range(len(self.phase)):
+            left = self.remaining[g] - dt
+            phase = self.phase[g]
+            # a phase that has run out hands its deficit to its successors until one of them outlasts it; a countdown
+            # that lands on exactly zero starts the successor with its full duration
+            while left <= 0:
+                nxt = self.successor[g][phase]
+                if left == 0:
+                    phase, left = nxt, self.duration[g][nxt]
+                    break
+                left += self.duration[g][nxt]
+                phase = nxt
+            self.phase[g], self.remaining[g] = phase, left
 
     def set_to(self, light_states: Sequence[Tuple[float, float]]) -> None:
-        """[(state index, time remaining)] per group (traffic_lights.py:240-244)."""
-        for fsm, (state, time_remaining) in zip(self.traffic_fsms, light_states):
-            fsm.set_to(int(state), time_remaining)
+        """[(phase, seconds remaining)] per group (traffic_lights.py:240-244)."""
+        for g, (phase, remaining) in enumerate(light_states):
+            if g < len(self.phase):
+                self._enter(g, int(phase), remaining)
 
+    # ---- queries ----------------------------------------------------------------------------------------------
     @property
     def state_per_machine(self) -> List[int]:
-        return [fsm.current_state.sequence_number for fsm in self.traffic_fsms]
+        return [self.sequence_number[g][p] for g, p in enumerate(self.phase)]
 
     @property
     def time_remaining(self) -> List[float]:
-        return [fsm.time_remaining for fsm in self.traffic_fsms]
+        return list(self.remaining)
 
     @property
     def current_state_with_name(self) -> Dict[str, str]:
         out: Dict[str, str] = {}
-        for fsm in self.traffic_fsms:
-            out.update(fsm.current_state.actor_states)
+        for g, p in enumerate(self.phase):
+            out.update(self.lights[g][p])
         return out
 
     def get_number_of_light_groups(self) -> int:
-        return len(self.traffic_fsms)
+        return len(self.phase)
 
     def current_state_tensor(self, traffic_light_ids: Sequence[int], allowed_states: Sequence[str] = ("red", "yellow", "green")) -> torch.Tensor:
         """current_light_state_tensor_from_controller (traffic_lights.py:295-301): index of every light's state in the
@@ -122,9 +122,4 @@ class TrafficLightController:
         """[L, steps] int64: the state of every light before tick 0, 1, ..., steps-1 from the controller's current
         state on (the controller itself is advanced by steps - 1 ticks).  Feed it to
         `TrafficLightControl(pos, replay_states=unrolled[None].expand(B, -1, -1))`."""
-        cols = []
-        for t in range(steps):
-            cols.append(self.current_state_tensor(traffic_light_ids, allowed_states))
-            if t + 1 < steps:
-                self.tick(dt)
-        return torch.stack(cols, dim=-1)
+        return unroll_controller(self, traffic_light_ids, dt, steps, allowed_states)
