@@ -22,6 +22,10 @@ def boxes(B, A, span):
 
 
 def timed(name, fn, n=5):
+    if os.environ.get("TDS_PROFILE_ONCE"):      # under `ncu --set full`: every workload once
+        fn()
+        torch.cuda.synchronize()
+        return
     for _ in range(2):
         fn()
     torch.cuda.synchronize()

@@ -73,6 +73,7 @@ def test_golden_reference_images():
     ("carla_Town02", 320, 70.0, 0, 0.1, True),
     ("carla_Town10HD", 64, 35.0, 3, 0.1, True),      # a map built from its lanelet2 OSM file (joint lane markings)
     ("carla_Town10HD", 128, 60.0, 0, 0.0, True),
+    ("carla_Town01", 512, 70.0, 0, 0.0, False),      # beyond the 448 pixels of round 1 (the planes of 5 classes still fit an SM)
 ])
 def test_vs_oracle_random_scenes(mapname, res, fov, ped_every, absent_p, lights):
     rng = np.random.default_rng(res * 7 + int(fov))
@@ -304,27 +305,30 @@ def test_custom_agent_colours_and_static_meshes_golden():
 
 
 def test_dense_scene_unlisted_dynamic_branch():
-    """BASELINE config 4 density: more than kCullCap = 128 dynamic primitives reach one view quad, so the kernel walks
-    ALL agents instead of its per-camera list (20 % of them absent, which that branch must skip itself); 256x256."""
-    rng = np.random.default_rng(44)
+    """BASELINE config 4 density.  A camera lists the dynamic primitives that reach its view quad - up to 128 (warp per
+    camera) or 512 (CTA per camera); beyond that it walks ALL agents instead (20 % of them absent, which that branch must
+    skip itself).  260 agents in one view: listed at 256x256, unlisted at 64x64; 700 agents: unlisted at 128x128 too."""
     m = util.load_map_np("carla_Town01")
-    B, A = 2, 260
-    state, size, types, present = util.random_scene(m, B, A, rng, spread=9.0, ped_every=5, absent_p=0.2)
-    present[:, 0] = [True, False]
-    cams = [(b, c) for b in range(B) for c in range(8)]
-    # cameras on the 8 agents nearest to the middle of the crowd
-    near = np.argsort(np.abs(state[..., :2] - np.median(state[..., :2], axis=1, keepdims=True)).max(-1), axis=1)[:, :8]
-    cam_xy = np.take_along_axis(state[..., :2], near[..., None], 1).copy()
-    cam_sc = _sincos_torch(np.take_along_axis(state[..., 2], near, 1))
-    # how many agents does a camera see?  (35 m view: everything within ~17 m)
-    d = np.abs(state[:, None, :, :2] - cam_xy[:, :, None, :]).max(-1)
-    assert ((d < 15.0) & present[:, None, :]).sum(-1).min() > 130
     names = ["vehicle", "pedestrian"]
-    for res, fov in ((256, 35.0), (64, 35.0)):
-        img = _gpu_render(["carla_Town01"], None, state, size, types, present, names, None, None, cam_xy, cam_sc, res, fov)
-        ora = util.oracle_render_batch(m, state, size, types, present, names, None, None, cam_xy, cam_sc, res, fov, cams=cams)
-        bad = sum(int((img[b, c] != o).any(0).sum()) for (b, c), o in ora.items())
-        assert bad == 0, f"res {res}: {bad} mismatching pixels over {len(ora)} cameras"
+    for A, spread, need, cases in ((260, 9.0, 130, ((256, 35.0), (64, 35.0))), (700, 6.0, 512, ((128, 35.0),))):
+        rng = np.random.default_rng(44 + A)
+        B = 2
+        state, size, types, present = util.random_scene(m, B, A, rng, spread=spread, ped_every=5, absent_p=0.2)
+        present[:, 0] = [True, False]
+        ncam = 8 if A == 260 else 3
+        cams = [(b, c) for b in range(B) for c in range(ncam)]
+        # cameras on the agents nearest to the middle of the crowd
+        near = np.argsort(np.abs(state[..., :2] - np.median(state[..., :2], axis=1, keepdims=True)).max(-1), axis=1)[:, :ncam]
+        cam_xy = np.take_along_axis(state[..., :2], near[..., None], 1).copy()
+        cam_sc = _sincos_torch(np.take_along_axis(state[..., 2], near, 1))
+        # how many agents does a camera see?  (35 m view: everything within ~17 m)
+        d = np.abs(state[:, None, :, :2] - cam_xy[:, :, None, :]).max(-1)
+        assert ((d < 15.0) & present[:, None, :]).sum(-1).min() > need
+        for res, fov in cases:
+            img = _gpu_render(["carla_Town01"], None, state, size, types, present, names, None, None, cam_xy, cam_sc, res, fov)
+            ora = util.oracle_render_batch(m, state, size, types, present, names, None, None, cam_xy, cam_sc, res, fov, cams=cams)
+            bad = sum(int((img[b, c] != o).any(0).sum()) for (b, c), o in ora.items())
+            assert bad == 0, f"{A} agents, res {res}: {bad} mismatching pixels over {len(ora)} cameras"
 
 
 def test_extreme_zoom_huge_coordinates():

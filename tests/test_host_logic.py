@@ -284,3 +284,19 @@ def test_compound_npc_controller_gathers_by_assignment():
     one = c.select_batch_elements(torch.tensor([1]), in_place=False).extend(3)
     assert one.npc_state.shape == (3, Np, 4) and one.controller_indices.shape == (3, Np) and c.npc_state.shape == (B, Np, 4)
     assert torch.equal(one.get_npc_state()[0, :, 0], want[1])
+
+
+def test_torch_library_ops_are_registered_with_shape_functions():
+    """torch.ops.tds_b200.* (torchdrivesim_b200/torch_ops.py): registered custom operators whose fake-tensor kernels give
+    the output shapes and dtypes without a GPU (what torch.compile / torch.export trace through)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        s, a, lr = torch.empty(2, 3, 4), torch.empty(2, 3, 2), torch.empty(2, 3)
+        assert torch.ops.tds_b200.kinematic_step(s, a, lr, None, 0, 0.1, True).shape == (2, 3, 4)
+        b, m = torch.empty(2, 3, 5), torch.empty(2, 3, dtype=torch.bool)
+        out, arg = torch.ops.tds_b200.collision_allpairs(b, b, m, 0, True)
+        assert out.shape == (2, 3) and arg.dtype == torch.int32
+        assert torch.ops.tds_b200.collision_pairwise(b, b, 1).shape == (2, 3)
+        assert torch.ops.tds_b200.agent_boxes(s, torch.empty(2, 3, 2)).shape == (2, 3, 5)
+    with pytest.raises(tds._lib.TdsError):          # and there is no CPU kernel behind them
+        torch.ops.tds_b200.agent_boxes(torch.zeros(1, 1, 4), torch.zeros(1, 1, 2))

@@ -50,7 +50,7 @@ def test_injected_objects_reproduce_the_stock_reference(monkeypatch):
     ref_img = ref.render_egocentric()
 
     # ---- the C ABI replaced by the oracle (no GPU in this container)
-    def fake_kinematic_step(st, act, lr_, model, uniform_model, params):
+    def fake_kinematic_step(st, act, lr_, model, uniform_model, params, out=None):
         assert uniform_model == tds._lib.MODEL_BICYCLE and params.left_handed == 1
         return OK.bicycle_step(st, act, lr_, params.dt, True)
 

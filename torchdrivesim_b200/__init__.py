@@ -20,7 +20,7 @@ from .observation_noise import (ObservationNoise, ObservationNoiseConfig, Standa
 from .simulator import CollisionMetric, Simulator, TorchDriveConfig  # noqa: F401
 from .graph import GraphedHotPath  # noqa: F401
 from .rollout import FusedRollout  # noqa: F401
-from . import distributed, ops  # noqa: F401
+from . import distributed, ops, torch_ops  # noqa: F401
 from .traffic_lights import TrafficLightController, unroll_controller  # noqa: F401
 from .traffic_controls import BaseTrafficControl, StopSignControl, TrafficLightControl, YieldControl  # noqa: F401
 

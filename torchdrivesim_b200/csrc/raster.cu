@@ -119,6 +119,8 @@ static void make_palette_dev(const tds_palette_t* palette, int N, int L, int R, 
         for (int t = 0; t < TDS_MAX_TL_STATES; t++)
             if (pal.tl_state_class[t] >= 0 && pal.tl_state_class[t] < TDS_MAX_CLASSES) pal.dyn_mask |= 1u << pal.tl_state_class[t];
     if (R > 0) pal.dyn_mask = 0xffffffffu;     // extra rectangles carry arbitrary classes
+    for (int c = 0; c < TDS_MAX_CLASSES; c++) pal.plane_of_class[c] = -1;
+    for (int k = 0; k < pal.n_classes; k++) pal.plane_of_class[pal.order[k]] = (int8_t)k;
 }
 
 // Library-owned scratch per (device, stream) for calls with more cameras than agents (free cameras of Simulator.render):
@@ -184,7 +186,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
     TDS_REQUIRE(L == 0 || (d_tl_corners && d_tl_state), "raster: null traffic light tensors");
     TDS_REQUIRE(R == 0 || (d_rect_corners && d_rect_class), "raster: null rectangle tensors");
     TDS_REQUIRE(Tc >= 0 && (Tc == 0 || (d_cam_tris && d_cam_tri_class)), "raster: null per-camera triangle tensors");
-    TDS_REQUIRE(res >= 4 && res % 4 == 0 && res <= 448, "raster: res=%d must be a multiple of 4 in [4,448]", res);
+    TDS_REQUIRE(res >= 4 && res % 4 == 0 && res <= 1024, "raster: res=%d must be a multiple of 4 in [4,1024]", res);
     TDS_REQUIRE(scale > 0.0f, "raster: scale must be positive");
     TDS_REQUIRE(palette->n_classes >= 0 && palette->n_classes <= TDS_MAX_CLASSES, "raster: bad palette");
     TDS_REQUIRE(image_format == TDS_IMAGE_F32 || image_format == TDS_IMAGE_U8 || image_format == TDS_IMAGE_RANK,

@@ -48,7 +48,18 @@ struct PaletteDev {
     int32_t direction_class;
     int32_t tl_state_class[TDS_MAX_TL_STATES];
     uint32_t dyn_mask;                            // classes that dynamic primitives may carry
+    int8_t plane_of_class[TDS_MAX_CLASSES];       // draw rank (plane) of every class, -1: inactive (filled by the host)
 };
+
+// ceil(2^32 / (2 dy)) for dy <= 1024 (tds::row_rcp), evaluated by the compiler: the kernels copy the entries they need
+// into shared memory instead of carrying division code in their prologue
+struct RcpTable { uint32_t v[1025]; };
+constexpr RcpTable make_rcp_table() {
+    RcpTable t{};
+    for (int i = 1; i <= 1024; i++) t.v[i] = 0xffffffffu / (uint32_t)(2 * i) + 1u;
+    return t;
+}
+static __device__ const RcpTable g_rcp = make_rcp_table();
 
 
 // workspace layout per environment: float tri[T][6] followed by uint8 cls[Tpad]
@@ -301,13 +312,15 @@ struct RasterArgs {
 constexpr int kRows = tds::kMaxRasterRows;
 constexpr int kQueues = 3;                          // short inside, tall inside, clipped
 constexpr int kQueueBytes = (64 + 64 + 40) * 16;    // inside queues: up to 31 left over + 32 new; clipped: 7 + 32
-constexpr int kCullCap = 128;                       // dynamic primitives in view that a camera can list
-constexpr int kGroupExtra = 16 + kCullCap * 2;      // counters, that list
+// dynamic primitives in view that a camera can list: 128 for the warp-per-camera kernels (shared memory is what limits
+// their occupancy), 512 for the CTA-per-camera kernels of the large tiles (BASELINE config 4: a camera sees 100-200
+// of 512 agents; without the list it would walk all 1 536 agent faces)
+__host__ __device__ constexpr int cull_cap(int G) { return G == 32 ? 128 : 512; }
 constexpr int kSlowCap = 40;                        // strips waiting for their faces to be classified (7 left over + 32 new)
 
 __host__ __device__ constexpr int raster_group_bytes(int res, int n_planes, int G) {
     // planes of the camera | per warp of the group: the three face queues + the queue of strips | tables
-    return n_planes * res * ((res + 31) / 32) * 4 + (G / 32) * (kQueueBytes + kSlowCap * 32) + kGroupExtra;
+    return n_planes * res * ((res + 31) / 32) * 4 + (G / 32) * (kQueueBytes + kSlowCap * 32) + 16 + cull_cap(G) * 2;
 }
 // The 64x64 variants (the benchmark configuration) reserve KS = 5 or 7 planes per camera in STATIC shared memory:
 // every address is then a compile-time offset and nothing has to be re-derived from the dynamic base.
@@ -388,7 +401,6 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
 
     // CTA-wide tables: colour per draw rank (0 = background), reciprocals of the row runs, class -> plane
     __shared__ float4 s_lut[TDS_MAX_CLASSES + 1];
-    __shared__ int8_t s_plane_of_class[TDS_MAX_CLASSES];
     constexpr bool STATIC = raster_static_smem(G, RES, KS_);
     constexpr int STATIC_RCP = ((64 + 1) * 4 + 15) & ~15;
     constexpr int STATIC_BYTES = STATIC ? STATIC_RCP + 4 * raster_group_bytes(64, KS_, 32) : 16;
@@ -402,14 +414,9 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         // .w = the colour packed as bytes r | g << 8 | b << 16 (uint8 output)
         s_lut[i] = make_float4(c[0], c[1], c[2], __uint_as_float((uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16)));
     }
-    for (int i = threadIdx.x; i < TDS_MAX_CLASSES; i += blockDim.x) {
-        int p = -1;
-        for (int k = 0; k < K; k++) p = pal.order[k] == i ? k : p;
-        s_plane_of_class[i] = (int8_t)p;
-    }
-    for (int i = threadIdx.x; i <= res; i += blockDim.x) s_rcp[i] = tds::row_rcp(i);
+    for (int i = threadIdx.x; i <= res; i += blockDim.x) s_rcp[i] = g_rcp.v[i];
     __syncthreads();
-    const int plane_tbl = s_plane_of_class[lane];       // lane c holds the plane of class c (TDS_MAX_CLASSES == 32)
+    const int plane_tbl = pal.plane_of_class[lane];     // lane c holds the plane of class c (TDS_MAX_CLASSES == 32)
 
     // per-group shared memory: planes | queues | counters, edge functions, list of dynamic primitives
     const int plane_words = res * W32;
@@ -424,6 +431,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
     const uint32_t queue_sa = queues_sa + (G == 32 ? 0u : (uint32_t)(threadIdx.x >> 5) * WARP_Q);   // this warp's
     const uint32_t slow_sa = queue_sa + kQueueBytes;                        // [kSlowCap] x 32 B
     int* s_cnt = reinterpret_cast<int*>(base + KS * plane_words * 4 + WARPS * WARP_Q);   // [3] = next camera (G > 32)
+    constexpr int kCullCap = cull_cap(G);
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_cnt + 4);             // [kCullCap] dynamic primitives in view
 
     // persistent grid: every group (warp or CTA) pulls the next camera from a global counter, so uneven cameras

@@ -81,15 +81,15 @@ class GraphedHotPath:
     def _body(self) -> None:
         sim = self.sim
         sim.kinematic_model.set_state(self.state)
-        sim.kinematic_model.step(self.action)        # Simulator.step minus the host-side control / NPC stepping
-        self.state.copy_(sim.get_state())           # the graph chains steps through this static buffer
-        sim.kinematic_model.set_state(self.state)
+        # Simulator.step minus the host-side control / NPC stepping; the state is updated in place: the graph chains
+        # steps through this static buffer
+        sim.kinematic_model.step(self.action, out=self.state)
         if self._goals is not None:
             self._goals.step(self.state, sim.internal_time, threshold=sim.cfg.waypoint_removal_threshold, in_place=True)
         if self._render:
             sim.render_egocentric(res=self._res, fov=self._fov, out=self.images)
-        self.collision.copy_(sim.compute_collision())
-        self.offroad.copy_(sim.compute_offroad())
+        sim.compute_collision(out=self.collision)
+        sim.compute_offroad(out=self.offroad)
 
     def run(self, action: Tensor) -> Tuple[Optional[Tensor], Tensor, Tensor]:
         """One step with `action` [B,A,Ac] (device or pinned host tensor).  Returns the static output

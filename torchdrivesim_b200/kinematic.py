@@ -28,7 +28,9 @@ class KinematicModel:
     def batch_size(self) -> int:
         return self.get_state()[..., 0].numel()
 
-    def step(self, action: Tensor, dt: Optional[float] = None) -> None:
+    def step(self, action: Tensor, dt: Optional[float] = None, out: Optional[Tensor] = None) -> None:
+        """`out`: a float32 tensor of the state's shape that receives the new state and becomes the model's state (it may
+        BE the current state: the kernel updates in place); no autograd tape is recorded then - what a CUDA graph uses."""
         raise NotImplementedError
 
     def fit_action(self, future_state: Tensor, current_state: Optional[Tensor] = None, dt: Optional[float] = None) -> Tensor:
@@ -146,9 +148,9 @@ class KinematicBicycle(KinematicModel):
         return ops.kinematic_params(self.dt if dt is None else dt, self.max_acceleration, self.max_steering,
                                     self.max_steering, self.left_handed)
 
-    def step(self, action, dt=None):
+    def step(self, action, dt=None, out=None):
         assert action.shape[-1] == 2, "The bicycle model takes as input only acceleration and steering"
-        self.set_state(ops.kinematic_step(self.get_state(), action, self.lr, None, self._model_id, self._params(dt)))
+        self.set_state(ops.kinematic_step(self.get_state(), action, self.lr, None, self._model_id, self._params(dt), out=out))
 
     def fit_action(self, future_state, current_state=None, dt=None):
         """Inverse of `step` (kinematic.py:479-506); plain torch, not on the per-step path."""
@@ -198,11 +200,11 @@ class KinematicUnicycle(KinematicModel):
     def denormalize_action(self, action):
         return action * self._normalization_factor.to(action.device)
 
-    def step(self, action, dt=None):
+    def step(self, action, dt=None, out=None):
         assert action.shape[-1] == 2
         p = ops.kinematic_params(self.dt if dt is None else dt, self.max_acceleration, math.pi / 2, self.max_yaw_rate,
                                  self.left_handed)
-        self.set_state(ops.kinematic_step(self.get_state(), action, None, None, _lib.MODEL_UNICYCLE, p))
+        self.set_state(ops.kinematic_step(self.get_state(), action, None, None, _lib.MODEL_UNICYCLE, p, out=out))
 
     def fit_action(self, future_state, current_state=None, dt=None):
         dt = self.dt if dt is None else dt
@@ -236,11 +238,11 @@ class SimpleKinematicModel(KinematicModel):
     def denormalize_action(self, action):
         return action * self._normalization_factor.to(action.device)
 
-    def step(self, action, dt=None):
+    def step(self, action, dt=None, out=None):
         assert action.shape[-1] == self.action_size
         p = ops.kinematic_params(self.dt if dt is None else dt, max_dx=self.max_dx, max_dpsi=self.max_dpsi,
                                  max_dv=self.max_dv)
-        self.set_state(ops.kinematic_step(self.get_state(), action, None, None, self._model_id, p))
+        self.set_state(ops.kinematic_step(self.get_state(), action, None, None, self._model_id, p, out=out))
 
     def fit_action(self, future_state, current_state=None, dt=None):
         dt = self.dt if dt is None else dt
@@ -294,8 +296,8 @@ class FusedCompoundKinematicModel(KinematicBicycle):
         self.model_assignments = self.model_assignments[idx]
         super().select_batch_elements(idx)
 
-    def step(self, action, dt=None):
+    def step(self, action, dt=None, out=None):
         assert action.shape[-1] == self.action_size
         p = ops.kinematic_params(self.dt if dt is None else dt, self.max_acceleration, self.max_steering,
                                  self.max_yaw_rate, self.left_handed)
-        self.set_state(ops.kinematic_step(self.get_state(), action, self.lr, self.model_assignments, 0, p))
+        self.set_state(ops.kinematic_step(self.get_state(), action, self.lr, self.model_assignments, 0, p, out=out))

@@ -118,7 +118,8 @@ class B200BirdviewMeshGenerator:
     def initialize_actors_mesh(self, agent_attributes: Tensor, agent_types: Optional[Tensor],
                                agent_type_names: Optional[List[str]], render_agent_direction: bool = True):
         self.agent_size = agent_attributes[..., :2]
-        self.agent_type = agent_types
+        # int32 once, here: the kernel's index type (a conversion per render call would be a library kernel on the hot path)
+        self.agent_type = None if agent_types is None else agent_types.to(torch.int32)
         self.agent_type_names = list(agent_type_names) if agent_type_names else ["vehicle"]
         self.render_agent_direction = render_agent_direction
         self._batch_size = agent_attributes.shape[0]

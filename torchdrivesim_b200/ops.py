@@ -63,9 +63,23 @@ class _KinematicStep(torch.autograd.Function):
 
 def kinematic_step(state: torch.Tensor, action: torch.Tensor, lr: Optional[torch.Tensor],
                    model: Optional[torch.Tensor] = None, uniform_model: int = _lib.MODEL_BICYCLE,
-                   params: Optional["_lib.KinematicParams"] = None) -> torch.Tensor:
-    """state [...,4], action [...,2|4], lr [...], model [...] int (or None: `uniform_model`) -> new state."""
-    return _KinematicStep.apply(state, action, lr, model, uniform_model, params or kinematic_params())
+                   params: Optional["_lib.KinematicParams"] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """state [...,4], action [...,2|4], lr [...], model [...] int (or None: `uniform_model`) -> new state.
+    `out` (contiguous float32, the state's shape; may alias `state`): written directly, no autograd tape."""
+    params = params or kinematic_params()
+    if out is None:
+        return _KinematicStep.apply(state, action, lr, model, uniform_model, params)
+    if out.dtype != torch.float32 or not out.is_contiguous() or out.shape != state.shape:
+        raise _lib.TdsError("kinematic_step: `out` must be a contiguous float32 tensor of the state's shape")
+    lib = _lib.load()
+    s = _lib.as_f32(state).reshape(-1, 4)
+    adim = action.shape[-1]
+    a = _lib.as_f32(action).reshape(-1, adim)
+    l = None if lr is None else _lib.as_f32(lr).reshape(-1)
+    m = None if model is None else _lib.as_i32(model).reshape(-1)
+    _lib.check(lib.tds_kinematic_step_fwd(_lib.ptr(s), _lib.ptr(a), adim, _lib.ptr(l), _lib.ptr(m), uniform_model, s.shape[0],
+                                          ctypes.byref(params), _lib.ptr(out), _lib.stream_ptr(s.device)))
+    return out
 
 
 # ------------------------------------------------------------------------------------ collisions
@@ -132,15 +146,23 @@ class _AllPairs(torch.autograd.Function):
 
 
 def collision_allpairs(ego_box: torch.Tensor, all_box: torch.Tensor, mask: torch.Tensor,
-                       metric: int = _lib.METRIC_DISCS, ego_is_prefix: bool = True) -> torch.Tensor:
-    """Fused Simulator.compute_collision: ego_box [B,A,5], all_box [B,N,5], mask [B,N] -> [B,A], differentiable."""
+                       metric: int = _lib.METRIC_DISCS, ego_is_prefix: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused Simulator.compute_collision: ego_box [B,A,5], all_box [B,N,5], mask [B,N] -> [B,A], differentiable.
+    `out` (contiguous float32 [B,A]): written directly, no autograd tape."""
     if ego_box.dim() != 3 or all_box.dim() != 3 or ego_box.shape[-1] != 5 or all_box.shape[-1] != 5:
         raise _lib.TdsError("collision_allpairs: expected ego_box [B,A,5] and all_box [B,N,5]")
     if ego_box.shape[0] != all_box.shape[0] or tuple(mask.shape) != tuple(all_box.shape[:2]):
         raise _lib.TdsError("collision_allpairs: batch / mask shape mismatch")
     if metric not in (_lib.METRIC_DISCS, _lib.METRIC_IOU):
         raise _lib.TdsError(f"collision_allpairs: unknown metric {metric}")
-    return _AllPairs.apply(ego_box, all_box, mask, metric, ego_is_prefix)
+    if out is None:
+        return _AllPairs.apply(ego_box, all_box, mask, metric, ego_is_prefix)
+    e, a, m = _lib.as_f32(ego_box), _lib.as_f32(all_box), _lib.as_u8(mask)
+    if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != tuple(e.shape[:2]):
+        raise _lib.TdsError("collision_allpairs: `out` must be a contiguous float32 [B,A] tensor")
+    _lib.check(_lib.load().tds_collision_allpairs_fwd(_lib.ptr(e), _lib.ptr(a), _lib.ptr(m), e.shape[0], e.shape[1], a.shape[1], metric,
+                                                      1 if ego_is_prefix else 0, _lib.ptr(out), None, _lib.stream_ptr(e.device)))
+    return out
 
 
 class _AgentBoxes(torch.autograd.Function):
@@ -323,15 +345,25 @@ class _Offroad(torch.autograd.Function):
 
 
 def offroad(state: torch.Tensor, lenwid: torch.Tensor, mapset: MapSet, threshold: float = 0.0,
-            present: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """state [B,A,4], lenwid [B,A,2] -> [B,A] sum over corners of thresholded squared distance to the map."""
+            present: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """state [B,A,4], lenwid [B,A,2] -> [B,A] sum over corners of thresholded squared distance to the map.
+    `out` (contiguous float32 [B,A]): written directly, no autograd tape."""
     if state.dim() != 3 or state.shape[-1] != 4:
         raise _lib.TdsError("offroad: expected state [B,A,4]")
     if lenwid.dim() == 2:
         lenwid = lenwid.unsqueeze(-2).expand(lenwid.shape[0], state.shape[1], lenwid.shape[1])
     if tuple(lenwid.shape) != (state.shape[0], state.shape[1], 2):
         raise _lib.TdsError("offroad: expected lenwid [B,A,2] or [B,2]")
-    return _Offroad.apply(state, lenwid, present, mapset, threshold)
+    if out is None:
+        return _Offroad.apply(state, lenwid, present, mapset, threshold)
+    s, lw = _lib.as_f32(state), _lib.as_f32(lenwid)
+    p = None if present is None else _lib.as_u8(present)
+    if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != tuple(s.shape[:2]):
+        raise _lib.TdsError("offroad: `out` must be a contiguous float32 [B,A] tensor")
+    handles, n_maps = mapset.handles(s.device)
+    _lib.check(_lib.load().tds_offroad_fwd(handles, n_maps, _lib.ptr(mapset.env_map_on(s.device)), _lib.ptr(s), _lib.ptr(lw), _lib.ptr(p),
+                                           s.shape[0], s.shape[1], float(threshold), _lib.ptr(out), None, _lib.stream_ptr(s.device)))
+    return out
 
 
 # ------------------------------------------------------------------------------------ raster

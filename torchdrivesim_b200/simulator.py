@@ -400,10 +400,10 @@ class Simulator:
         """BxAx(A+Npc-1 or A+Npc)x6: the perceived agents in the frame of the perceiving agent's own perceived pose."""
         return ops.agents_relative(self.get_noisy_all_agents_absolute(), exclude_self=exclude_self)
 
-    def compute_offroad(self) -> Tensor:
-        """simulator.py:1035-1044: offroad_infraction_loss(...) * present mask."""
+    def compute_offroad(self, out: Optional[Tensor] = None) -> Tensor:
+        """simulator.py:1035-1044: offroad_infraction_loss(...) * present mask.  `out`: see ops.offroad."""
         return ops.offroad(self.get_state(), self.get_agent_size(), self.road_mesh, self.cfg.offroad_threshold,
-                           self.get_present_mask())
+                           self.get_present_mask(), out=out)
 
     def compute_traffic_lights_violations(self) -> Tensor:
         """simulator.py:1046-1062: which agents run a red light (TrafficLightControl.compute_violation) times the
@@ -416,8 +416,9 @@ class Simulator:
         return ops.traffic_light_violation(box, tl.corners, tl.state, tl.allowed_states.index('red'),
                                            tl.violation_rear_factor, present=self.get_present_mask()).to(state.dtype)
 
-    def compute_collision(self) -> Tensor:
-        """simulator.py:1161-1194 for the `discs` and `iou` metrics, all agents in one launch."""
+    def compute_collision(self, out: Optional[Tensor] = None) -> Tensor:
+        """simulator.py:1161-1194 for the `discs` and `iou` metrics, all agents in one launch.  `out`: see
+        ops.collision_allpairs."""
         state, size = self.get_state(), self.get_agent_size()[..., :2]
         if state.shape[-2] == 0:
             return torch.zeros_like(state[..., 0])
@@ -426,4 +427,4 @@ class Simulator:
         all_box = box
         if self.npc_count > 0:
             all_box = ops.agent_boxes(self.get_all_agent_state(), self.get_all_agent_size()[..., :2])
-        return ops.collision_allpairs(box, all_box, self.get_all_agent_present_mask(), metric, ego_is_prefix=True)
+        return ops.collision_allpairs(box, all_box, self.get_all_agent_present_mask(), metric, ego_is_prefix=True, out=out)
