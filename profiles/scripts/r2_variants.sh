@@ -1,0 +1,7 @@
+# usage: bash profiles/scripts/r2_variants.sh libA.so libB.so ...   (raster timing + issue / instruction-fetch metrics per build)
+M=smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,smsp__inst_executed.sum,launch__registers_per_thread
+for l in "$@"; do
+  echo "== $l"
+  TDS_B200_LIB=$PWD/torchdrivesim_b200/_build/$l python profiles/time_raster.py
+  TDS_B200_LIB=$PWD/torchdrivesim_b200/_build/$l timeout 120 ncu --metrics $M --clock-control none -k regex:raster_kernel -s 6 -c 1 python profiles/time_raster.py 2>&1 | grep -E "no_instruction|issue_active|duration|inst_executed|registers"
+done

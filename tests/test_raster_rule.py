@@ -143,3 +143,82 @@ def test_degenerate_and_collinear():
         pts = np.array(pts, np.int32)
         assert np.array_equal(R.fill_convex_poly(pts, 32, 32), _cv2_mask(pts, 32))
     assert R.fill_convex_poly(np.array([[5, 5]] * 3, np.int32), 32, 32).sum() == 1
+
+
+def test_quad_patterns_against_cv2(host_rule):
+    """Sliver quads (two faces of a road / lane-marking strip inside the image) drawn from the coverage-pattern table, the way
+    the kernel does it, vs the two cv2 triangles: random quads at random positions, both namings of the rungs."""
+    rng = np.random.default_rng(11)
+    res, accepted = 64, 0
+    for k in range(8000):
+        a = rng.integers(0, res, 2)
+        rung = rng.integers(-17, 18, 2)
+        r1, r2 = rng.integers(-1 - (k % 7 == 0), 2 + (k % 7 == 0), 2), rng.integers(-1, 2, 2)
+        b = a + rung
+        c, d = a + r1, b + r2
+        pts = np.ascontiguousarray(np.stack([a, b, c, d] if k % 2 else [a, c, b, d]), np.int32)
+        img = np.zeros((res, res), np.uint8)
+        naming = host_rule.tds_host_draw_quad(img.ctypes.data_as(ctypes.c_void_p), res, res, pts.ctypes.data_as(ctypes.c_void_p))
+        inside = bool(((pts >= 0) & (pts < res)).all())
+        in_table = inside and np.abs(rung).max() <= 15 and np.abs(r1).max() <= 1
+        assert (naming != 0) == in_table or (naming != 0 and inside), (pts.tolist(), naming)
+        if not naming:
+            continue
+        accepted += 1
+        want = _cv2_mask(pts[[0, 1, 2]], res) | _cv2_mask(pts[[1, 2, 3]], res)
+        assert img.max() <= 1, "pattern contract violated"
+        assert np.array_equal(img > 0, want), pts.tolist()
+    assert accepted > 1500
+
+
+def test_quad_pattern_table_entries_against_cv2(host_rule):
+    """Entries of the table itself (generated by the product's triangle rule at start-up) against cv2, at a fixed anchor."""
+    shape = (ctypes.c_int * 3)()
+    host_rule.tds_host_quad_table_shape(shape)
+    n_pat, n_rows, R = shape[0], shape[1], shape[2]
+    host_rule.tds_host_quad_table.restype = ctypes.POINTER(ctypes.c_uint32)
+    table = np.ctypeslib.as_array(host_rule.tds_host_quad_table(), shape=(n_pat, n_rows))
+    assert n_pat == (2 * R + 1) ** 2 * 81
+    rng = np.random.default_rng(5)
+    span = 2 * R + 1
+    for idx in rng.integers(0, n_pat, 3000):
+        r2, rest = idx % 9, idx // 9
+        r1, rest = rest % 9, rest // 9
+        gx, gy = rest % span - R, rest // span - R
+        a = np.array([24, 24])
+        b = a + [gx, gy]
+        c = a + [r1 % 3 - 1, r1 // 3 - 1]
+        d = b + [r2 % 3 - 1, r2 // 3 - 1]
+        pts = np.stack([a, b, c, d]).astype(np.int32)
+        want = _cv2_mask(pts[[0, 1, 2]], 64) | _cv2_mask(pts[[1, 2, 3]], 64)
+        x0, y0 = pts[:, 0].min(), pts[:, 1].min()
+        got = np.zeros((64, 64), bool)
+        for r in range(n_rows):
+            for j in range(32):
+                if (int(table[idx, r]) >> j) & 1:
+                    got[y0 + r, x0 + j] = True
+        assert np.array_equal(got, want), (idx, pts.tolist())
+
+
+@pytest.mark.parametrize("res", [32, 64, 128])
+def test_three_line_triangles_match_cv2(host_rule, res):
+    """Triangles inside the image as three line walkers (the kernel's path for every face inside the image)."""
+    rng = np.random.default_rng(res + 5)
+    for k in range(4000):
+        if k % 3 == 0:
+            pts = rng.integers(0, res, (3, 2))
+        elif k % 3 == 1:
+            pts = (rng.integers(3, res - 3, (1, 2)) + rng.integers(-3, 4, (3, 2)))
+        else:
+            pts = (rng.integers(8, res - 8, (1, 2)) + np.stack([rng.integers(-8, 9, 3), rng.integers(0, 2, 3)], 1))
+        pts = np.ascontiguousarray(pts, np.int32)
+        img = np.zeros((res, res), np.uint8)
+        assert host_rule.tds_host_draw_triangle_lines3(img.ctypes.data_as(ctypes.c_void_p), res, res, pts.ctypes.data_as(ctypes.c_void_p)) == 1
+        assert img.max() <= 1, "row contract violated"
+        assert np.array_equal(img > 0, _cv2_mask(pts, res)), pts.tolist()
+
+
+def test_three_line_triangles_exhaustive_small(host_rule):
+    """All 262 144 triangles with vertices in a 8 x 8 window (every degenerate and collinear case included)."""
+    host_rule.tds_host_lines3_triangle_sweep.restype = ctypes.c_longlong
+    assert host_rule.tds_host_lines3_triangle_sweep(8) == 0

@@ -5,7 +5,10 @@
 #include <cstring>
 #include <vector>
 
+#include <mutex>
+
 #include "tds_map.cuh"
+#include "tds_quad_table.h"
 
 namespace tds {
 
@@ -35,7 +38,37 @@ bool upload(const std::vector<T>& h, void** d, int64_t& bytes) {
     return true;
 }
 
+constexpr int kMaxDevices = 64;
+std::mutex g_quad_mu;
+void* g_quad_table[kMaxDevices] = {};
+
+// library-owned, one per device, lives until the process ends
+bool quad_table_ensure() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    std::lock_guard<std::mutex> lock(g_quad_mu);
+    if (g_quad_table[dev]) return true;
+    static std::vector<uint32_t> host;          // generated once per process by the reference's triangle rule
+    if (host.empty()) {
+        host.resize((size_t)tds::kQuadPatterns * tds::kQuadRows);
+        tds::quad_table_fill(host.data());
+    }
+    void* d = nullptr;
+    const size_t n = host.size() * sizeof(uint32_t);
+    if (cudaMalloc(&d, n) != cudaSuccess) return false;
+    if (cudaMemcpy(d, host.data(), n, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return false; }
+    g_quad_table[dev] = d;
+    return true;
+}
+
 }  // namespace
+
+const void* tds::quad_table_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    std::lock_guard<std::mutex> lock(g_quad_mu);
+    return g_quad_table[dev];
+}
 
 extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int32_t* h_faces, int32_t nf,
                                      const uint8_t* h_face_class, float raster_cell, float offroad_cell) {
@@ -68,6 +101,10 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
             miny = std::min(miny, h_verts[2 * v + 1]); maxy = std::max(maxy, h_verts[2 * v + 1]);
         }
     }
+    if (!quad_table_ensure()) {
+        fail(TDS_ERR_CUDA, "map_create: could not build the quad pattern table: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
     tds_map* m = new tds_map();
     MapDev& d = m->dev;
     for (auto& a : m->allocations) a = nullptr;
@@ -98,18 +135,49 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     };
     // ---- strips of four faces over six vertices (see tds_map.cuh); the other faces become face records
     std::vector<uint8_t> in_strip((size_t)nf, 0);
-    struct Strip { int v[6]; int cls; };
+    struct Strip { int v[6]; int cls; bool ordered; };
     std::vector<Strip> strips;
     auto finite_v = [&](int v) { return std::isfinite(h_verts[2 * v]) && std::isfinite(h_verts[2 * v + 1]); };
+    // Faces f .. f+3 form a strip when, AS SETS, face k = {v_k, v_k+1, v_k+2} for six distinct vertices v_0 .. v_5 (the
+    // pixels of a face do not depend on the order of its vertices).  Lane markings list their faces as
+    // (a,b,c),(b,c,d),(c,d,e),(d,e,f) (lanelet2.py:253-283), road surfaces as (a,b,c),(c,b,d),(c,d,e),(e,d,f).
+    auto has = [](const int32_t* q, int v) { return q[0] == v || q[1] == v || q[2] == v; };
+    auto strip_of = [&](const int32_t* q, int* v) {
+        const int32_t *f0 = q, *f1 = q + 3, *f2 = q + 6, *f3 = q + 9;
+        int shared[2], ns = 0, v0 = -1;
+        for (int k = 0; k < 3; k++) { if (has(f1, f0[k])) { if (ns < 2) shared[ns] = f0[k]; ns++; } else v0 = f0[k]; }
+        if (ns != 2 || v0 < 0) return false;
+        int v3 = -1, n3 = 0;
+        for (int k = 0; k < 3; k++) if (!has(f0, f1[k])) { v3 = f1[k]; n3++; }
+        if (n3 != 1) return false;
+        // v2 = the shared vertex that face 2 keeps, v1 = the one it drops
+        const bool k0 = has(f2, shared[0]), k1 = has(f2, shared[1]);
+        if (k0 == k1) return false;
+        const int v2 = k0 ? shared[0] : shared[1], v1 = k0 ? shared[1] : shared[0];
+        if (!has(f2, v3)) return false;
+        int v4 = -1, n4 = 0;
+        for (int k = 0; k < 3; k++) if (f2[k] != v2 && f2[k] != v3) { v4 = f2[k]; n4++; }
+        if (n4 != 1) return false;
+        if (!has(f3, v3) || !has(f3, v4) || has(f3, v2)) return false;
+        int v5 = -1, n5 = 0;
+        for (int k = 0; k < 3; k++) if (f3[k] != v3 && f3[k] != v4) { v5 = f3[k]; n5++; }
+        if (n5 != 1) return false;
+        v[0] = v0; v[1] = v1; v[2] = v2; v[3] = v3; v[4] = v4; v[5] = v5;
+        for (int a = 0; a < 6; a++)
+            for (int b = a + 1; b < 6; b++)
+                if (v[a] == v[b]) return false;
+        return true;
+    };
     for (int f = 0; f + 3 < nf;) {
         const int32_t* q = h_faces + 3 * (size_t)f;
         bool ok = h_face_class[f] == h_face_class[f + 1] && h_face_class[f] == h_face_class[f + 2] &&
                   h_face_class[f] == h_face_class[f + 3];
-        for (int k = 0; ok && k < 3; k++) ok = q[3 * (k + 1)] == q[3 * k + 1] && q[3 * (k + 1) + 1] == q[3 * k + 2];
+        Strip s;
+        ok = ok && strip_of(q, s.v);
         if (ok) {
-            Strip s;
-            s.v[0] = q[0]; s.v[1] = q[1]; s.v[2] = q[2]; s.v[3] = q[5]; s.v[4] = q[8]; s.v[5] = q[11];
             s.cls = h_face_class[f];
+            s.ordered = true;
+            for (int k = 0; s.ordered && k < 3; k++) s.ordered = q[3 * (k + 1)] == q[3 * k + 1] && q[3 * (k + 1) + 1] == q[3 * k + 2];
             for (int k = 0; ok && k < 6; k++) ok = finite_v(s.v[k]);
             if (ok) {
                 strips.push_back(s);
@@ -199,18 +267,22 @@ extern "C" tds_map_t* tds_map_create(const float* h_verts, int32_t nv, const int
     const int32_t n_recs = build_face_records(false, rcell, recdata);
     if (strips.empty()) { rcell_all = rcell; recdata_all = recdata; }
     else build_face_records(true, rcell_all, recdata_all);
-    // median length of the long side of a strip (vertex 0 -> vertex 1): the host side decides from it whether a
-    // strip is a handful of pixels at the requested zoom
+    // median length of the long side of a lane-marking strip (vertex 0 -> vertex 1 of the strips whose faces are listed
+    // as (a,b,c),(b,c,d),...): the host side decides from it whether such a strip is a handful of pixels at the
+    // requested zoom.  Road-surface strips are not counted: their faces are always drawn.
     d.strip_len = 0.f;
-    if (!strips.empty()) {
-        std::vector<float> len(strips.size());
+    {
+        std::vector<float> len;
         for (size_t i = 0; i < strips.size(); i++) {
+            if (!strips[i].ordered) continue;
             const float dx = h_verts[2 * strips[i].v[1]] - h_verts[2 * strips[i].v[0]];
             const float dy = h_verts[2 * strips[i].v[1] + 1] - h_verts[2 * strips[i].v[0] + 1];
-            len[i] = std::sqrt(dx * dx + dy * dy);
+            len.push_back(std::sqrt(dx * dx + dy * dy));
         }
-        std::nth_element(len.begin(), len.begin() + len.size() / 2, len.end());
-        d.strip_len = len[len.size() / 2];
+        if (!len.empty()) {
+            std::nth_element(len.begin(), len.begin() + len.size() / 2, len.end());
+            d.strip_len = len[len.size() / 2];
+        }
     }
     // ---------------- offroad grid (bounding-box binning)
     d.ocs = offroad_cell;

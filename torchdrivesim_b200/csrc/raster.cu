@@ -180,6 +180,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
                                        const uint8_t* d_agent_class, int32_t image_format, void* d_out, void* d_workspace,
                                        void* stream) {
     TDS_REQUIRE(B >= 0 && Nc >= 0 && N >= 0 && L >= 0 && R >= 0, "raster: negative size");
+    TDS_REQUIRE(B < (1 << 22), "raster: at most 4 194 303 environments per call");
     if (B == 0 || Nc == 0) return TDS_OK;
     TDS_REQUIRE(d_cam_xy && d_cam_sc && d_out && palette, "raster: null pointer");
     TDS_REQUIRE(N == 0 || (d_agent_state && d_agent_size), "raster: null agent tensors");
@@ -236,6 +237,9 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
         a.strip_mode = (0.525f * (float)res - band >= half + 1.001f && strip_px > 0.f && strip_px <= 1.4f) ? 1 : 0;
         if (const char* e = getenv("TDS_RASTER_STRIPS"))
             a.strip_mode = (atoi(e) != 0 && 0.525f * (float)res - band >= half + 1.001f) ? 1 : 0;
+        // sliver quads (pairs of strip faces as one item drawn from the pattern table): 64x64 warp-per-camera kernels
+        a.quad_table = (a.strip_mode && res == 64) ? reinterpret_cast<const uint4*>(tds::quad_table_device()) : nullptr;
+        if (const char* e = getenv("TDS_RASTER_QUADS")) { if (atoi(e) == 0) a.quad_table = nullptr; }
     }
     const int K = pal.n_classes;
     TDS_REQUIRE(K <= 31, "raster: at most 31 active classes (got %d)", K);

@@ -31,6 +31,7 @@
 #include "tds_map.cuh"
 #include "tds_raster_tri.h"
 #include "tds_raster_rows.h"
+#include "tds_quad_table.h"
 
 namespace tds_raster {
 
@@ -264,19 +265,50 @@ __device__ __forceinline__ void draw_inside(uint32_t plane, int res, uint32_t rc
     });
 }
 
+// stage 2a of the 64x64 kernels: a triangle inside the image as three line walkers (tds_raster_rows.h): one interval and
+// one atomic OR per row and word.  Vertices packed as x | y << 8, two per word.
+__device__ __forceinline__ uint32_t pack_vertex8(int x, int y) { return (uint32_t)x | ((uint32_t)y << 8); }
+__device__ __forceinline__ void draw_lines3_64(uint32_t plane, uint32_t rcp_sa, uint32_t w0, uint32_t w1) {
+    tds::Lines3 q;
+    tds::lines3_setup((int)(w0 & 0xffu), (int)((w0 >> 8) & 0xffu), (int)((w0 >> 16) & 0xffu), (int)(w0 >> 24), (int)(w1 & 0xffu),
+                      (int)((w1 >> 8) & 0xffu), q, [&](int dy) { return slds_const(rcp_sa + 4u * (uint32_t)dy); });
+    tds::lines3_rows(q, [&](int yy, int lo, int hi) { or_mask64(plane, yy, (~0ull >> (63 - (hi - lo))) << lo); });
+}
+
+// stage 2q: two faces of a strip that form a sliver quad inside the image: the rows of its coverage pattern
+// (tds_quad_table.h), shifted to the quad's corner.  w0 = xmin | ymin << 8 | rows << 16 | plane << 24.
+__device__ __forceinline__ void draw_quad_pattern64(uint32_t planes_sa, uint32_t plane_bytes, const uint4* __restrict__ table, uint32_t w0,
+                                                    uint32_t index) {
+    const int xmin = (int)(w0 & 0xffu), ymin = (int)((w0 >> 8) & 0xffu), h = (int)((w0 >> 16) & 0xffu);
+    const uint32_t plane = planes_sa + (w0 >> 24) * plane_bytes;
+    const uint4* tp = table + (size_t)index * (tds::kQuadRows / 4);
+    // rows past the pattern hold zeros: OR-ed into the last image row at most.  The first two groups of four rows (most
+    // quads are at most 8 rows tall) are requested together: one L2 latency instead of two.
+    uint4 m = __ldg(tp);
+    uint4 m_next = __ldg(tp + 1);
+#pragma unroll 1
+    for (int r = 0; r < h; r += 4) {
+        const uint32_t rows[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) or_mask64(plane, min(ymin + r + k, 63), (unsigned long long)rows[k] << xmin);
+        m = m_next;
+        if (r + 8 < h) m_next = __ldg(tp + (r >> 2) + 2);
+    }
+}
+
 // stage 2b: a triangle that crosses the image border (|coordinates| < 8192), drawn by FOUR lanes (lane & 3 = part): the
 // clipped runs of one outline edge each for parts 0..2, the fill set-up by part 3, then a fourth of the clamped fill rows
 // each (tds_raster_rows.h: row_tri_part).  Called with the four lanes of a face converged.
 template <int RES>
 __device__ __forceinline__ void draw_clipped_part(uint32_t plane, int res, uint32_t rcp_sa, int x0, int y0, int x1, int y1,
                                                   int x2, int y2, int part, unsigned lanes) {
-    const int src = (threadIdx.x & 28) | 3;       // the part-3 lane of this face
+    const int first = threadIdx.x & 28;           // the part-0 lane of this face
     tds::row_tri_part(res, res, x0, y0, x1, y1, x2, y2, part, [&](int dy) { return slds_const(rcp_sa + 4u * (uint32_t)dy); },
         [&](int y, int lo, int hi) {
             if (RES == 64) or_mask64(plane, y, (~0ull >> (63 - (hi - lo))) << lo);
             else or_span(plane, res, y, lo, hi);
         },
-        [&](int v) { return __shfl_sync(lanes, v, src); });
+        [&](int v, int w) { return __shfl_sync(lanes, v, first | w); });
 }
 
 // coordinates beyond +-8000 pixels (extreme zoom / giant rectangles): 64-bit rule, pixel by pixel.  Rare.
@@ -302,6 +334,7 @@ struct RasterArgs {
     const int32_t* cam_cls;    // [B*Nc][Tc] their classes (< 0: skipped)
     int32_t Tc;
     int32_t strip_mode;        // 1: strips take stage 1S, the face segments hold the other faces; 0: the face segments hold all faces
+    const uint4* quad_table;   // coverage patterns of sliver quads (tds_quad_table.h), or NULL: pairs of strip faces are drawn one by one
     int32_t out_format;        // TDS_IMAGE_F32 / TDS_IMAGE_U8 / TDS_IMAGE_RANK
     const uint8_t* agent_cls;  // [B*Nc][N] class of each agent's rectangle as this camera sees it (custom colours), or NULL
     int32_t* redo;             // [0] = number of cameras in redo[4..]: LEAN kernels list the cameras they cannot finish
@@ -317,10 +350,15 @@ constexpr int kQueueBytes = (64 + 64 + 40) * 16;    // inside queues: up to 31 l
 // of 512 agents; without the list it would walk all 1 536 agent faces)
 __host__ __device__ constexpr int cull_cap(int G) { return G == 32 ? 128 : 512; }
 constexpr int kSlowCap = 40;                        // strips waiting for their faces to be classified (7 left over + 32 new)
+// the warp-per-camera kernels of 64x64 tiles draw every face inside the image as an item of three lines, and pairs of
+// strip faces that form a sliver quad as ONE such item (tds_raster_rows.h)
+__host__ __device__ constexpr bool raster_quads(int G, int res) { return G == 32 && res == 64; }
+// ... whose queue of sliver quads takes up to 31 left over + 64 new (two per strip and thread of stage 1S)
+__host__ __device__ constexpr int raster_queue_bytes(int G, int res) { return raster_quads(G, res) ? (64 + 40 + 96) * 16 : kQueueBytes; }
 
 __host__ __device__ constexpr int raster_group_bytes(int res, int n_planes, int G) {
     // planes of the camera | per warp of the group: the three face queues + the queue of strips | tables
-    return n_planes * res * ((res + 31) / 32) * 4 + (G / 32) * (kQueueBytes + kSlowCap * 32) + 16 + cull_cap(G) * 2;
+    return n_planes * res * ((res + 31) / 32) * 4 + (G / 32) * (raster_queue_bytes(G, res) + kSlowCap * 32) + 16 + cull_cap(G) * 2;
 }
 // The 64x64 variants (the benchmark configuration) reserve KS = 5 or 7 planes per camera in STATIC shared memory:
 // every address is then a compile-time offset and nothing has to be re-derived from the dynamic base.
@@ -427,9 +465,13 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
     const uint32_t plane_bytes = 4u * (uint32_t)plane_words;
     constexpr int WARPS = G / 32;
     const uint32_t queues_sa = planes_sa + (uint32_t)KS * plane_bytes;     // [WARPS] x (3 queues of QN x 16 B + the strip queue)
-    constexpr int WARP_Q = kQueueBytes + kSlowCap * 32;
+    constexpr bool QUADS = raster_quads(G, RES);
+    constexpr int QUEUE_BYTES = raster_queue_bytes(G, RES);
+    constexpr int WARP_Q = QUEUE_BYTES + kSlowCap * 32;
+    // queue 0: short faces inside the image (QUADS: all of them), queue 1: tall ones (QUADS: sliver quads, 96 entries), queue 2: clipped
+    constexpr int Q1 = QUADS ? QN + 40 : QN, Q2 = QUADS ? QN : 2 * QN;
     const uint32_t queue_sa = queues_sa + (G == 32 ? 0u : (uint32_t)(threadIdx.x >> 5) * WARP_Q);   // this warp's
-    const uint32_t slow_sa = queue_sa + kQueueBytes;                        // [kSlowCap] x 32 B
+    const uint32_t slow_sa = queue_sa + QUEUE_BYTES;                        // [kSlowCap] x 32 B
     int* s_cnt = reinterpret_cast<int*>(base + KS * plane_words * 4 + WARPS * WARP_Q);   // [3] = next camera (G > 32)
     constexpr int kCullCap = cull_cap(G);
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_cnt + 4);             // [kCullCap] dynamic primitives in view
@@ -451,7 +493,13 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
             if (camid >= a.cam_list[0]) break;
             camid = a.cam_list[4 + camid];
         } else if (camid >= a.ncam) break;
-        const int b = camid / a.Nc;
+        // environment of the camera: camid / Nc through the fp32 reciprocal, fixed with the remainder (exact below 2^22
+        // environments, which the launcher checks)
+        int b = __float2int_rz(__fdividef((float)camid, (float)a.Nc));
+        {
+            const int r = camid - b * a.Nc;
+            b += r < 0 ? -1 : (r >= a.Nc ? 1 : 0);
+        }
         const MapDev& map = maps.m[a.env_map ? a.env_map[b] : 0];
         Camera cam;
         const float2 cxy = reinterpret_cast<const float2*>(a.cam_xy)[camid];
@@ -459,6 +507,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         group_sync<G>();                            // previous camera of this group is completely done
         make_camera(cam, cxy.x, cxy.y, csc.x, csc.y, a.scale, res);
         {
+#pragma unroll 1
             for (int i = tid; i < K * plane_words / 4; i += G) ssts4(planes_sa + 16u * (uint32_t)i, make_uint4(0u, 0u, 0u, 0u));
             if (G != 32 && tid < 3) s_cnt[tid] = 0;
         }
@@ -494,6 +543,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         const int items = a.N + a.LR;
         int n_view = 0;
         bool any_absent = false;
+#pragma unroll 1
         for (int i0 = 0; i0 < items; i0 += G) {
             const int i = i0 + tid;
             bool keep = false;
@@ -581,13 +631,14 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                 xy[0] = (int16_t)(w0 & 0xffff); xy[1] = (int32_t)w0 >> 16;
                 xy[2] = (int16_t)(w1 & 0xffff); xy[3] = (int32_t)w1 >> 16;
                 xy[4] = (int16_t)(w2 & 0xffff); xy[5] = (int32_t)w2 >> 16;
-                plane = (int)(m >> 8);
+                plane = (int)((m >> 8) & 0xffu);
                 const int fxmin = min(min(xy[0], xy[2]), xy[4]), fxmax = max(max(xy[0], xy[2]), xy[4]);
                 const int fymin = min(min(xy[1], xy[3]), xy[5]), fymax = max(max(xy[1], xy[3]), xy[5]);
                 const bool off = ((fxmax | fymax) < 0) | (fxmin >= res) | (fymin >= res);
                 const bool tiny = ((fxmax - fxmin) | (fymax - fymin)) <= 1;      // its vertices: plotted by stage 1S
                 const bool inside = ((fxmin | fymin) >= 0) & (fxmax < res) & (fymax < res);
-                const bool kept = ((m >> f) & 7u) != 0u;                         // some vertex inside the view quad
+                // some vertex inside the view quad, and not already drawn as half of a sliver quad (stage 1S)
+                const bool kept = ((m >> f) & 7u) != 0u && !((m >> (16 + f)) & 1u);
                 kind = (!act | off | tiny | !kept) ? kCulled : (!inside ? kClipped : (fymax - fymin <= kShortRows ? kShort : kTall));
             } else if (seg <= seg_dyn) {
                 // uniform control flow: every lane fetches a valid record (the last one of the segment past its end)
@@ -632,18 +683,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                         xi[k] = __float2int_rz(u[k]);
                         yi[k] = __float2int_rz(v[k]);
                     }
-                    // every vertex inside the image is a pixel of each kept face it belongs to (the outline of a face
-                    // contains its end points), and such a face IS kept: the image lies inside the view quad with a
-                    // margin of more than one pixel (strip_mode).  A vertex outside the image ORs a zero into
-                    // pixel (0, 0): no branch around the reduction.
                     const uint32_t pl = planes_sa + (uint32_t)max(spl, 0) * plane_bytes;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        const bool in = spl >= 0 && (POW2 ? (unsigned)(xi[k] | yi[k]) < (unsigned)res
-                                                          : ((unsigned)xi[k] < (unsigned)res && (unsigned)yi[k] < (unsigned)res));
-                        const int x = in ? xi[k] : 0, y = in ? yi[k] : 0;
-                        sred_or(pl + 4u * (uint32_t)((x >> 5) * res + y), in ? 1u << (x & 31) : 0u);
-                    }
                     const int sxmin = min(min(min(xi[0], xi[1]), min(xi[2], xi[3])), min(xi[4], xi[5]));
                     const int sxmax = max(max(max(xi[0], xi[1]), max(xi[2], xi[3])), max(xi[4], xi[5]));
                     const int symin = min(min(min(yi[0], yi[1]), min(yi[2], yi[3])), min(yi[4], yi[5]));
@@ -674,6 +714,61 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                         }
                         slow = false;
                     }
+                    uint32_t done = 0u;              // faces that need nothing more: half of a sliver quad (queued, or just its vertices)
+                    uint32_t queued = 0u;            // faces of the quads that were queued
+                    if (QUADS && a.quad_table) {
+                        // The strip is two quads: faces (0, 1) over vertices 0..3 and faces (2, 3) over vertices 2..5.  A quad
+                        // whose faces are both kept, with its four vertices inside the image and a shape of the pattern
+                        // table, is queued as ONE item right here (tds_quad_table.h: the union of the two triangles by the
+                        // reference's rule, so it does not matter that one of them may be tiny); within 2x2 pixels it is just
+                        // its vertices, which are plotted already.
+#pragma unroll
+                        for (int qd = 0; qd < 2; qd++) {
+                            const int k = 2 * qd;
+                            const bool both = ((cb >> k) & 7u) != 0u && ((cb >> (k + 1)) & 7u) != 0u;
+                            const int qxmin = min(min(xi[k], xi[k + 1]), min(xi[k + 2], xi[k + 3])), qxmax = max(max(xi[k], xi[k + 1]), max(xi[k + 2], xi[k + 3]));
+                            const int qymin = min(min(yi[k], yi[k + 1]), min(yi[k + 2], yi[k + 3])), qymax = max(max(yi[k], yi[k + 1]), max(yi[k + 2], yi[k + 3]));
+                            const bool allin = (unsigned)(qxmin | qymin) < 64u && (unsigned)(qxmax | qymax) < 64u;
+                            // rungs (v0, v1), (v2, v3) with rails (v0, v2), (v1, v3) - or the other way round
+                            int gx = xi[k + 1] - xi[k], gy = yi[k + 1] - yi[k], r1x = xi[k + 2] - xi[k], r1y = yi[k + 2] - yi[k];
+                            int r2x = xi[k + 3] - xi[k + 1], r2y = yi[k + 3] - yi[k + 1];
+                            if (!tds::quad_in_table(gx, gy, r1x, r1y, r2x, r2y)) {
+                                int t = gx; gx = r1x; r1x = t; t = gy; gy = r1y; r1y = t;
+                                r2x = xi[k + 3] - xi[k + 2]; r2y = yi[k + 3] - yi[k + 2];
+                            }
+                            const bool covered = slow && both && allin && tds::quad_in_table(gx, gy, r1x, r1y, r2x, r2y);
+                            const bool quad = covered && (((qxmax - qxmin) | (qymax - qymin)) > 1);
+                            done |= covered ? 3u << k : 0u;
+                            queued |= quad ? 3u << k : 0u;
+                            const unsigned mq = __ballot_sync(0xffffffffu, quad);
+                            if (quad) {
+                                const int pos = Q1 + nq1 + __popc(mq & ((1u << lane) - 1));
+                                ssts4(queue_sa + 16u * (uint32_t)pos,
+                                      make_uint4((uint32_t)qxmin | ((uint32_t)qymin << 8) | ((uint32_t)(qymax - qymin + 1) << 16) | ((uint32_t)spl << 24),
+                                                 (uint32_t)tds::quad_pattern_index(gx, gy, r1x, r1y, r2x, r2y), 0u, 0u));
+                            }
+                            nq1 += __popc(mq);
+                        }
+                        // faces that are kept and not covered by a quad still go through the strip queue
+                        uint32_t left = 0u;
+#pragma unroll
+                        for (int f = 0; f < 4; f++) left |= (((cb >> f) & 7u) != 0u && !((done >> f) & 1u)) ? 1u << f : 0u;
+                        slow = slow && left != 0u;
+                    }
+                    // every vertex inside the image is a pixel of each kept face it belongs to (the outline of a face
+                    // contains its end points), and such a face IS kept: the image lies inside the view quad with a
+                    // margin of more than one pixel (strip_mode).  A vertex outside the image ORs a zero into
+                    // pixel (0, 0): no branch around the reduction.  Strips whose four faces went on as quads need no
+                    // vertices (road surfaces, batch after batch: the records of a cell are sorted by class).
+                    if (__any_sync(0xffffffffu, spl >= 0 && queued != 15u)) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) {
+                            const bool in = spl >= 0 && (POW2 ? (unsigned)(xi[k] | yi[k]) < (unsigned)res
+                                                              : ((unsigned)xi[k] < (unsigned)res && (unsigned)yi[k] < (unsigned)res));
+                            const int x = in ? xi[k] : 0, y = in ? yi[k] : 0;
+                            sred_or(pl + 4u * (uint32_t)((x >> 5) * res + y), in ? 1u << (x & 31) : 0u);
+                        }
+                    }
                     // the others wait in the strip queue until 8 of them make a full warp of faces
                     const unsigned ms = __ballot_sync(0xffffffffu, slow);
                     if (slow) {
@@ -681,7 +776,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                         ssts4(ea, make_uint4((uint32_t)(xi[0] & 0xffff) | ((uint32_t)yi[0] << 16), (uint32_t)(xi[1] & 0xffff) | ((uint32_t)yi[1] << 16),
                                              (uint32_t)(xi[2] & 0xffff) | ((uint32_t)yi[2] << 16), (uint32_t)(xi[3] & 0xffff) | ((uint32_t)yi[3] << 16)));
                         ssts4(ea + 16u, make_uint4((uint32_t)(xi[4] & 0xffff) | ((uint32_t)yi[4] << 16), (uint32_t)(xi[5] & 0xffff) | ((uint32_t)yi[5] << 16),
-                                                   cb | ((uint32_t)spl << 8), 0u));
+                                                   cb | ((uint32_t)spl << 8) | (done << 16), 0u));
                     }
                     nslow += __popc(ms);
                 } else {
@@ -745,44 +840,86 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
             const bool drain = seg > seg_dyn && nslow == 0;
             // queue the faces by kind (warp-aggregated append)
             if (__any_sync(0xffffffffu, kind >= kShort)) {
-                const unsigned m0 = __ballot_sync(0xffffffffu, kind == kShort), m1 = __ballot_sync(0xffffffffu, kind == kTall),
-                               m2 = __ballot_sync(0xffffffffu, kind == kClipped);
-                const int b0 = nq0, b1 = nq1, b2 = nq2;
-                nq0 += __popc(m0); nq1 += __popc(m1); nq2 += __popc(m2);
-                if (kind >= kShort) {
-                    const unsigned mine = kind == kShort ? m0 : (kind == kTall ? m1 : m2);
-                    const int qb = kind == kShort ? b0 : (kind == kTall ? QN + b1 : 2 * QN + b2);
-                    const int pos = qb + __popc(mine & ((1u << lane) - 1));
-                    ssts4(queue_sa + 16u * (uint32_t)pos,
-                          make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
-                                     (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
-                                     (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane));
+                if (QUADS) {
+                    // queue 0: triangles inside the image (three line walkers), queue 2: faces that cross the border
+                    // (queue 1, the sliver quads, is filled by stage 1S)
+                    const bool ins = kind == kShort || kind == kTall;
+                    const unsigned m0 = __ballot_sync(0xffffffffu, ins), m2 = __ballot_sync(0xffffffffu, kind == kClipped);
+                    const int b0 = nq0, b2 = nq2;
+                    nq0 += __popc(m0); nq2 += __popc(m2);
+                    if (kind >= kShort) {
+                        const int pos = (ins ? b0 : Q2 + b2) + __popc((ins ? m0 : m2) & ((1u << lane) - 1));
+                        const uint4 item = ins ? make_uint4(pack_vertex8(xy[0], xy[1]) | (pack_vertex8(xy[2], xy[3]) << 16), pack_vertex8(xy[4], xy[5]),
+                                                            (uint32_t)plane, 0u)
+                                               : make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
+                                                            (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
+                                                            (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
+                        ssts4(queue_sa + 16u * (uint32_t)pos, item);
+                    }
+                } else {
+                    const unsigned m0 = __ballot_sync(0xffffffffu, kind == kShort), m1 = __ballot_sync(0xffffffffu, kind == kTall),
+                                   m2 = __ballot_sync(0xffffffffu, kind == kClipped);
+                    const int b0 = nq0, b1 = nq1, b2 = nq2;
+                    nq0 += __popc(m0); nq1 += __popc(m1); nq2 += __popc(m2);
+                    if (kind >= kShort) {
+                        const unsigned mine = kind == kShort ? m0 : (kind == kTall ? m1 : m2);
+                        const int qb = kind == kShort ? b0 : (kind == kTall ? Q1 + b1 : Q2 + b2);
+                        const int pos = qb + __popc(mine & ((1u << lane) - 1));
+                        ssts4(queue_sa + 16u * (uint32_t)pos,
+                              make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
+                                         (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
+                                         (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane));
+                    }
                 }
             }
             __syncwarp();
             if (!(drain | (nq0 >= 32) | (nq1 >= 32) | (nq2 >= 8))) continue;
             // stage 2: a queue is drawn when it holds a full group (or, at the end, whatever is left)
-#pragma unroll 1
-            for (int which = 0; which < 2; which++) {
-                const int nq = which ? nq1 : nq0;
-                if (nq >= 32 || (drain && nq > 0)) {
-                    const int take = min(nq, 32);
+            if (QUADS) {
+                while (nq1 >= 32 || (drain && nq1 > 0)) {
+                    const int take = min(nq1, 32);
                     if (lane < take) {
-                        const uint4 q = slds4(queue_sa + 16u * (uint32_t)(which * QN + nq - take + lane));
-                        draw_inside<RES, SMALL>(planes_sa + q.w * plane_bytes, res, rcp_sa,
-                                                (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
-                                                (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
+                        const uint4 q = slds4(queue_sa + 16u * (uint32_t)(Q1 + nq1 - take + lane));
+                        draw_quad_pattern64(planes_sa, plane_bytes, a.quad_table, q.x, q.y);
                     }
-                    if (which) nq1 -= take; else nq0 -= take;
+                    nq1 -= take;
                     __syncwarp();
+                }
+                if (nq0 >= 32 || (drain && nq0 > 0)) {
+                    const int take = min(nq0, 32);
+                    if (lane < take) {
+                        const uint4 q = slds4(queue_sa + 16u * (uint32_t)(nq0 - take + lane));
+                        draw_lines3_64(planes_sa + q.z * plane_bytes, rcp_sa, q.x, q.y);
+                    }
+                    nq0 -= take;
+                    __syncwarp();
+                }
+            } else {
+#pragma unroll 1
+                for (int which = 0; which < 2; which++) {
+                    const int nq = which ? nq1 : nq0;
+                    if (nq >= 32 || (drain && nq > 0)) {
+                        const int take = min(nq, 32);
+                        if (lane < take) {
+                            const uint4 q = slds4(queue_sa + 16u * (uint32_t)(which * Q1 + nq - take + lane));
+                            draw_inside<RES, SMALL>(planes_sa + q.w * plane_bytes, res, rcp_sa,
+                                                    (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
+                                                    (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16);
+                        }
+                        if (which) nq1 -= take; else nq0 -= take;
+                        __syncwarp();
+                    }
                 }
             }
             // faces that cross the border: 4 lanes per face (its three outline edges and its fill), 8 faces per round
+#ifdef TDS_EXP_NOCLIP
+            nq2 = 0;
+#endif
             while (nq2 >= 8 || (drain && nq2 > 0)) {
                 const int take = min(nq2, 8);
                 const unsigned lanes = take >= 8 ? 0xffffffffu : (1u << (4 * take)) - 1u;
                 if ((lane >> 2) < take) {
-                    const uint4 q = slds4(queue_sa + 16u * (uint32_t)(2 * QN + nq2 - take + (lane >> 2)));
+                    const uint4 q = slds4(queue_sa + 16u * (uint32_t)(Q2 + nq2 - take + (lane >> 2)));
                     draw_clipped_part<RES>(planes_sa + q.w * plane_bytes, res, rcp_sa,
                                            (int16_t)(q.x & 0xffff), (int32_t)q.x >> 16, (int16_t)(q.y & 0xffff),
                                            (int32_t)q.y >> 16, (int16_t)(q.z & 0xffff), (int32_t)q.z >> 16, lane & 3, lanes);
@@ -807,6 +944,9 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         // slices of the top-most draw rank (registers), then walks the 32 columns: one 128-bit store per channel
         // (float32), one 32-bit store per channel (uint8) or one 32-bit store (draw ranks).
         const int nyq = res >> 2;
+#ifdef TDS_EXP_NORESOLVE
+        if (a.ncam >= 0) continue;
+#endif
         for (int item = tid; item < W32 * nyq; item += G) {
             const int w = item / nyq, yq = item - w * nyq;
             uint32_t sl[NS][4];

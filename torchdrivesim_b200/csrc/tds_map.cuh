@@ -57,4 +57,7 @@ struct tds_map {
 
 namespace tds {
 int gather_maps(const tds_map_t* const* maps, int32_t n_maps, MapSetDev& out);
+// coverage patterns of sliver quads (tds_quad_table.h) on the current device: built and uploaded by the first
+// tds_map_create on that device (never inside a raster call, which may be under CUDA-graph capture); NULL before that
+const void* quad_table_device();
 }

@@ -173,19 +173,21 @@ TDS_HD void row_tri_step(RowTri& t, int W, int y, Emit&& emit) {
 
 // The same pixel set spread over FOUR cooperating workers (the raster kernel: four lanes per face that crosses the
 // image border; a third of the code of row_tri_setup + row_tri_step).  Worker `part` = 0, 1, 2
-// walks the runs of the outline edge v2->v0, v0->v1, v1->v2 in its rows; worker 3 sets the fill up and hands it to all
-// four through share(value) -> the value held by worker 3 (a shuffle on the GPU, the identity on the host, where one
-// caller plays the four workers in turn); then every worker takes each fourth fill row, evaluated from the set-up
-// alone.  emit(y, lo, hi) per interval: the intervals of a row arrive from different workers; a bit-per-pixel target
-// ORs them, so the order does not matter.
+// A triangle that crosses the image border, drawn by FOUR cooperating workers (part = 0..3; four lanes on the GPU, one
+// caller playing them in turn on the host).  Workers 0..2 walk the clipped runs of the outline edges v2->v0, v0->v1,
+// v1->v2 and compute the 16.16 fill slope of their edge; share(value, w) -> the value held by worker w (a shuffle on the
+// GPU).  Then every worker takes each fourth fill row: the span of a row joins the fill columns of the edges that are
+// active in it (edge top -> bottom is active in rows [y_top, y_bottom - 1]: exactly two of them in every fill row),
+// evaluated from the vertices and the three slopes alone.  emit(y, lo, hi) per interval: the intervals of a row arrive
+// from different workers; a bit-per-pixel target ORs them, so the order does not matter.
 template <class RcpFn, class Emit, class Share>
 TDS_HD void row_tri_part(int W, int H, int x0, int y0, int x1, int y1, int x2, int y2, int part, RcpFn&& rcp_of, Emit&& emit,
                          Share&& share) {
-    RowFill f;
-    f.fylo = 1; f.fyhi = 0; f.my = 0; f.ty = 0; f.xa = 0; f.dTB = 0; f.xT = 0; f.dTM = 0; f.xM = 0; f.dMB = 0;
+    int slope = 0;
     if (part < 3) {
         const int ax = part == 0 ? x2 : (part == 1 ? x0 : x1), ay = part == 0 ? y2 : (part == 1 ? y0 : y1);
         const int bx = part == 0 ? x0 : (part == 1 ? x1 : x2), by = part == 0 ? y0 : (part == 1 ? y1 : y2);
+        if (ay != by) slope = ay < by ? edge_dx32(ax, ay, bx, by) : edge_dx32(bx, by, ax, ay);
         RowEdge e;
         row_edge_setup(W, H, ax, ay, bx, by, e, rcp_of);
 #if defined(__CUDA_ARCH__)
@@ -196,19 +198,27 @@ TDS_HD void row_tri_part(int W, int H, int x0, int y0, int x1, int y1, int x2, i
             row_edge_step(e, y, lo, hi);
             emit(y, lo, hi);
         }
-    } else {
-        row_fill_setup(W, H, x0, y0, x1, y1, x2, y2, f);
     }
-    // the fill: rows fylo + part, fylo + part + 4, ... (row_fill_at: the span of a row from the set-up alone)
-    f.fylo = share(f.fylo); f.fyhi = share(f.fyhi); f.my = share(f.my); f.ty = share(f.ty);
-    f.xa = share(f.xa); f.dTB = share(f.dTB); f.xT = share(f.xT); f.dTM = share(f.dTM); f.xM = share(f.xM); f.dMB = share(f.dMB);
+    // the fill (FillConvexPoly): nothing when the bounding box misses the image; rows [max(y_top, 0), min(y_bottom - 1, H - 1)]
+    const int d20 = share(slope, 0), d01 = share(slope, 1), d12 = share(slope, 2);
+    int xmin = x0 < x1 ? x0 : x1; xmin = xmin < x2 ? xmin : x2;
+    int xmax = x0 > x1 ? x0 : x1; xmax = xmax > x2 ? xmax : x2;
+    int ty = y0 < y1 ? y0 : y1; ty = ty < y2 ? ty : y2;
+    int by = y0 > y1 ? y0 : y1; by = by > y2 ? by : y2;
+    if (xmax < 0 || by < 0 || xmin >= W || ty >= H) return;
+    const int ylo = ty > 0 ? ty : 0, yhi = (by - 1) < (H - 1) ? (by - 1) : (H - 1);
+    // edges oriented top -> bottom: (x at the top) << 16, top row, bottom row
+    const int t20 = y2 < y0 ? y2 : y0, b20 = y2 < y0 ? y0 : y2, s20 = (y2 < y0 ? x2 : x0) << 16;
+    const int t01 = y0 < y1 ? y0 : y1, b01 = y0 < y1 ? y1 : y0, s01 = (y0 < y1 ? x0 : x1) << 16;
+    const int t12 = y1 < y2 ? y1 : y2, b12 = y1 < y2 ? y2 : y1, s12 = (y1 < y2 ? x1 : x2) << 16;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int y = f.fylo + part; y <= f.fyhi; y += 4) {
-        const int xb = y < f.my ? f.xT + (y - f.ty) * f.dTM : f.xM + (y - f.my) * f.dMB;
-        const int xa = f.xa + (y - f.fylo) * f.dTB;
-        const int xl = xa < xb ? xa : xb, xr = xa < xb ? xb : xa;
+    for (int y = ylo + part; y <= yhi; y += 4) {
+        int xl = 0x7fffffff, xr = -0x7fffffff - 1;
+        if (t20 <= y && y < b20) { const int x = s20 + (y - t20) * d20; xl = xl < x ? xl : x; xr = xr > x ? xr : x; }
+        if (t01 <= y && y < b01) { const int x = s01 + (y - t01) * d01; xl = xl < x ? xl : x; xr = xr > x ? xr : x; }
+        if (t12 <= y && y < b12) { const int x = s12 + (y - t12) * d12; xl = xl < x ? xl : x; xr = xr > x ? xr : x; }
         const int c1 = (xl + 32768) >> 16, c2 = (xr + 32768) >> 16;
         if (c2 >= 0 && c1 < W) emit(y, c1 < 0 ? 0 : c1, c2 >= W ? W - 1 : c2);
     }
@@ -351,6 +361,99 @@ TDS_HD void fast_tri_rows(FastTri& t, Emit&& emit) {
         int L = xl >> 16, R = xr >> 16;
         L = L < l1 ? L : l1; L = L < l2 ? L : l2; L = L < eL ? L : eL;
         R = R > h1 ? R : h1; R = R > h2 ? R : h2; R = R > eH ? R : eH;
+        emit(y, L, R);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A triangle INSIDE the image as three line walkers: each edge is an 8-connected line with the 16.16 fill column of
+// FillConvexPoly's edge walker, and a row is ONE interval - from the left-most to the right-most of the lines' pixels
+// and fill columns in that row.  (The outline is the three lines; the fill span of a row joins the fill columns of the
+// two edges that are active in it; all three sets lie in one interval because the outline is convex.)  No
+// middle-vertex switch, no vertex sorting: the three walkers are the same code, active in their own row ranges.
+
+struct LineWalk {
+    FastEdge e;      // LineIterator runs of the line, stepped once per row
+    int xf, d;       // 16.16 fill column (+0.5) of the row that is evaluated next, and its slope
+    int t, len;      // rows since the line's first row (negative before it), index of its last row
+};
+
+// line (px,py)-(qx,qy) inside the image (up to 128 pixels: slopes through the reciprocal table)
+template <class RcpFn>
+TDS_HD void line_walk_setup(int px, int py, int qx, int qy, LineWalk& l, RcpFn&& rcp_of) {
+    if (qy < py) { int w = px; px = qx; qx = w; w = py; py = qy; qy = w; }
+    const int dy = qy - py;
+    l.d = dy > 0 ? edge_dx_rcp(qx - px, dy, rcp_of(dy)) : 0;
+    l.xf = (px << 16) + 32768;
+    l.t = py;            // lines3_setup turns this into (first row of the item - py)
+    l.len = dy;
+    fast_edge_setup(px, py, qx, qy, l.e, rcp_of);
+    if (dy == 0) {
+        // a horizontal line is a single run; fast_edge_setup hands it out at the FIRST step, but this walker may be
+        // stepped before its row: keep the run for the step whose numerator reaches 2^20 (mulhi(2^20, 2^32 - 1) > dx)
+        l.e.rcp = 0xffffffffu;
+        l.e.n = 1 << 20;
+        l.e.b1 = 1 << 20;
+        l.e.cur = l.e.lx;
+    }
+}
+
+struct Lines3 {
+    LineWalk l[3];
+    int y0, y1;
+};
+
+template <class RcpFn>
+TDS_HD void lines3_setup(int x0, int y0_, int x1, int y1_, int x2, int y2_, Lines3& q, RcpFn&& rcp_of) {
+    line_walk_setup(x0, y0_, x1, y1_, q.l[0], rcp_of);
+    line_walk_setup(x1, y1_, x2, y2_, q.l[1], rcp_of);
+    line_walk_setup(x2, y2_, x0, y0_, q.l[2], rcp_of);
+    int y0 = q.l[0].t, y1 = q.l[0].t + q.l[0].len;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 1; k < 3; k++) {
+        const int ys = q.l[k].t, ye = ys + q.l[k].len;
+        y0 = y0 < ys ? y0 : ys; y1 = y1 > ye ? y1 : ye;
+    }
+    q.y0 = y0; q.y1 = y1;
+    // all three walkers start at row y0: a LineIterator walker stepped before its first row stays where it is (the
+    // clamps of fast_edge_step), the fill column is linear
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; k++) {
+        const int lead = q.l[k].t - y0;         // rows until the line starts
+        q.l[k].e.n -= lead * q.l[k].e.b1;
+        q.l[k].xf -= lead * q.l[k].d;
+        q.l[k].t = -lead;
+    }
+}
+
+// emit(y, L, R) once per row y0..y1, in order
+template <class Emit>
+TDS_HD void lines3_rows(Lines3& q, Emit&& emit) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int y = q.y0; y <= q.y1; y++) {
+        int L = 0x7fffffff, R = -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 3; k++) {
+            LineWalk& l = q.l[k];
+            int lo, hi;
+            fast_edge_step(l.e, lo, hi);
+            const int xf = l.xf >> 16;
+            l.xf += l.d;
+            const bool on = (unsigned)l.t <= (unsigned)l.len;       // 0 <= t <= len
+            l.t++;
+            if (on) {
+                lo = lo < xf ? lo : xf; hi = hi > xf ? hi : xf;
+                L = L < lo ? L : lo; R = R > hi ? R : hi;
+            }
+        }
         emit(y, L, R);
     }
 }
