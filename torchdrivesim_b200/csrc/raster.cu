@@ -155,6 +155,34 @@ static int raster_scratch(int64_t ncam, cudaStream_t st, int32_t** out) {
     return TDS_OK;
 }
 
+// Hand-over buffers of the two-pass 64x64 kernels (bitplanes + lists of border-crossing faces), library-owned per
+// (device, stream) and at most kTwoPassBytes: more cameras than fit are rendered in rounds.  Allocated by the first call
+// on a stream; inside a CUDA graph capture a missing buffer is not an error - the call falls back to the one-pass kernel.
+constexpr int64_t kTwoPassBytes = 512ll << 20;
+static uint8_t* two_pass_scratch(int64_t bytes, cudaStream_t st) {
+    struct Entry { int dev; cudaStream_t st; uint8_t* ptr; int64_t cap; };
+    static std::mutex mu;
+    static std::vector<Entry> entries;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* hit = nullptr;
+    for (auto& e : entries)
+        if (e.dev == dev && e.st == st) hit = &e;
+    if (!hit) { entries.push_back({dev, st, nullptr, 0}); hit = &entries.back(); }
+    if (hit->cap < bytes) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs != cudaStreamCaptureStatusNone) return nullptr;
+        uint8_t* p = nullptr;
+        if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (hit->ptr) { cudaStreamSynchronize(st); cudaFree(hit->ptr); }
+        hit->ptr = p;
+        hit->cap = bytes;
+    }
+    return hit->ptr;
+}
+
 extern "C" int32_t tds_raster_rank_table(const tds_palette_t* palette, uint8_t h_rgb[][3], int32_t* h_class) {
     if (!palette || !h_rgb || palette->n_classes < 0 || palette->n_classes > TDS_MAX_CLASSES) return 0;
     PaletteDev pal = {};
@@ -256,6 +284,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
     a.next_cam = scratch;              // work counter of the first launch
     a.redo = scratch + 4;              // [0] = count, [4 ..] = cameras
     a.cam_list = nullptr;
+    a.cam_begin = 0; a.planes_io = nullptr; a.clip_list = nullptr; a.clip_count = nullptr;
 
     // Threads per camera.  Tiles up to 96x96: a warp per camera, 4 cameras in flight per CTA (at 128x128 only 16 such
     // warps fit an SM: 4 sets of bitplanes per CTA).  Above: a CTA of 4, 8 or 16 independent warps per camera - the
@@ -290,7 +319,45 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
         if (G == 128) return launch_g128(cfg, f32, is_lean);
         return launch_g256(cfg, G, f32, is_lean);
     };
-    if (int e = go(c, lean)) return e;
+    // Two passes for the 64x64 LEAN kernels: draw (everything but the border-crossing faces) -> finish (those faces +
+    // resolve), handing bitplanes and face lists over in library-owned memory.  Each program fits the instruction caches
+    // where the one-pass kernel does not.  TDS_RASTER_TWO_PASS=0 forces one pass.
+    bool two_pass = lean && G == 32 && g32_two_pass_available(c);
+    if (const char* e = getenv("TDS_RASTER_TWO_PASS")) two_pass = two_pass && atoi(e) != 0;
+    int64_t round_cams = 0;
+    uint8_t* hand = nullptr;
+    if (two_pass) {
+        const int64_t per_cam = two_pass_bytes_per_camera(K);
+        round_cams = std::min<int64_t>(ncam, std::max<int64_t>(kTwoPassBytes / per_cam, 1));
+        hand = two_pass_scratch(round_cams * per_cam, st);
+        two_pass = hand != nullptr;
+    }
+    if (two_pass) {
+        const int KS = K <= 5 ? 5 : 7;
+        if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);   // the timed region spans both passes (and all rounds)
+        for (int64_t begin = 0; begin < ncam; begin += round_cams) {
+            const int64_t end = std::min<int64_t>(ncam, begin + round_cams);
+            LaunchCfg d = c;
+            d.ev_start = d.ev_stop = nullptr;
+            d.ncam = end;
+            d.a.ncam = (int32_t)end;
+            d.a.cam_begin = (int32_t)begin;
+            d.a.planes_io = reinterpret_cast<uint32_t*>(hand);
+            d.a.clip_list = reinterpret_cast<uint4*>(hand + round_cams * KS * 512);
+            d.a.clip_count = reinterpret_cast<int32_t*>(hand + round_cams * (KS * 512 + (int64_t)kClipCap * 16));
+            // work counters: [0] draw pass, [2] finish pass (the redo list at [4..] spans all rounds)
+            TDS_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), st));
+            d.a.next_cam = scratch;
+            if (int e = launch_g32_draw(d)) return e;
+            LaunchCfg f = d;
+            f.a.next_cam = scratch + 2;
+            f.ev_start = f.ev_stop = nullptr;
+            if (int e = launch_g32_finish(f, f32)) return e;
+        }
+        if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+    } else {
+        if (int e = go(c, lean)) return e;
+    }
     if (lean) {
         // the cameras on the list (normally none: every CTA of this launch leaves at once)
         LaunchCfg r = c;

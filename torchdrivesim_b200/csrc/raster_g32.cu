@@ -23,4 +23,17 @@ int launch_g32(const LaunchCfg& c, bool f32, bool lean) {
     return pick<0, 5, 0>(c, f32, lean, false);
 }
 
+// ---- two-pass form of the 64x64 LEAN kernels (static shared memory, NS = 3)
+bool g32_two_pass_available(const LaunchCfg& c) { return c.res == 64 && c.K <= 7; }
+
+int launch_g32_draw(const LaunchCfg& c) {
+    if (c.K <= 5) return launch_variant(raster_kernel<32, 64, 3, true, 5, true, true, 1>, c, 4, 128, true);
+    return launch_variant(raster_kernel<32, 64, 3, true, 7, true, true, 1>, c, 4, 128, true);
+}
+
+int launch_g32_finish(const LaunchCfg& c, bool f32) {
+    if (c.K <= 5) return f32 ? launch_finish(raster_finish_kernel<3, 5, true>, c) : launch_finish(raster_finish_kernel<3, 5, false>, c);
+    return f32 ? launch_finish(raster_finish_kernel<3, 7, true>, c) : launch_finish(raster_finish_kernel<3, 7, false>, c);
+}
+
 }  // namespace tds_raster

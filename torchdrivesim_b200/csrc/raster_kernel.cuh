@@ -340,7 +340,16 @@ struct RasterArgs {
     int32_t* redo;             // [0] = number of cameras in redo[4..]: LEAN kernels list the cameras they cannot finish
                                // (coordinates beyond +-8000 pixels); a general kernel launched with cam_list = redo
     const int32_t* cam_list;   // NULL: cameras 0..ncam-1; else the general kernel renders cam_list[4 + i], i < cam_list[0]
+    // two-pass form of the 64x64 LEAN kernels: the draw pass (PHASE 1) renders cameras [cam_begin, ncam) except the faces
+    // that cross the image border, which it lists per camera, and hands the bitplanes over; the finish pass (raster_finish_kernel)
+    // draws the listed faces and resolves.  Each pass is a smaller program than the two together: instruction fetch, not
+    // instruction count, limits the one-pass kernel.  Indexed by camera - cam_begin.
+    int32_t cam_begin;
+    uint32_t* planes_io;       // [cameras][KS][res * W32] words
+    uint4* clip_list;          // [cameras][kClipCap] faces: x | y << 16 per vertex, plane
+    int32_t* clip_count;       // [cameras] listed faces; -1: the camera is on the redo list (the general kernel renders it)
 };
+constexpr int kClipCap = 192;  // border-crossing faces a camera can list (60 on average at 64x64 / 35 m, 150 at a junction); more: redo
 
 constexpr int kRows = tds::kMaxRasterRows;
 constexpr int kQueues = 3;                          // short inside, tall inside, clipped
@@ -413,8 +422,109 @@ __device__ __forceinline__ void project2(const Camera& cam, uint64_t X, uint64_t
     }
 }
 
+// ---- resolve painter's order and expand through the colour LUT: out[cam][ch][x][y].
+template <int G, int RES, int NS, bool F32>
+__device__ __forceinline__ void resolve_camera(const RasterArgs& a, int camid, int tid, int res, int W32, int K, uint32_t planes_sa,
+                                               uint32_t plane_bytes, uint32_t lut_sa) {
+    // A thread owns 4 image rows y of one 32-pixel word column: it folds the K planes of those rows into bit
+    // slices of the top-most draw rank (registers), then walks the 32 columns: one 128-bit store per channel
+    // (float32), one 32-bit store per channel (uint8) or one 32-bit store (draw ranks).
+    const int nyq = res >> 2;
+    for (int item = tid; item < W32 * nyq; item += G) {
+        const int w = item / nyq, yq = item - w * nyq;
+        uint32_t sl[NS][4];
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) sl[s][k] = 0u;
+        uint32_t rem[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll 1
+        for (int p = K - 1; p >= 0; p--) {          // last drawn = on top
+            const uint4 v = slds4(planes_sa + (uint32_t)p * plane_bytes + 4u * (uint32_t)(w * res + 4 * yq));
+            const uint32_t pw[4] = {v.x, v.y, v.z, v.w};
+            const int id = p + 1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t e = pw[k] & rem[k];
+                rem[k] &= ~e;
+#pragma unroll
+                for (int s = 0; s < NS; s++) sl[s][k] |= ((id >> s) & 1) ? e : 0u;
+            }
+        }
+        const int nx = min(32, res - 32 * w);
+        const int plane_stride = res * res;
+        const int64_t pix = (int64_t)(32 * w) * res + 4 * yq;
+        const bool rgb = F32 || a.out_format != TDS_IMAGE_RANK;
+        uint8_t* o = reinterpret_cast<uint8_t*>(a.out) + ((int64_t)camid * (rgb ? 3 : 1) * plane_stride + pix) * (F32 ? 4 : 1);
+        // draw rank of column x of the thread's row k = bit x of the NS slices.  NS = 3: the slices are interleaved once
+        // into nibbles - column 4 j + t of row k is nibble j of nib[t][k] - so a column costs a shift and a mask.
+        constexpr int NT = NS == 3 ? 4 : 1;
+        uint32_t nib[NT][4];
+        if (NS == 3) {
+#pragma unroll
+            for (int t = 0; t < NT; t++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    nib[t][k] = ((sl[0][k] >> t) & 0x11111111u) | (((sl[1][k] >> t) & 0x11111111u) << 1) |
+                                (((sl[2 % NS][k] >> t) & 0x11111111u) << 2);
+        }
+        auto rank_of = [&](int x, int t, int k) -> uint32_t {
+            if (NS == 3) return (nib[t % NT][k] >> (x - t)) & 7u;          // x - t = 4 j
+            uint32_t v = 0u;
+#pragma unroll
+            for (int q = 0; q < NS; q++) v |= ((sl[q][k] >> x) & 1u) << q;
+            return v;
+        };
+        if (F32) {
+#pragma unroll 1
+            for (int x0 = 0; x0 < nx; x0 += NT) {
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const int x = x0 + t;
+                    float4 c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint4 q = slds4(lut_sa + 16u * rank_of(x, t, k));
+                        c[k] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), 0.f);
+                    }
+                    float* of = reinterpret_cast<float*>(o) + (int64_t)x * res;
+                    tds::st_cs_f4(reinterpret_cast<float4*>(of), make_float4(c[0].x, c[1].x, c[2].x, c[3].x));
+                    tds::st_cs_f4(reinterpret_cast<float4*>(of + plane_stride), make_float4(c[0].y, c[1].y, c[2].y, c[3].y));
+                    tds::st_cs_f4(reinterpret_cast<float4*>(of + 2 * plane_stride), make_float4(c[0].z, c[1].z, c[2].z, c[3].z));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int x0 = 0; x0 < nx; x0 += NT) {
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const int x = x0 + t;
+                    uint32_t c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t v = rank_of(x, t, k);
+                        c[k] = rgb ? slds(lut_sa + 16u * v + 12u) : v;
+                    }
+                    // byte b of the four rows -> one word (rows 4 yq .. 4 yq + 3 are consecutive bytes of the output)
+                    uint8_t* ob = o + (int64_t)x * res;
+                    const uint32_t lo01 = __byte_perm(c[0], c[1], 0x5140), lo23 = __byte_perm(c[2], c[3], 0x5140);   // (r0 r1 g0 g1), (r2 r3 g2 g3)
+                    tds::st_cs_u32(reinterpret_cast<uint32_t*>(ob), __byte_perm(lo01, lo23, 0x5410));
+                    if (rgb) {
+                        const uint32_t hi01 = __byte_perm(c[0], c[1], 0x7362), hi23 = __byte_perm(c[2], c[3], 0x7362);   // (b0 b1 - -), (b2 b3 - -)
+                        tds::st_cs_u32(reinterpret_cast<uint32_t*>(ob + plane_stride), __byte_perm(lo01, lo23, 0x7632));
+                        tds::st_cs_u32(reinterpret_cast<uint32_t*>(ob + 2 * plane_stride), __byte_perm(hi01, hi23, 0x5410));
+                    }
+                }
+            }
+        }
+    }
+}
+
 #ifndef TDS_RASTER_MINB
 #define TDS_RASTER_MINB 7
+#endif
+#ifndef TDS_FINISH_MINB
+#define TDS_FINISH_MINB 8
 #endif
 #ifndef TDS_RASTER_MINB_BIG
 #define TDS_RASTER_MINB_BIG 2
@@ -424,7 +534,7 @@ __device__ __forceinline__ void project2(const Camera& cam, uint64_t X, uint64_t
 // F32: float32 image (else uint8 RGB / draw ranks, a.out_format).  LEAN: the common case only - no
 // per-camera triangles, no per-camera agent classes, and cameras that meet coordinates beyond +-8000 pixels are handed
 // to the general kernel through a.redo: code that is never executed still costs instruction-cache reach
-template <int G, int RES, int NS, bool SMALL, int KS_, bool F32, bool LEAN>
+template <int G, int RES, int NS, bool SMALL, int KS_, bool F32, bool LEAN, int PHASE = 0>
 __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB : (G == 256 ? 2 * TDS_RASTER_MINB_BIG : TDS_RASTER_MINB_BIG)) raster_kernel(MapSetDev maps, RasterArgs a, PaletteDev pal) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int QN = 64;                      // queue capacity per warp and kind
@@ -492,7 +602,10 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         if (!LEAN && a.cam_list) {
             if (camid >= a.cam_list[0]) break;
             camid = a.cam_list[4 + camid];
-        } else if (camid >= a.ncam) break;
+        } else {
+            if (PHASE == 1) camid += a.cam_begin;
+            if (camid >= a.ncam) break;
+        }
         // environment of the camera: camid / Nc through the fp32 reciprocal, fixed with the remainder (exact below 2^22
         // environments, which the launcher checks)
         int b = __float2int_rz(__fdividef((float)camid, (float)a.Nc));
@@ -848,14 +961,20 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                     const int b0 = nq0, b2 = nq2;
                     nq0 += __popc(m0); nq2 += __popc(m2);
                     if (kind >= kShort) {
-                        const int pos = (ins ? b0 : Q2 + b2) + __popc((ins ? m0 : m2) & ((1u << lane) - 1));
+                        const int pos = (ins ? b0 : (PHASE == 1 ? b2 : Q2 + b2)) + __popc((ins ? m0 : m2) & ((1u << lane) - 1));
                         const uint4 item = ins ? make_uint4(pack_vertex8(xy[0], xy[1]) | (pack_vertex8(xy[2], xy[3]) << 16), pack_vertex8(xy[4], xy[5]),
                                                             (uint32_t)plane, 0u)
                                                : make_uint4((uint32_t)(xy[0] & 0xffff) | ((uint32_t)xy[1] << 16),
                                                             (uint32_t)(xy[2] & 0xffff) | ((uint32_t)xy[3] << 16),
                                                             (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
-                        ssts4(queue_sa + 16u * (uint32_t)pos, item);
+                        if (PHASE == 1 && !ins) {
+                            // the finish pass draws the faces that cross the border (nq2 counts them over the whole camera)
+                            if (pos < kClipCap) a.clip_list[(int64_t)(camid - a.cam_begin) * kClipCap + pos] = item;
+                        } else {
+                            ssts4(queue_sa + 16u * (uint32_t)pos, item);
+                        }
                     }
+                    if (PHASE == 1 && nq2 > kClipCap) redo = true;
                 } else {
                     const unsigned m0 = __ballot_sync(0xffffffffu, kind == kShort), m1 = __ballot_sync(0xffffffffu, kind == kTall),
                                    m2 = __ballot_sync(0xffffffffu, kind == kClipped);
@@ -873,7 +992,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                 }
             }
             __syncwarp();
-            if (!(drain | (nq0 >= 32) | (nq1 >= 32) | (nq2 >= 8))) continue;
+            if (!(drain | (nq0 >= 32) | (nq1 >= 32) | (PHASE != 1 && nq2 >= 8))) continue;
             // stage 2: a queue is drawn when it holds a full group (or, at the end, whatever is left)
             if (QUADS) {
                 while (nq1 >= 32 || (drain && nq1 > 0)) {
@@ -912,10 +1031,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                 }
             }
             // faces that cross the border: 4 lanes per face (its three outline edges and its fill), 8 faces per round
-#ifdef TDS_EXP_NOCLIP
-            nq2 = 0;
-#endif
-            while (nq2 >= 8 || (drain && nq2 > 0)) {
+            while (PHASE != 1 && (nq2 >= 8 || (drain && nq2 > 0))) {
                 const int take = min(nq2, 8);
                 const unsigned lanes = take >= 8 ? 0xffffffffu : (1u << (4 * take)) - 1u;
                 if ((lane >> 2) < take) {
@@ -928,117 +1044,112 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                 __syncwarp();
             }
             if (drain) {
-                if ((nq0 | nq1 | nq2) == 0) break;     // a queue held more than one group: drain again
+                if ((nq0 | nq1 | (PHASE == 1 ? 0 : nq2)) == 0) break;     // a queue held more than one group: drain again
             }
         }
         group_sync<G>();
+        bool any_redo = false;
         if (LEAN) {
             // a camera this kernel could not finish exactly goes on the list of the general kernel (which overwrites its image)
-            const bool any = G == 32 ? __any_sync(0xffffffffu, redo) : (__syncthreads_or(redo) != 0);
-            if (any && tid == 0) a.redo[4 + atomicAdd(a.redo, 1)] = camid;
+            any_redo = G == 32 ? __any_sync(0xffffffffu, redo) : (__syncthreads_or(redo) != 0);
+            if (any_redo && tid == 0) a.redo[4 + atomicAdd(a.redo, 1)] = camid;
         }
         group_sync<G>();
 
-        // ---- resolve painter's order and expand through the colour LUT: out[cam][ch][x][y].
-        // A thread owns 4 image rows y of one 32-pixel word column: it folds the K planes of those rows into bit
-        // slices of the top-most draw rank (registers), then walks the 32 columns: one 128-bit store per channel
-        // (float32), one 32-bit store per channel (uint8) or one 32-bit store (draw ranks).
-        const int nyq = res >> 2;
-#ifdef TDS_EXP_NORESOLVE
-        if (a.ncam >= 0) continue;
-#endif
-        for (int item = tid; item < W32 * nyq; item += G) {
-            const int w = item / nyq, yq = item - w * nyq;
-            uint32_t sl[NS][4];
-#pragma unroll
-            for (int s = 0; s < NS; s++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) sl[s][k] = 0u;
-            uint32_t rem[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        // ---- resolve painter's order and expand through the colour LUT (or hand the bitplanes to the finish kernel)
+        if (PHASE == 1) {
+            const int li = camid - a.cam_begin;
+            uint4* po = reinterpret_cast<uint4*>(a.planes_io) + (int64_t)li * (KS * plane_words / 4);
 #pragma unroll 1
-            for (int p = K - 1; p >= 0; p--) {          // last drawn = on top
-                const uint4 v = slds4(planes_sa + (uint32_t)p * plane_bytes + 4u * (uint32_t)(w * res + 4 * yq));
-                const uint32_t pw[4] = {v.x, v.y, v.z, v.w};
-                const int id = p + 1;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t e = pw[k] & rem[k];
-                    rem[k] &= ~e;
-#pragma unroll
-                    for (int s = 0; s < NS; s++) sl[s][k] |= ((id >> s) & 1) ? e : 0u;
-                }
-            }
-            const int nx = min(32, res - 32 * w);
-            const int plane_stride = res * res;
-            const int64_t pix = (int64_t)(32 * w) * res + 4 * yq;
-            const bool rgb = F32 || a.out_format != TDS_IMAGE_RANK;
-            uint8_t* o = reinterpret_cast<uint8_t*>(a.out) + ((int64_t)camid * (rgb ? 3 : 1) * plane_stride + pix) * (F32 ? 4 : 1);
-            // draw rank of column x of the thread's row k = bit x of the NS slices.  NS = 3: the slices are interleaved once
-            // into nibbles - column 4 j + t of row k is nibble j of nib[t][k] - so a column costs a shift and a mask.
-            constexpr int NT = NS == 3 ? 4 : 1;
-            const uint32_t lut_sa = smem_addr(s_lut);
-            uint32_t nib[NT][4];
-            if (NS == 3) {
-#pragma unroll
-                for (int t = 0; t < NT; t++)
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        nib[t][k] = ((sl[0][k] >> t) & 0x11111111u) | (((sl[1][k] >> t) & 0x11111111u) << 1) |
-                                    (((sl[2 % NS][k] >> t) & 0x11111111u) << 2);
-            }
-            auto rank_of = [&](int x, int t, int k) -> uint32_t {
-                if (NS == 3) return (nib[t % NT][k] >> (x - t)) & 7u;          // x - t = 4 j
-                uint32_t v = 0u;
-#pragma unroll
-                for (int q = 0; q < NS; q++) v |= ((sl[q][k] >> x) & 1u) << q;
-                return v;
-            };
-            if (F32) {
-#pragma unroll 1
-                for (int x0 = 0; x0 < nx; x0 += NT) {
-#pragma unroll
-                    for (int t = 0; t < NT; t++) {
-                        const int x = x0 + t;
-                        float4 c[4];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint4 q = slds4(lut_sa + 16u * rank_of(x, t, k));
-                            c[k] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), 0.f);
-                        }
-                        float* of = reinterpret_cast<float*>(o) + (int64_t)x * res;
-                        tds::st_cs_f4(reinterpret_cast<float4*>(of), make_float4(c[0].x, c[1].x, c[2].x, c[3].x));
-                        tds::st_cs_f4(reinterpret_cast<float4*>(of + plane_stride), make_float4(c[0].y, c[1].y, c[2].y, c[3].y));
-                        tds::st_cs_f4(reinterpret_cast<float4*>(of + 2 * plane_stride), make_float4(c[0].z, c[1].z, c[2].z, c[3].z));
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (int x0 = 0; x0 < nx; x0 += NT) {
-#pragma unroll
-                    for (int t = 0; t < NT; t++) {
-                        const int x = x0 + t;
-                        uint32_t c[4];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t v = rank_of(x, t, k);
-                            c[k] = rgb ? slds(lut_sa + 16u * v + 12u) : v;
-                        }
-                        // byte b of the four rows -> one word (rows 4 yq .. 4 yq + 3 are consecutive bytes of the output)
-                        uint8_t* ob = o + (int64_t)x * res;
-                        const uint32_t lo01 = __byte_perm(c[0], c[1], 0x5140), lo23 = __byte_perm(c[2], c[3], 0x5140);   // (r0 r1 g0 g1), (r2 r3 g2 g3)
-                        tds::st_cs_u32(reinterpret_cast<uint32_t*>(ob), __byte_perm(lo01, lo23, 0x5410));
-                        if (rgb) {
-                            const uint32_t hi01 = __byte_perm(c[0], c[1], 0x7362), hi23 = __byte_perm(c[2], c[3], 0x7362);   // (b0 b1 - -), (b2 b3 - -)
-                            tds::st_cs_u32(reinterpret_cast<uint32_t*>(ob + plane_stride), __byte_perm(lo01, lo23, 0x7632));
-                            tds::st_cs_u32(reinterpret_cast<uint32_t*>(ob + 2 * plane_stride), __byte_perm(hi01, hi23, 0x5410));
-                        }
-                    }
-                }
-            }
+            for (int i = tid; i < K * plane_words / 4; i += G) po[i] = slds4(planes_sa + 16u * (uint32_t)i);
+            if (tid == 0) a.clip_count[li] = any_redo ? -1 : nq2;   // -1: the general kernel renders this camera
+        } else {
+            resolve_camera<G, RES, NS, F32>(a, camid, tid, res, W32, K, planes_sa, plane_bytes, smem_addr(s_lut));
         }
     }
 }
 
+
+// ---- finish pass of the two-pass 64x64 form: bitplanes of the draw pass + its list of border-crossing faces -> image.
+// A warp per camera, 4 cameras in flight per CTA; the program is the clipped-face path and the resolve, nothing else.
+// The hand-over data of the NEXT camera (bitplanes by cp.async into the other half of a double buffer, face count and
+// the first eight faces into registers) is requested before the current camera is drawn: the pass is bound by the
+// latency of these loads and by the 3.2 GB of image it writes, not by instructions.
+__device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NS, int KS, bool F32>
+__global__ void __launch_bounds__(128, TDS_FINISH_MINB) raster_finish_kernel(RasterArgs a, PaletteDev pal) {
+    constexpr int RES = 64, W32 = 2, PLANE_WORDS = RES * W32;
+    __shared__ float4 s_lut[TDS_MAX_CLASSES + 1];
+    __shared__ __align__(16) uint32_t s_rcp[RES + 4];
+    __shared__ __align__(16) uint32_t s_planes[4][2][KS * PLANE_WORDS];
+    const int K = pal.n_classes;
+    for (int i = threadIdx.x; i <= K; i += blockDim.x) {
+        const float* c = pal.rgb[i == 0 ? 0 : pal.order[i - 1] + 1];
+        s_lut[i] = make_float4(c[0], c[1], c[2], __uint_as_float((uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16)));
+    }
+    for (int i = threadIdx.x; i <= RES; i += blockDim.x) s_rcp[i] = g_rcp.v[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t buf_sa[2] = {smem_addr(s_planes[threadIdx.x >> 5][0]), smem_addr(s_planes[threadIdx.x >> 5][1])};
+    const uint32_t rcp_sa = smem_addr(s_rcp), lut_sa = smem_addr(s_lut);
+    constexpr uint32_t plane_bytes = 4u * PLANE_WORDS;
+    const int n_local = a.ncam - a.cam_begin;
+
+    // request camera li: planes -> buffer b (one commit group), count and first faces -> registers
+    auto fetch = [&](int& li, int& count, uint4& q0, int b) {
+        li = 0;
+        if (lane == 0) li = atomicAdd(a.next_cam, 1);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        count = -1;
+        q0 = make_uint4(0u, 0u, 0u, 0u);
+        if (li < n_local) {
+            const uint4* pi = reinterpret_cast<const uint4*>(a.planes_io) + (int64_t)li * (KS * PLANE_WORDS / 4);
+#pragma unroll 1
+            for (int i = lane; i < K * PLANE_WORDS / 4; i += 32) cp_async16(buf_sa[b] + 16u * (uint32_t)i, pi + i);
+            count = a.clip_count[li];
+            q0 = a.clip_list[(int64_t)li * kClipCap + (lane >> 2)];     // slots past the count hold stale data: not used
+        }
+        cp_async_commit();
+    };
+
+    int li, count, b = 0;
+    uint4 q0;
+    fetch(li, count, q0, 0);
+    while (li < n_local) {
+        int li_next, count_next;
+        uint4 q0_next;
+        __syncwarp();                               // the resolve of the camera before last has read the other buffer
+        fetch(li_next, count_next, q0_next, b ^ 1);
+        cp_async_wait<1>();                         // this camera's planes have landed (the next one's may be in flight)
+        __syncwarp();
+        if (count >= 0) {                           // -1: on the redo list, the general kernel renders this camera
+            const int camid = li + a.cam_begin;
+            const uint32_t planes_sa = buf_sa[b];
+            const uint4* faces = a.clip_list + (int64_t)li * kClipCap;
+#pragma unroll 1
+            for (int i0 = 0; i0 < count; i0 += 8) {
+                const int take = min(count - i0, 8);
+                const unsigned lanes = take >= 8 ? 0xffffffffu : (1u << (4 * take)) - 1u;
+                uint4 q_after = q0;
+                if (i0 + 8 < count) q_after = faces[i0 + 8 + (lane >> 2)];          // the next round's faces, ahead of the draw
+                if ((lane >> 2) < take)
+                    draw_clipped_part<RES>(planes_sa + q0.w * plane_bytes, RES, rcp_sa, (int16_t)(q0.x & 0xffff), (int32_t)q0.x >> 16,
+                                           (int16_t)(q0.y & 0xffff), (int32_t)q0.y >> 16, (int16_t)(q0.z & 0xffff), (int32_t)q0.z >> 16, lane & 3, lanes);
+                q0 = q_after;
+                __syncwarp();
+            }
+            resolve_camera<32, RES, NS, F32>(a, camid, lane, RES, W32, K, planes_sa, plane_bytes, lut_sa);
+        }
+        li = li_next; count = count_next; q0 = q0_next; b ^= 1;
+    }
+    cp_async_wait<0>();
+}
 
 // ---- launch of one kernel variant (shared by the translation units that instantiate the variants)
 struct LaunchCfg {
@@ -1062,7 +1173,7 @@ int launch_variant(Kernel kernel, const LaunchCfg& c, int groups, int threads, b
     TDS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     TDS_REQUIRE(per_sm >= 1, "raster: kernel does not fit an SM (res=%d, %d classes)", c.res, c.K);
     // persistent grid: every resident CTA slot of the GPU, cameras pulled from a global counter
-    const int64_t want = (c.ncam + groups - 1) / groups;
+    const int64_t want = (c.ncam - c.a.cam_begin + groups - 1) / groups;
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)c.sms * per_sm);
     if (c.ev_start && c.ev_stop) cudaEventRecord(c.ev_start, c.st);
     kernel<<<grid, threads, smem, c.st>>>(c.set, c.a, c.pal);
@@ -1070,6 +1181,25 @@ int launch_variant(Kernel kernel, const LaunchCfg& c, int groups, int threads, b
     TDS_LAUNCH_OK();
     return TDS_OK;
 }
+
+template <class Kernel>
+int launch_finish(Kernel kernel, const LaunchCfg& c) {
+    int per_sm = 0;
+    TDS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0));
+    TDS_REQUIRE(per_sm >= 1, "raster: finish kernel does not fit an SM");
+    const int64_t cams = c.ncam - c.a.cam_begin;
+    const unsigned grid = (unsigned)std::min<int64_t>((cams + 3) / 4, (int64_t)c.sms * per_sm);
+    kernel<<<grid, 128, 0, c.st>>>(c.a, c.pal);
+    TDS_LAUNCH_OK();
+    return TDS_OK;
+}
+
+// two-pass form (64x64 tiles, LEAN, K <= 7): launch_g32_draw = pass 1, launch_g32_finish = pass 2 (raster_g32.cu)
+bool g32_two_pass_available(const LaunchCfg& c);
+int launch_g32_draw(const LaunchCfg& c);
+int launch_g32_finish(const LaunchCfg& c, bool f32);
+// bytes per camera of the hand-over buffers: bitplanes, face list, face count
+inline int64_t two_pass_bytes_per_camera(int K) { return (int64_t)(K <= 5 ? 5 : 7) * 512 + (int64_t)kClipCap * 16 + 4; }
 
 // defined in raster_g32.cu / raster_g128.cu / raster_g256.cu: picks the instantiation for (G, res, K, format, lean)
 int launch_g32(const LaunchCfg& c, bool f32, bool lean);

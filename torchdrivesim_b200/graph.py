@@ -68,7 +68,9 @@ class GraphedHotPath:
         torch.cuda.synchronize(dev)
         self._restore(saved)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        # captured on the stream of the warm-up: the library keys its scratch buffers by (device, stream), and a buffer
+        # that the warm-up allocated must be the one the captured kernels find
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=s):
             self._body()
         self._restore(saved)
 

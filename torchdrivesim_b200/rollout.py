@@ -82,7 +82,9 @@ class FusedRollout:
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        # captured on the stream of the warm-up: the library keys its scratch buffers by (device, stream), and a buffer
+        # that the warm-up allocated must be the one the captured kernels find
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=s):
             self._body()
 
     # ---- the fixed launch sequence (eager during warm-up, recorded once) --------------------------------------
