@@ -477,10 +477,12 @@ def run_ours(args):
             "e2e_device_images": {"value": e2e["device_images"], "unit": "agent-env-steps/s",
                                   "h2d_bytes_per_step": int(h_act[0].numel() * 4), "d2h_bytes_per_step": int(small_out),
                                   "note": "same, images stay in HBM for a GPU consumer (the reference API returns device tensors)"},
-            # per step, all ours (csrc/): kin_fwd, agent_boxes (cameras), dyn_prep, raster (LEAN) + raster (general, on the
-            # LEAN kernel's redo list), agent_boxes (boxes), allpairs_fwd, offroad_fwd, infraction_metrics; no library kernel
+            # per step, all ours (csrc/): kin_fwd, agent_boxes (cameras), dyn_prep, raster draw pass, raster finish pass, raster
+            # (general kernel, on the draw pass's redo list: normally empty), agent_boxes (boxes), allpairs_fwd, offroad_fwd;
+            # no library kernel (profiles/r2_launches_ncu.csv)
             "gpu_launches": 9 * K, "eager_ms_per_step": eager_ms,
-            "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "raster (64x64 two-pass form: raster_kernel<draw> + raster_finish_kernel, timed together)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "raster_ms_per_launch": raster_ms, "algorithmic_bytes_per_launch": B * A * 12 * RES * RES,
                          "step_frac_of_hbm_roofline": value / world * BYTES_PER_AGENT_STEP / 1e9 / peak},

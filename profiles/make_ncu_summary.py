@@ -5,6 +5,8 @@
 
 `raster`: one launch of raster_kernel (the dominant kernel): DRAM traffic against the algorithmic bytes, warp
 instructions per camera, pipe / issue / stall figures and the executed-instruction footprint.
+`raster2`: the two-pass 64x64 raster (draw pass raster_kernel<..., 1> + raster_finish_kernel, captured back to back):
+the same figures per pass, and their sum against the algorithmic bytes.
 `kernels`: every launch in the report, one row per kernel name (the first launch of each), same figures.
 """
 import csv
@@ -91,6 +93,29 @@ def main():
             s["sass_instructions"] = len(ie)
             s["sass_instructions_executed"] = sum(1 for x in ie if x > 0)
             s["sass_instructions_executed_at_least_half_per_camera"] = sum(1 for x in ie if x >= 0.5 * cameras)
+        json.dump(s, open(out, "w"), indent=1)
+        print(json.dumps({k: s[k] for k in ("kernel", "duration_ms_under_ncu", "traffic_over_algorithmic", "warp_instructions_per_camera")}))
+    elif mode == "raster2":
+        cameras = int(sys.argv[4]) if len(sys.argv) > 4 else 1024 * 64
+        res = int(sys.argv[5]) if len(sys.argv) > 5 else 64
+        draw = [r for r in rows if "raster_kernel" in r["Kernel Name"][1] and "1, 1>" in r["Kernel Name"][1]][0]
+        fin = [r for r in rows if "raster_finish_kernel" in r["Kernel Name"][1]][0]
+        passes = [summarize(draw), summarize(fin)]
+        for q in passes:
+            q["warp_instructions_per_camera"] = q["warp_instructions"] / cameras
+        s = {"kernel": "raster, 64x64 two-pass form: " + " + ".join(q["kernel"].split("(")[0] for q in passes),
+             "duration_ms_under_ncu": sum(q["duration_ms_under_ncu"] for q in passes),
+             "dram_bytes_read": sum(q["dram_bytes_read"] for q in passes), "dram_bytes_write": sum(q["dram_bytes_write"] for q in passes),
+             "warp_instructions": sum(q["warp_instructions"] for q in passes), "passes": passes}
+        s["traffic_bytes_per_launch"] = s["dram_bytes_read"] + s["dram_bytes_write"]
+        s["source"] = (f"ncu --set full --clock-control none -k regex:raster -c 2 python profiles/time_raster.py "
+                       f"({cameras} cameras of {res}x{res}), one launch of each pass")
+        s["report"] = rep + " (scratch, not committed)"
+        s["algorithmic_bytes_per_launch"] = cameras * 12 * res * res
+        s["traffic_over_algorithmic"] = s["traffic_bytes_per_launch"] / s["algorithmic_bytes_per_launch"]
+        s["warp_instructions_per_camera"] = s["warp_instructions"] / cameras
+        s["note"] = ("the traffic above the algorithmic bytes is the hand-over between the passes (bitplanes and lists of "
+                     "border-crossing faces, written by the draw pass and read by the finish pass)")
         json.dump(s, open(out, "w"), indent=1)
         print(json.dumps({k: s[k] for k in ("kernel", "duration_ms_under_ncu", "traffic_over_algorithmic", "warp_instructions_per_camera")}))
     else:

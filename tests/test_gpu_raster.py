@@ -382,11 +382,12 @@ def test_two_pass_and_pattern_table_equal_the_one_pass_walk(monkeypatch):
         state, size, types, present = util.random_scene(m, B, A, rng, spread=spread)
         cam_xy, cam_sc = state[..., :2].copy(), _sincos_torch(state[..., 2])
         imgs = {}
-        for name, env in (("product", {}), ("one pass", {"TDS_RASTER_TWO_PASS": "0"}),
+        for name, env in (("product", {}), ("product in rounds of 23 cameras", {"TDS_RASTER_TWO_PASS_KB": "128"}),
+                          ("one pass", {"TDS_RASTER_TWO_PASS": "0"}),
                           ("no table", {"TDS_RASTER_TWO_PASS": "0", "TDS_RASTER_QUADS": "0"}),
                           ("face walk", {"TDS_RASTER_TWO_PASS": "0", "TDS_RASTER_STRIPS": "0"}),
                           ("general kernel", {"TDS_RASTER_LEAN": "0"})):
-            for k in ("TDS_RASTER_TWO_PASS", "TDS_RASTER_QUADS", "TDS_RASTER_STRIPS", "TDS_RASTER_LEAN"):
+            for k in ("TDS_RASTER_TWO_PASS", "TDS_RASTER_TWO_PASS_KB", "TDS_RASTER_QUADS", "TDS_RASTER_STRIPS", "TDS_RASTER_LEAN"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)

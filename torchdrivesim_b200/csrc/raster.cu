@@ -328,7 +328,9 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
     uint8_t* hand = nullptr;
     if (two_pass) {
         const int64_t per_cam = two_pass_bytes_per_camera(K);
-        round_cams = std::min<int64_t>(ncam, std::max<int64_t>(kTwoPassBytes / per_cam, 1));
+        int64_t budget = kTwoPassBytes;
+        if (const char* e = getenv("TDS_RASTER_TWO_PASS_KB")) budget = std::max<int64_t>(atoll(e), 8) << 10;     // test hook: small rounds
+        round_cams = std::min<int64_t>(ncam, std::max<int64_t>(budget / per_cam, 1));
         hand = two_pass_scratch(round_cams * per_cam, st);
         two_pass = hand != nullptr;
     }

@@ -797,6 +797,20 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                         yi[k] = __float2int_rz(v[k]);
                     }
                     const uint32_t pl = planes_sa + (uint32_t)max(spl, 0) * plane_bytes;
+                    // every vertex inside the image is a pixel of each kept face it belongs to (the outline of a face
+                    // contains its end points), and such a face IS kept: the image lies inside the view quad with a
+                    // margin of more than one pixel (strip_mode).  A vertex outside the image ORs a zero into
+                    // pixel (0, 0): no branch around the reduction.  (The kernels with sliver quads plot further down,
+                    // and only the strips that need it.)
+                    if (!QUADS) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) {
+                            const bool in = spl >= 0 && (POW2 ? (unsigned)(xi[k] | yi[k]) < (unsigned)res
+                                                              : ((unsigned)xi[k] < (unsigned)res && (unsigned)yi[k] < (unsigned)res));
+                            const int x = in ? xi[k] : 0, y = in ? yi[k] : 0;
+                            sred_or(pl + 4u * (uint32_t)((x >> 5) * res + y), in ? 1u << (x & 31) : 0u);
+                        }
+                    }
                     const int sxmin = min(min(min(xi[0], xi[1]), min(xi[2], xi[3])), min(xi[4], xi[5]));
                     const int sxmax = max(max(max(xi[0], xi[1]), max(xi[2], xi[3])), max(xi[4], xi[5]));
                     const int symin = min(min(min(yi[0], yi[1]), min(yi[2], yi[3])), min(yi[4], yi[5]));
@@ -868,16 +882,12 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                         for (int f = 0; f < 4; f++) left |= (((cb >> f) & 7u) != 0u && !((done >> f) & 1u)) ? 1u << f : 0u;
                         slow = slow && left != 0u;
                     }
-                    // every vertex inside the image is a pixel of each kept face it belongs to (the outline of a face
-                    // contains its end points), and such a face IS kept: the image lies inside the view quad with a
-                    // margin of more than one pixel (strip_mode).  A vertex outside the image ORs a zero into
-                    // pixel (0, 0): no branch around the reduction.  Strips whose four faces went on as quads need no
-                    // vertices (road surfaces, batch after batch: the records of a cell are sorted by class).
-                    if (__any_sync(0xffffffffu, spl >= 0 && queued != 15u)) {
+                    // QUADS: the vertices are plotted here, unless the strip's four faces went on as quads (road surfaces,
+                    // batch after batch: the records of a cell are sorted by class)
+                    if (QUADS && __any_sync(0xffffffffu, spl >= 0 && queued != 15u)) {
 #pragma unroll
                         for (int k = 0; k < 6; k++) {
-                            const bool in = spl >= 0 && (POW2 ? (unsigned)(xi[k] | yi[k]) < (unsigned)res
-                                                              : ((unsigned)xi[k] < (unsigned)res && (unsigned)yi[k] < (unsigned)res));
+                            const bool in = spl >= 0 && (unsigned)(xi[k] | yi[k]) < (unsigned)res;
                             const int x = in ? xi[k] : 0, y = in ? yi[k] : 0;
                             sred_or(pl + 4u * (uint32_t)((x >> 5) * res + y), in ? 1u << (x & 31) : 0u);
                         }
