@@ -14,15 +14,21 @@
 //     its view quad's bounding box touches - one contiguous range per grid row;
 //   * ONE pass over the candidates; painter's order is kept in per-class BITPLANES (one bit per pixel and draw
 //     rank, shared memory, red.shared.or), resolved once at the end and expanded through a colour LUT;
-//   * stage 1S - lane-marking STRIPS (4 faces over 6 vertices, one record, one thread): six projections instead
-//     of twelve; every in-image vertex of a kept face is a covered pixel (the outline contains its end points), so
-//     the six vertices are plotted at once and only faces whose bounding box exceeds 2x2 pixels go on to stage 2;
-//   * stage 1F - single faces (road, dynamic primitives): cull + project + truncate, plotted (<= 2x2 pixels) or
-//     queued by kind (short / tall inside the image, crossing the border);
-//   * stage 2 - whenever a queue holds 32 faces: one face per thread, the cv2 rule per image row in closed form
-//     (tds_raster_rows.h), one 64-bit row mask = at most two atomic ORs per row;
+//   * stage 1S - STRIPS (4 faces over 6 vertices, one record, one thread: lane markings and road surfaces): six
+//     projections instead of twelve; every in-image vertex of a kept face is a covered pixel (the outline contains its
+//     end points), so the six vertices are plotted at once and only faces whose bounding box exceeds 2x2 pixels go on;
+//     64x64 tiles: the two quads of a strip whose shape is in the coverage-pattern table (tds_quad_table.h) are queued
+//     as ONE item each, drawn by OR-ing the rows of the pattern;
+//   * stage 1F - single faces (dynamic primitives, faces outside strips): cull + project + truncate, plotted (<= 2x2
+//     pixels) or queued by kind (inside the image, crossing the border);
+//   * stage 2 - whenever a queue holds 32 items: one face per thread, the cv2 rule per image row in closed form
+//     (tds_raster_rows.h), one 64-bit row mask = at most two atomic ORs per row; faces that cross the border: four
+//     lanes per face;
 //   * the planes are stored x-major, which IS the reference's final transpose (cv2.py:61); the image leaves as
-//     streaming 128-bit stores (float32, the reference's dtype) or as uint8 RGB / uint8 draw rank.
+//     streaming 128-bit stores (float32, the reference's dtype) or as uint8 RGB / uint8 draw rank;
+//   * 64x64 tiles run as TWO kernels (PHASE 1 of raster_kernel = draw, raster_finish_kernel = border-crossing faces +
+//     resolve) that hand the bitplanes over in memory: each program fits the 32 KB instruction cache of an SM, the
+//     one-pass program does not and loses a third of its issue slots to instruction fetch.
 // HBM traffic per camera: 12 * res^2 bytes of float32 image out (49 KB at 64x64); the map records are L2 hits.
 #pragma once
 #include <algorithm>
