@@ -371,9 +371,9 @@ def test_strip_stage_equals_face_by_face_walk(monkeypatch):
 def test_two_pass_and_pattern_table_equal_the_one_pass_walk(monkeypatch):
     """The 64x64 path in its product form - draw pass (sliver quads from the coverage-pattern table, triangles inside the
     image as three line walkers) + finish pass (border-crossing faces, resolve) - against the one-pass kernel, against the
-    kernel without the pattern table, and against the face-by-face walk: identical images on thousands of cameras,
-    including a dense junction scene where cameras list more border-crossing faces than the hand-over list holds (those
-    cameras are rendered again by the general kernel)."""
+    kernel without the pattern table, and against the face-by-face walk: identical images on thousands of cameras, also
+    when the hand-over list of a camera holds only 24 border-crossing faces (TDS_RASTER_CLIP_CAP: most cameras then go on
+    the redo list and are rendered by the general kernel behind the two passes)."""
     rng = np.random.default_rng(77)
     for mapname, fov, B, A, spread in (("carla_Town01", 35.0, 32, 64, 30.0), ("carla_Town10HD", 35.0, 8, 64, 25.0),
                                        ("carla_Town02", 60.0, 8, 32, 40.0), ("carla_Town01", 90.0, 4, 48, 60.0),
@@ -383,11 +383,12 @@ def test_two_pass_and_pattern_table_equal_the_one_pass_walk(monkeypatch):
         cam_xy, cam_sc = state[..., :2].copy(), _sincos_torch(state[..., 2])
         imgs = {}
         for name, env in (("product", {}), ("product in rounds of 23 cameras", {"TDS_RASTER_TWO_PASS_KB": "128"}),
+                          ("product with a short face list", {"TDS_RASTER_CLIP_CAP": "24"}),
                           ("one pass", {"TDS_RASTER_TWO_PASS": "0"}),
                           ("no table", {"TDS_RASTER_TWO_PASS": "0", "TDS_RASTER_QUADS": "0"}),
                           ("face walk", {"TDS_RASTER_TWO_PASS": "0", "TDS_RASTER_STRIPS": "0"}),
                           ("general kernel", {"TDS_RASTER_LEAN": "0"})):
-            for k in ("TDS_RASTER_TWO_PASS", "TDS_RASTER_TWO_PASS_KB", "TDS_RASTER_QUADS", "TDS_RASTER_STRIPS", "TDS_RASTER_LEAN"):
+            for k in ("TDS_RASTER_TWO_PASS", "TDS_RASTER_TWO_PASS_KB", "TDS_RASTER_CLIP_CAP", "TDS_RASTER_QUADS", "TDS_RASTER_STRIPS", "TDS_RASTER_LEAN"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)

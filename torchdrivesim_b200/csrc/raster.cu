@@ -284,7 +284,8 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
     a.next_cam = scratch;              // work counter of the first launch
     a.redo = scratch + 4;              // [0] = count, [4 ..] = cameras
     a.cam_list = nullptr;
-    a.cam_begin = 0; a.planes_io = nullptr; a.clip_list = nullptr; a.clip_count = nullptr;
+    a.cam_begin = 0; a.planes_io = nullptr; a.clip_list = nullptr; a.clip_count = nullptr; a.clip_cap = kClipCap;
+    if (const char* e = getenv("TDS_RASTER_CLIP_CAP")) a.clip_cap = std::min(std::max(atoi(e), 0), kClipCap);     // test hook: exercises the redo list
 
     // Threads per camera.  Tiles up to 96x96: a warp per camera, 4 cameras in flight per CTA (at 128x128 only 16 such
     // warps fit an SM: 4 sets of bitplanes per CTA).  Above: a CTA of 4, 8 or 16 independent warps per camera - the

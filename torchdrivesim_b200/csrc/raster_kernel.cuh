@@ -354,6 +354,7 @@ struct RasterArgs {
     uint32_t* planes_io;       // [cameras][KS][res * W32] words
     uint4* clip_list;          // [cameras][kClipCap] faces: x | y << 16 per vertex, plane
     int32_t* clip_count;       // [cameras] listed faces; -1: the camera is on the redo list (the general kernel renders it)
+    int32_t clip_cap;          // faces a camera may list before it goes on the redo list (<= kClipCap, the stride of clip_list)
 };
 constexpr int kClipCap = 192;  // border-crossing faces a camera can list (60 on average at 64x64 / 35 m, 150 at a junction); more: redo
 
@@ -985,12 +986,12 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                                                             (uint32_t)(xy[4] & 0xffff) | ((uint32_t)xy[5] << 16), (uint32_t)plane);
                         if (PHASE == 1 && !ins) {
                             // the finish pass draws the faces that cross the border (nq2 counts them over the whole camera)
-                            if (pos < kClipCap) a.clip_list[(int64_t)(camid - a.cam_begin) * kClipCap + pos] = item;
+                            if (pos < a.clip_cap) a.clip_list[(int64_t)(camid - a.cam_begin) * kClipCap + pos] = item;
                         } else {
                             ssts4(queue_sa + 16u * (uint32_t)pos, item);
                         }
                     }
-                    if (PHASE == 1 && nq2 > kClipCap) redo = true;
+                    if (PHASE == 1 && nq2 > a.clip_cap) redo = true;
                 } else {
                     const unsigned m0 = __ballot_sync(0xffffffffu, kind == kShort), m1 = __ballot_sync(0xffffffffu, kind == kTall),
                                    m2 = __ballot_sync(0xffffffffu, kind == kClipped);
