@@ -349,7 +349,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
             d.a.clip_list = reinterpret_cast<uint4*>(hand + round_cams * KS * 512);
             d.a.clip_count = reinterpret_cast<int32_t*>(hand + round_cams * (KS * 512 + (int64_t)kClipCap * 16));
             // work counters: [0] draw pass, [2] finish pass (the redo list at [4..] spans all rounds)
-            TDS_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), st));
+            if (begin > 0) TDS_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), st));     // round 0: zeroed above
             d.a.next_cam = scratch;
             if (int e = launch_g32_draw(d)) return e;
             LaunchCfg f = d;

@@ -866,11 +866,16 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                             // rungs (v0, v1), (v2, v3) with rails (v0, v2), (v1, v3) - or the other way round
                             int gx = xi[k + 1] - xi[k], gy = yi[k + 1] - yi[k], r1x = xi[k + 2] - xi[k], r1y = yi[k + 2] - yi[k];
                             int r2x = xi[k + 3] - xi[k + 1], r2y = yi[k + 3] - yi[k + 1];
-                            if (!tds::quad_in_table(gx, gy, r1x, r1y, r2x, r2y)) {
-                                int t = gx; gx = r1x; r1x = t; t = gy; gy = r1y; r1y = t;
-                                r2x = xi[k + 3] - xi[k + 2]; r2y = yi[k + 3] - yi[k + 2];
+                            const bool cand = slow && both && allin;
+                            bool tab = tds::quad_in_table(gx, gy, r1x, r1y, r2x, r2y);
+                            if (__any_sync(0xffffffffu, cand && !tab)) {        // rare: the first naming fits almost every quad
+                                if (!tab) {
+                                    int t = gx; gx = r1x; r1x = t; t = gy; gy = r1y; r1y = t;
+                                    r2x = xi[k + 3] - xi[k + 2]; r2y = yi[k + 3] - yi[k + 2];
+                                    tab = tds::quad_in_table(gx, gy, r1x, r1y, r2x, r2y);
+                                }
                             }
-                            const bool covered = slow && both && allin && tds::quad_in_table(gx, gy, r1x, r1y, r2x, r2y);
+                            const bool covered = cand && tab;
                             const bool quad = covered && (((qxmax - qxmin) | (qymax - qymin)) > 1);
                             done |= covered ? 3u << k : 0u;
                             queued |= quad ? 3u << k : 0u;
@@ -894,9 +899,10 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                     if (QUADS && __any_sync(0xffffffffu, spl >= 0 && queued != 15u)) {
 #pragma unroll
                         for (int k = 0; k < 6; k++) {
-                            const bool in = spl >= 0 && (unsigned)(xi[k] | yi[k]) < (unsigned)res;
-                            const int x = in ? xi[k] : 0, y = in ? yi[k] : 0;
-                            sred_or(pl + 4u * (uint32_t)((x >> 5) * res + y), in ? 1u << (x & 31) : 0u);
+                            // 64x64: the address is formed from the low six bits (always inside the plane), the bit is
+                            // zero for a vertex outside the image
+                            const bool in = spl >= 0 && (unsigned)(xi[k] | yi[k]) < 64u;
+                            sred_or(pl + (((uint32_t)xi[k] & 32u) << 3) + (((uint32_t)yi[k] & 63u) << 2), in ? 1u << (xi[k] & 31) : 0u);
                         }
                     }
                     // the others wait in the strip queue until 8 of them make a full warp of faces
