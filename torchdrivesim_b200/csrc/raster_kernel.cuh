@@ -1158,12 +1158,14 @@ __global__ void __launch_bounds__(128, TDS_FINISH_MINB) raster_finish_kernel(Ras
 #pragma unroll 1
             for (int i0 = 0; i0 < count; i0 += 8) {
                 const int take = min(count - i0, 8);
-                const unsigned lanes = take >= 8 ? 0xffffffffu : (1u << (4 * take)) - 1u;
                 uint4 q_after = q0;
                 if (i0 + 8 < count) q_after = faces[i0 + 8 + (lane >> 2)];          // the next round's faces, ahead of the draw
-                if ((lane >> 2) < take)
-                    draw_clipped_part<RES>(planes_sa + q0.w * plane_bytes, RES, rcp_sa, (int16_t)(q0.x & 0xffff), (int32_t)q0.x >> 16,
-                                           (int16_t)(q0.y & 0xffff), (int32_t)q0.y >> 16, (int16_t)(q0.z & 0xffff), (int32_t)q0.z >> 16, lane & 3, lanes);
+                // every lane takes part (full-mask shuffles: one instruction each); the lanes past the last face draw a face that
+                // lies off the image - all its edges are rejected by clipLine, its bounding box misses the image
+                if ((lane >> 2) >= take) q0 = make_uint4(0xff9cff9cu, 0xff9cff9cu, 0xff9cff9cu, 0u);          // (-100, -100) x 3
+                draw_clipped_part<RES>(planes_sa + q0.w * plane_bytes, RES, rcp_sa, (int16_t)(q0.x & 0xffff), (int32_t)q0.x >> 16,
+                                       (int16_t)(q0.y & 0xffff), (int32_t)q0.y >> 16, (int16_t)(q0.z & 0xffff), (int32_t)q0.z >> 16, lane & 3,
+                                       0xffffffffu);
                 q0 = q_after;
                 __syncwarp();
             }
