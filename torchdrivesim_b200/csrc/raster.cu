@@ -320,10 +320,10 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
         if (G == 128) return launch_g128(cfg, f32, is_lean);
         return launch_g256(cfg, G, f32, is_lean);
     };
-    // Two passes for the 64x64 LEAN kernels: draw (everything but the border-crossing faces) -> finish (those faces +
+    // Two passes for the 64x64 warp-per-camera kernels (LEAN or general, up to 7 active classes): draw (everything but the border-crossing faces) -> finish (those faces +
     // resolve), handing bitplanes and face lists over in library-owned memory.  Each program fits the instruction caches
     // where the one-pass kernel does not.  TDS_RASTER_TWO_PASS=0 forces one pass.
-    bool two_pass = lean && G == 32 && g32_two_pass_available(c);
+    bool two_pass = G == 32 && g32_two_pass_available(c);
     if (const char* e = getenv("TDS_RASTER_TWO_PASS")) two_pass = two_pass && atoi(e) != 0;
     int64_t round_cams = 0;
     uint8_t* hand = nullptr;
@@ -351,7 +351,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
             // work counters: [0] draw pass, [2] finish pass (the redo list at [4..] spans all rounds)
             if (begin > 0) TDS_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), st));     // round 0: zeroed above
             d.a.next_cam = scratch;
-            if (int e = launch_g32_draw(d)) return e;
+            if (int e = launch_g32_draw(d, lean)) return e;
             LaunchCfg f = d;
             f.a.next_cam = scratch + 2;
             f.ev_start = f.ev_stop = nullptr;
@@ -361,7 +361,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
     } else {
         if (int e = go(c, lean)) return e;
     }
-    if (lean) {
+    if (lean || two_pass) {
         // the cameras on the list (normally none: every CTA of this launch leaves at once)
         LaunchCfg r = c;
         r.a.next_cam = scratch + 1;

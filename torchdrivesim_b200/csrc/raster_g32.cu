@@ -26,9 +26,14 @@ int launch_g32(const LaunchCfg& c, bool f32, bool lean) {
 // ---- two-pass form of the 64x64 LEAN kernels (static shared memory, NS = 3)
 bool g32_two_pass_available(const LaunchCfg& c) { return c.res == 64 && c.K <= 7; }
 
-int launch_g32_draw(const LaunchCfg& c) {
-    if (c.K <= 5) return launch_variant(raster_kernel<32, 64, 3, true, 5, true, true, 1>, c, 4, 128, true);
-    return launch_variant(raster_kernel<32, 64, 3, true, 7, true, true, 1>, c, 4, 128, true);
+int launch_g32_draw(const LaunchCfg& c, bool lean) {
+    if (lean) {
+        if (c.K <= 5) return launch_variant(raster_kernel<32, 64, 3, true, 5, true, true, 1>, c, 4, 128, true);
+        return launch_variant(raster_kernel<32, 64, 3, true, 7, true, true, 1>, c, 4, 128, true);
+    }
+    // scenes with per-camera triangles (goal-waypoint discs) or per-camera agent classes (custom colours)
+    if (c.K <= 5) return launch_variant(raster_kernel<32, 64, 3, true, 5, true, false, 1>, c, 4, 128, true);
+    return launch_variant(raster_kernel<32, 64, 3, true, 7, true, false, 1>, c, 4, 128, true);
 }
 
 int launch_g32_finish(const LaunchCfg& c, bool f32) {

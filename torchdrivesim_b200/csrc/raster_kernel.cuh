@@ -1072,7 +1072,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         }
         group_sync<G>();
         bool any_redo = false;
-        if (LEAN) {
+        if (LEAN || PHASE == 1) {
             // a camera this kernel could not finish exactly goes on the list of the general kernel (which overwrites its image)
             any_redo = G == 32 ? __any_sync(0xffffffffu, redo) : (__syncthreads_or(redo) != 0);
             if (any_redo && tid == 0) a.redo[4 + atomicAdd(a.redo, 1)] = camid;
@@ -1221,7 +1221,7 @@ int launch_finish(Kernel kernel, const LaunchCfg& c) {
 
 // two-pass form (64x64 tiles, LEAN, K <= 7): launch_g32_draw = pass 1, launch_g32_finish = pass 2 (raster_g32.cu)
 bool g32_two_pass_available(const LaunchCfg& c);
-int launch_g32_draw(const LaunchCfg& c);
+int launch_g32_draw(const LaunchCfg& c, bool lean);
 int launch_g32_finish(const LaunchCfg& c, bool f32);
 // bytes per camera of the hand-over buffers: bitplanes, face list, face count
 inline int64_t two_pass_bytes_per_camera(int K) { return (int64_t)(K <= 5 ? 5 : 7) * 512 + (int64_t)kClipCap * 16 + 4; }
