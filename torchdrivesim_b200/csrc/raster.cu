@@ -284,7 +284,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
     a.next_cam = scratch;              // work counter of the first launch
     a.redo = scratch + 4;              // [0] = count, [4 ..] = cameras
     a.cam_list = nullptr;
-    a.cam_begin = 0; a.planes_io = nullptr; a.clip_list = nullptr; a.clip_count = nullptr; a.clip_cap = kClipCap;
+    a.cam_begin = 0; a.planes_io = nullptr; a.plane_stride = 0; a.clip_list = nullptr; a.clip_count = nullptr; a.clip_cap = kClipCap;
     if (const char* e = getenv("TDS_RASTER_CLIP_CAP")) a.clip_cap = std::min(std::max(atoi(e), 0), kClipCap);     // test hook: exercises the redo list
 
     // Threads per camera.  Tiles up to 96x96: a warp per camera, 4 cameras in flight per CTA (at 128x128 only 16 such
@@ -320,7 +320,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
         if (G == 128) return launch_g128(cfg, f32, is_lean);
         return launch_g256(cfg, G, f32, is_lean);
     };
-    // Two passes for the 64x64 warp-per-camera kernels (LEAN or general, up to 7 active classes): draw (everything but the border-crossing faces) -> finish (those faces +
+    // Two passes for the 64x64 warp-per-camera kernels (LEAN or general, up to 15 active classes): draw (everything but the border-crossing faces) -> finish (those faces +
     // resolve), handing bitplanes and face lists over in library-owned memory.  Each program fits the instruction caches
     // where the one-pass kernel does not.  TDS_RASTER_TWO_PASS=0 forces one pass.
     bool two_pass = G == 32 && g32_two_pass_available(c);
@@ -336,7 +336,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
         two_pass = hand != nullptr;
     }
     if (two_pass) {
-        const int KS = K <= 5 ? 5 : 7;
+        const int KS = two_pass_planes(K);
         if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);   // the timed region spans both passes (and all rounds)
         for (int64_t begin = 0; begin < ncam; begin += round_cams) {
             const int64_t end = std::min<int64_t>(ncam, begin + round_cams);
@@ -346,6 +346,7 @@ extern "C" int tds_raster_birdview_fmt(const tds_map_t* const* maps, int32_t n_m
             d.a.ncam = (int32_t)end;
             d.a.cam_begin = (int32_t)begin;
             d.a.planes_io = reinterpret_cast<uint32_t*>(hand);
+            d.a.plane_stride = KS * 32;
             d.a.clip_list = reinterpret_cast<uint4*>(hand + round_cams * KS * 512);
             d.a.clip_count = reinterpret_cast<int32_t*>(hand + round_cams * (KS * 512 + (int64_t)kClipCap * 16));
             // work counters: [0] draw pass, [2] finish pass (the redo list at [4..] spans all rounds)

@@ -351,7 +351,8 @@ struct RasterArgs {
     // draws the listed faces and resolves.  Each pass is a smaller program than the two together: instruction fetch, not
     // instruction count, limits the one-pass kernel.  Indexed by camera - cam_begin.
     int32_t cam_begin;
-    uint32_t* planes_io;       // [cameras][KS][res * W32] words
+    uint32_t* planes_io;       // [cameras][plane_stride] uint4: the K bitplanes of a camera
+    int32_t plane_stride;      // uint4 per camera in planes_io (>= K * res * W32 / 4)
     uint4* clip_list;          // [cameras][kClipCap] faces: x | y << 16 per vertex, plane
     int32_t* clip_count;       // [cameras] listed faces; -1: the camera is on the redo list (the general kernel renders it)
     int32_t clip_cap;          // faces a camera may list before it goes on the redo list (<= kClipCap, the stride of clip_list)
@@ -1082,7 +1083,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
         // ---- resolve painter's order and expand through the colour LUT (or hand the bitplanes to the finish kernel)
         if (PHASE == 1) {
             const int li = camid - a.cam_begin;
-            uint4* po = reinterpret_cast<uint4*>(a.planes_io) + (int64_t)li * (KS * plane_words / 4);
+            uint4* po = reinterpret_cast<uint4*>(a.planes_io) + (int64_t)li * a.plane_stride;
 #pragma unroll 1
             for (int i = tid; i < K * plane_words / 4; i += G) po[i] = slds4(planes_sa + 16u * (uint32_t)i);
             if (tid == 0) a.clip_count[li] = any_redo ? -1 : nq2;   // -1: the general kernel renders this camera
@@ -1110,7 +1111,8 @@ __global__ void __launch_bounds__(128, TDS_FINISH_MINB) raster_finish_kernel(Ras
     constexpr int RES = 64, W32 = 2, PLANE_WORDS = RES * W32;
     __shared__ float4 s_lut[TDS_MAX_CLASSES + 1];
     __shared__ __align__(16) uint32_t s_rcp[RES + 4];
-    __shared__ __align__(16) uint32_t s_planes[4][2][KS * PLANE_WORDS];
+    constexpr int NB = KS <= 7 ? 2 : 1;          // double buffer while it fits the 48 KB of static shared memory
+    __shared__ __align__(16) uint32_t s_planes[4][NB][KS * PLANE_WORDS];
     const int K = pal.n_classes;
     for (int i = threadIdx.x; i <= K; i += blockDim.x) {
         const float* c = pal.rgb[i == 0 ? 0 : pal.order[i - 1] + 1];
@@ -1119,12 +1121,21 @@ __global__ void __launch_bounds__(128, TDS_FINISH_MINB) raster_finish_kernel(Ras
     for (int i = threadIdx.x; i <= RES; i += blockDim.x) s_rcp[i] = g_rcp.v[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint32_t buf_sa[2] = {smem_addr(s_planes[threadIdx.x >> 5][0]), smem_addr(s_planes[threadIdx.x >> 5][1])};
+    const uint32_t buf_sa[2] = {smem_addr(s_planes[threadIdx.x >> 5][0]), smem_addr(s_planes[threadIdx.x >> 5][NB - 1])};
     const uint32_t rcp_sa = smem_addr(s_rcp), lut_sa = smem_addr(s_lut);
     constexpr uint32_t plane_bytes = 4u * PLANE_WORDS;
     const int n_local = a.ncam - a.cam_begin;
 
-    // request camera li: planes -> buffer b (one commit group), count and first faces -> registers
+    // planes of camera li -> buffer b (one commit group)
+    auto request_planes = [&](int li, int b) {
+        if (li < n_local) {
+            const uint4* pi = reinterpret_cast<const uint4*>(a.planes_io) + (int64_t)li * a.plane_stride;
+#pragma unroll 1
+            for (int i = lane; i < K * PLANE_WORDS / 4; i += 32) cp_async16(buf_sa[b] + 16u * (uint32_t)i, pi + i);
+        }
+        cp_async_commit();
+    };
+    // next camera of this warp: its face count and first faces -> registers (and, with two buffers, its planes -> buffer b)
     auto fetch = [&](int& li, int& count, uint4& q0, int b) {
         li = 0;
         if (lane == 0) li = atomicAdd(a.next_cam, 1);
@@ -1132,13 +1143,10 @@ __global__ void __launch_bounds__(128, TDS_FINISH_MINB) raster_finish_kernel(Ras
         count = -1;
         q0 = make_uint4(0u, 0u, 0u, 0u);
         if (li < n_local) {
-            const uint4* pi = reinterpret_cast<const uint4*>(a.planes_io) + (int64_t)li * (KS * PLANE_WORDS / 4);
-#pragma unroll 1
-            for (int i = lane; i < K * PLANE_WORDS / 4; i += 32) cp_async16(buf_sa[b] + 16u * (uint32_t)i, pi + i);
             count = a.clip_count[li];
             q0 = a.clip_list[(int64_t)li * kClipCap + (lane >> 2)];     // slots past the count hold stale data: not used
         }
-        cp_async_commit();
+        if (NB == 2) request_planes(li, b);
     };
 
     int li, count, b = 0;
@@ -1147,13 +1155,18 @@ __global__ void __launch_bounds__(128, TDS_FINISH_MINB) raster_finish_kernel(Ras
     while (li < n_local) {
         int li_next, count_next;
         uint4 q0_next;
-        __syncwarp();                               // the resolve of the camera before last has read the other buffer
+        __syncwarp();                               // the resolve of the camera before (last) has read the buffer that is filled next
         fetch(li_next, count_next, q0_next, b ^ 1);
-        cp_async_wait<1>();                         // this camera's planes have landed (the next one's may be in flight)
+        if (NB == 2) {
+            cp_async_wait<1>();                     // this camera's planes have landed (the next one's may be in flight)
+        } else {
+            request_planes(li, 0);
+            cp_async_wait<0>();
+        }
         __syncwarp();
         if (count >= 0) {                           // -1: on the redo list, the general kernel renders this camera
             const int camid = li + a.cam_begin;
-            const uint32_t planes_sa = buf_sa[b];
+            const uint32_t planes_sa = buf_sa[NB == 2 ? b : 0];
             const uint4* faces = a.clip_list + (int64_t)li * kClipCap;
 #pragma unroll 1
             for (int i0 = 0; i0 < count; i0 += 8) {
@@ -1219,12 +1232,13 @@ int launch_finish(Kernel kernel, const LaunchCfg& c) {
     return TDS_OK;
 }
 
-// two-pass form (64x64 tiles, LEAN, K <= 7): launch_g32_draw = pass 1, launch_g32_finish = pass 2 (raster_g32.cu)
+// two-pass form (64x64 tiles, K <= 15): launch_g32_draw = pass 1, launch_g32_finish = pass 2 (raster_g32.cu)
 bool g32_two_pass_available(const LaunchCfg& c);
 int launch_g32_draw(const LaunchCfg& c, bool lean);
 int launch_g32_finish(const LaunchCfg& c, bool f32);
 // bytes per camera of the hand-over buffers: bitplanes, face list, face count
-inline int64_t two_pass_bytes_per_camera(int K) { return (int64_t)(K <= 5 ? 5 : 7) * 512 + (int64_t)kClipCap * 16 + 4; }
+inline int two_pass_planes(int K) { return K <= 5 ? 5 : (K <= 7 ? 7 : K); }      // planes stored per camera
+inline int64_t two_pass_bytes_per_camera(int K) { return (int64_t)two_pass_planes(K) * 512 + (int64_t)kClipCap * 16 + 4; }
 
 // defined in raster_g32.cu / raster_g128.cu / raster_g256.cu: picks the instantiation for (G, res, K, format, lean)
 int launch_g32(const LaunchCfg& c, bool f32, bool lean);
