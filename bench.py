@@ -456,6 +456,8 @@ def run_ours(args):
                 nj = json.load(open(ncu_path))
                 if nj.get("algorithmic_bytes_per_launch") == B * A * 12 * RES * RES:
                     traffic, traffic_src = nj["traffic_bytes_per_launch"], f"profiles/{ncu_name} (dram__bytes_read+write.sum)"
+                    if nj.get("passes"):
+                        traffic_src += "; both raster passes, incl. the bitplanes and face lists handed from the draw to the finish pass"
                     break
         cpu_val, cpu_procs = float("nan"), 0
         if not args.kernels_only:
