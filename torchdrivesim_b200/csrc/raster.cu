@@ -146,8 +146,8 @@ static int raster_scratch(int64_t ncam, cudaStream_t st, int32_t** out) {
         int32_t* p = nullptr;
         const int64_t cap = std::max<int64_t>(ncam, 4096);
         TDS_CUDA_OK(cudaMalloc(&p, (size_t)(8 + cap) * sizeof(int32_t)));
-        // the old buffer may still be in use by work already enqueued: it is released when that work has drained
-        if (hit->ptr) { cudaStreamSynchronize(st); cudaFree(hit->ptr); }
+        // the old buffer is NOT released: work already enqueued, or a CUDA graph captured earlier on this stream, may still
+        // refer to it (it stays valid for them; new calls use the larger one)
         hit->ptr = p;
         hit->cap = cap;
     }
@@ -176,7 +176,7 @@ static uint8_t* two_pass_scratch(int64_t bytes, cudaStream_t st) {
         if (cs != cudaStreamCaptureStatusNone) return nullptr;
         uint8_t* p = nullptr;
         if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        if (hit->ptr) { cudaStreamSynchronize(st); cudaFree(hit->ptr); }
+        // the old buffer is kept (see raster_scratch): a graph captured with it stays valid
         hit->ptr = p;
         hit->cap = bytes;
     }
