@@ -1055,6 +1055,9 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
                 }
             }
             // faces that cross the border: 4 lanes per face (its three outline edges and its fill), 8 faces per round
+#ifdef TDS_EXP_NOCLIP
+            if (PHASE != 1) nq2 = 0;                   // experiment: border-crossing faces are not drawn (wrong images)
+#endif
             while (PHASE != 1 && (nq2 >= 8 || (drain && nq2 > 0))) {
                 const int take = min(nq2, 8);
                 const unsigned lanes = take >= 8 ? 0xffffffffu : (1u << (4 * take)) - 1u;
@@ -1088,6 +1091,9 @@ __global__ void __launch_bounds__(G == 32 ? 128 : G, G <= 128 ? TDS_RASTER_MINB 
             for (int i = tid; i < K * plane_words / 4; i += G) po[i] = slds4(planes_sa + 16u * (uint32_t)i);
             if (tid == 0) a.clip_count[li] = any_redo ? -1 : nq2;   // -1: the general kernel renders this camera
         } else {
+#ifdef TDS_EXP_NORESOLVE
+            if (a.ncam < 0)                            // experiment: the resolve is compiled in but never executed (no images)
+#endif
             resolve_camera<G, RES, NS, F32>(a, camid, tid, res, W32, K, planes_sa, plane_bytes, smem_addr(s_lut));
         }
     }
